@@ -1,0 +1,199 @@
+/* mdvc.h -- C-ABI of the B200-native voxel hot path of MDVContainment.
+ *
+ * The reference (BartBruininks/mdvcontainment v1.1.1) has no FFI of its own: its hot path is
+ * reached through Python import-level seam functions.  Every entry point
+ * below names the reference function(s) it replaces (file:line relative to the reference
+ * root).  INTEGRATION.md shows the ctypes binding a maintainer would add on the reference side.
+ *
+ * Conventions
+ *  - plain pointers and sizes only; every pointer is a DEVICE pointer unless the name ends in
+ *    `_host`; the caller owns every buffer, the library allocates nothing persistent;
+ *  - every function takes a `cudaStream_t` (passed as void*), enqueues its kernels on it and
+ *    returns without synchronising unless documented otherwise;
+ *  - return value: MDVC_OK (0), a negative MDVC_ERR_* for bad arguments / CUDA failures, or a
+ *    positive MDVC_OVERFLOW_* bit set when a caller-provided capacity was too small (retry
+ *    with the sizes reported in the header block); nothing is ever silently truncated;
+ *  - grids are C-order [X][Y][Z], Z fastest (the reference's NumPy layout).  The occupancy grid
+ *    is bit-packed: row (x,y) is `pitch` uint32 words, bit k of word w is voxel z = 32*w + k;
+ *    `pitch` = mdvc_row_pitch_words(Z) (a multiple of 4 words = 16 B); bits with z >= Z and the
+ *    pad words are zero on input and on output of every function.
+ */
+#ifndef MDVC_H
+#define MDVC_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MDVC_OK 0
+#define MDVC_ERR_BADARG (-1)
+#define MDVC_ERR_CUDA (-2)
+#define MDVC_ERR_WORKSPACE (-3)
+/* capacity overflow bits (also found in mdvc_frame_header.flags) */
+#define MDVC_OVERFLOW_RUNS 1
+#define MDVC_OVERFLOW_CONTACTS 2
+#define MDVC_OVERFLOW_BRIDGES 4
+#define MDVC_OVERFLOW_LABELS 8
+#define MDVC_OVERFLOW_ROWS 16
+
+int mdvc_version(void);
+/* last CUDA error string seen by the calling thread's most recent failing call */
+const char *mdvc_last_error(void);
+int mdvc_row_pitch_words(int Z);
+
+/* ---------------------------------------------------------------------------------------
+ * T1  bool grid <-> bit grid        (reference type: dense bool ndarray,
+ *     atomgroup_to_voxels.py:195-197; containment_main.py:460)
+ * ------------------------------------------------------------------------------------- */
+int mdvc_pack_bool(const uint8_t *grid, int X, int Y, int Z, uint32_t *bits, int pitch, void *stream);
+int mdvc_unpack_bool(const uint32_t *bits, int X, int Y, int Z, int pitch, uint8_t *grid, void *stream);
+/* number of True voxels (device popcount); *count_dev is a device int64 */
+int mdvc_popcount(const uint32_t *bits, int X, int Y, int Z, int pitch, unsigned long long *count_dev, void *stream);
+
+/* ---------------------------------------------------------------------------------------
+ * A1  binning        replaces _voxelate_atomgroup + the scatter of create_voxels
+ *     (atomgroup_to_voxels.py:131-142, 192-197).
+ *  pos[n][3] float32 (A); T = inv(box) @ nbox, invT = inv(T) (row-major float64[9], computed on
+ *  the host with the reference's NumPy expressions); nbox int64[9] row-major.
+ *  Optional outputs (NULL to skip): occ_bits (atomicOr into the bit grid, NOT cleared here),
+ *  vox_out[n][3] int32 wrapped voxel coordinates, pos_out[n][3] float32 rewritten positions
+ *  (may alias pos).  T, invT, nbox are HOST pointers (copied by value into the launch).
+ * ------------------------------------------------------------------------------------- */
+int mdvc_bin_atoms(const float *pos, long long n, const double *T_host, const double *invT_host,
+                   const long long *nbox_host, uint32_t *occ_bits, int pitch,
+                   int32_t *vox_out, float *pos_out, void *stream);
+
+/* ---------------------------------------------------------------------------------------
+ * A3/A4  morphology  replaces dilate_voxels / erode_voxels / morph_voxels / close_voxels
+ *     (atomgroup_to_voxels.py:242-308): periodic 3x3x3 dilation 'd' / erosion 'e', applied left
+ *     to right.  bits_in is not modified; result in bits_out; tmp is a scratch bit grid of the
+ *     same size (needed when strlen(ops) > 1; may be NULL otherwise).  Unknown op character ->
+ *     MDVC_ERR_BADARG (the host layer raises the reference's ValueError, :303).
+ * ------------------------------------------------------------------------------------- */
+int mdvc_morph(const uint32_t *bits_in, uint32_t *bits_out, uint32_t *tmp, int X, int Y, int Z,
+               int pitch, const char *ops, void *stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Frame pipeline on the bit grid (the fast path):  A5 labels (label.py:4-19), A7 contacts
+ * (find_label_contacts.pyx:5-77), A6 bridges (find_bridges.pyx:4-89), the periodic-component
+ * numbering of rank_logic.py:112-134 / graph_logic.py:101-162, A8 relabel +
+ * counts (label.py:21-38, containment_main.py:510-512).
+ *
+ * Work happens on maximal z-runs of equal voxels (both polarities at once); only
+ * mdvc_frame_expand touches the dense int32 grids, exactly once.
+ * ------------------------------------------------------------------------------------- */
+typedef struct mdvc_frame_caps {
+    uint32_t max_runs;       /* capacity of the per-run tables                         */
+    uint32_t max_labels;     /* capacity of the per-label tables (n_true + n_false + 1)  */
+    uint32_t contact_slots;  /* hash-set slots for contact pairs  (power of two)       */
+    uint32_t bridge_slots;   /* hash-set slots for bridge records (power of two)       */
+} mdvc_frame_caps;
+
+/* 64 x uint32, first words of the workspace; fetched with mdvc_frame_read_header */
+typedef struct mdvc_frame_header {
+    uint32_t total_runs;     /* runs found (may exceed max_runs -> MDVC_OVERFLOW_RUNS)  */
+    uint32_t n_true;         /* number of positive labels                               */
+    uint32_t n_false;        /* number of negative labels                               */
+    uint32_t flags;          /* MDVC_OVERFLOW_* bits                                    */
+    uint32_t n_contacts;     /* unique contact rows                                     */
+    uint32_t n_bridges;      /* unique bridge rows                                      */
+    uint32_t n_comp_pos;     /* periodic components of True voxels                      */
+    uint32_t n_comp_neg;     /* periodic components of False voxels                     */
+    uint32_t reserved[56];
+} mdvc_frame_header;
+
+size_t mdvc_frame_workspace_bytes(int X, int Y, int Z, const mdvc_frame_caps *caps);
+
+/* Stage 1: runs -> union-find -> canonical label per run (+ label volumes).
+ * label numbering = rank of the component's first voxel in C-order, per polarity (scipy's). */
+int mdvc_frame_label(const uint32_t *bits, int X, int Y, int Z, int pitch,
+                     void *workspace, size_t workspace_bytes, const mdvc_frame_caps *caps, void *stream);
+/* Stage 2: unique contact pairs and bridge records, sorted like the reference's rows.
+ * periodic = 0 skips bridges (the reference's slab=True path, containment_main.py:67-69). */
+int mdvc_frame_pairs(const uint32_t *bits, int X, int Y, int Z, int pitch,
+                     void *workspace, size_t workspace_bytes, const mdvc_frame_caps *caps,
+                     int periodic, void *stream);
+/* Stage 3: periodic components on the device: union labels joined by same-sign bridges, number
+ * them with the reference's rule, build label->component LUT, per-component voxel counts.
+ * periodic = 0: every label is its own component (component id = label id). */
+int mdvc_frame_components(int X, int Y, int Z, void *workspace, size_t workspace_bytes,
+                          const mdvc_frame_caps *caps, int periodic, void *stream);
+/* Stage 3': alternatively install a host-computed LUT (lut_host[n_false + n_true + 1], index =
+ * label + n_false; the shape of create_components_grid's dict, label.py:21-38). */
+int mdvc_frame_set_lut(int X, int Y, int Z, void *workspace, size_t workspace_bytes,
+                       const mdvc_frame_caps *caps, const int32_t *lut_dev, uint32_t n_entries, void *stream);
+/* Stage 4: write the dense int32 grids, each voxel exactly once.  Either output may be NULL. */
+int mdvc_frame_expand(const uint32_t *bits, int X, int Y, int Z, int pitch,
+                      void *workspace, size_t workspace_bytes, const mdvc_frame_caps *caps,
+                      int32_t *labels_out, int32_t *components_out, void *stream);
+
+/* Synchronises the stream and copies the header to the host. Returns flags as MDVC_OVERFLOW_*. */
+int mdvc_frame_read_header(const void *workspace, mdvc_frame_header *header_host, void *stream);
+/* Device pointers into the workspace (valid after the producing stage; sizes from the header):
+ * contacts int32[n_contacts][2], bridges int32[n_bridges][5], label volumes int64[n_false+n_true+1]
+ * (index = label + n_false), LUT int32[same], component counts int64[n_comp_neg+n_comp_pos+1]
+ * (index = component + n_comp_neg). */
+const int32_t *mdvc_frame_contacts_ptr(const void *workspace, int X, int Y, int Z, const mdvc_frame_caps *caps);
+const int32_t *mdvc_frame_bridges_ptr(const void *workspace, int X, int Y, int Z, const mdvc_frame_caps *caps);
+const long long *mdvc_frame_label_volumes_ptr(const void *workspace, int X, int Y, int Z, const mdvc_frame_caps *caps);
+const int32_t *mdvc_frame_lut_ptr(const void *workspace, int X, int Y, int Z, const mdvc_frame_caps *caps);
+const long long *mdvc_frame_component_counts_ptr(const void *workspace, int X, int Y, int Z, const mdvc_frame_caps *caps);
+
+/* ---------------------------------------------------------------------------------------
+ * Seam-level functions on dense int32 grids (one-to-one with the reference's functions, for
+ * user-supplied label grids; also the independent cross-check of the run-based path).
+ * ------------------------------------------------------------------------------------- */
+/* find_label_contacts (find_label_contacts.pyx:5-77).  set_slots: power-of-two scratch of uint64;
+ * rows_out int32[rows_cap][2]; *n_rows_dev (device uint32) receives the unique count. */
+int mdvc_grid_contacts(const int32_t *labels, int X, int Y, int Z, unsigned long long *set_slots,
+                       uint32_t n_slots, int32_t *rows_out, uint32_t rows_cap, uint32_t *n_rows_dev,
+                       uint32_t *flags_dev, void *stream);
+/* find_bridges (find_bridges.pyx:4-89); rows_out int32[rows_cap][5]. */
+int mdvc_grid_bridges(const int32_t *labels, int X, int Y, int Z, unsigned long long *set_slots,
+                      uint32_t n_slots, int32_t *rows_out, uint32_t rows_cap, uint32_t *n_rows_dev,
+                      uint32_t *flags_dev, void *stream);
+/* create_components_grid (label.py:21-38): out = lut[label - lut_lo] (0 where outside the LUT). */
+int mdvc_grid_relabel(const int32_t *labels, long long n, const int32_t *lut, int lut_lo, int lut_n,
+                      int32_t *out, void *stream);
+/* np.unique(grid, return_counts=True) for values in [lo, lo+n_bins) (containment_main.py:510-512):
+ * counts[v - lo] += 1.  counts is NOT cleared here. */
+int mdvc_grid_count(const int32_t *grid, long long n, int lo, int n_bins, unsigned long long *counts,
+                    void *stream);
+/* np.isin(components_grid, nodes) + np.where (containment_main.py:360-378): member[v - lo] != 0
+ * selects value v.  Writes the C-ordered voxel coordinates int64[M][3] to pos_out (capacity
+ * pos_cap rows), M to *n_out_dev (device uint64).  block_counts: scratch of
+ * mdvc_grid_select_scratch_words(n) uint32.  mask_out (uint8[n], optional) gets the boolean mask. */
+size_t mdvc_grid_select_scratch_words(long long n);
+int mdvc_grid_select(const int32_t *grid, int X, int Y, int Z, const uint8_t *member, int lo, int n_member,
+                     uint32_t *scratch, long long *pos_out, unsigned long long pos_cap,
+                     unsigned long long *n_out_dev, uint8_t *mask_out, void *stream);
+
+/* ---------------------------------------------------------------------------------------
+ * A2/A9  voxel <-> atom mapping   replaces create_efficient_mapping_cy / voxels2atomgroup_cy
+ *     (atoms_voxels_mapping.pyx:17-91) and the per-node loop of set_betafactors
+ *     (mda_containment.py:191-203).  Exact multimap keyed by the voxel's linear index (the
+ *     reference's hash collisions, SURVEY.md Appendix B1, are deliberately not reproduced).
+ * ------------------------------------------------------------------------------------- */
+/* component id of the voxel each atom sits in: out[i] = grid[vox[i]] (float64, the betafactor) */
+int mdvc_atom_components(const int32_t *vox, long long n, const int32_t *grid, int X, int Y, int Z,
+                         double *out, void *stream);
+/* CSR build: atoms stably sorted by voxel linear index.  order_out uint32[n] = positions-in-group
+ * in (voxel C-order, atom order); keys_out uint64[n] = sorted linear indices.
+ * scratch: mdvc_atom_sort_scratch_bytes(n) bytes. */
+size_t mdvc_atom_sort_scratch_bytes(long long n);
+int mdvc_atom_sort_by_voxel(const int32_t *vox, long long n, int X, int Y, int Z, uint32_t *order_out,
+                            unsigned long long *keys_out, void *scratch, void *stream);
+/* gather: atoms (in CSR order) whose voxel value is selected by member[] -> atom_ix[order] int64.
+ * out capacity n. *n_out_dev device uint64. scratch as for mdvc_grid_select on n items. */
+int mdvc_atom_select(const uint32_t *order, const unsigned long long *keys, long long n,
+                     const int32_t *grid, const uint8_t *member, int lo, int n_member,
+                     const long long *atom_ix, uint32_t *scratch, long long *out,
+                     unsigned long long *n_out_dev, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MDVC_H */

@@ -1,0 +1,255 @@
+// bits.cu -- bit-packed occupancy grid: pack/unpack, atom binning, periodic morphology.
+//
+// Reference behaviour restated (file:line relative to /root/reference/mdvcontainment/):
+//   binning      atomgroup_to_voxels.py:131-142, 192-197
+//   morphology   atomgroup_to_voxels.py:32-92, 242-308
+#include "common.cuh"
+
+#include <string.h>
+
+// ------------------------------------------------------------------------------------------
+// error state
+// ------------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+void mdvc_set_error(const char *where, cudaError_t e) {
+    snprintf(g_err, sizeof(g_err), "%s: %s", where, cudaGetErrorString(e));
+}
+void mdvc_set_error_msg(const char *msg) { snprintf(g_err, sizeof(g_err), "%s", msg); }
+
+extern "C" int mdvc_version(void) { return 100; }
+extern "C" const char *mdvc_last_error(void) { return g_err; }
+extern "C" int mdvc_row_pitch_words(int Z) { return ((mdvc_words(Z) + 3) / 4) * 4; }
+
+// ------------------------------------------------------------------------------------------
+// T1  pack / unpack
+// ------------------------------------------------------------------------------------------
+// One warp packs 32 voxels per ballot; lanes walk z so byte loads are contiguous.
+__global__ void __launch_bounds__(256)
+k_pack_bool(const uint8_t *__restrict__ grid, long long rows, int Z, int pitch, uint32_t *__restrict__ bits) {
+    int lane = threadIdx.x & 31;
+    long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    long long items = rows * pitch;                     // one item = one output word
+    for (long long it = warp; it < items; it += nwarps) {
+        long long row = it / pitch;
+        int w = (int)(it - row * pitch);
+        int z = (w << 5) + lane;
+        bool on = (z < Z) && grid[row * (long long)Z + z] != 0;
+        uint32_t word = __ballot_sync(MDVC_FULL, on);
+        if (lane == 0) bits[it] = word;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+k_unpack_bool(const uint32_t *__restrict__ bits, long long rows, int Z, int pitch, uint8_t *__restrict__ grid) {
+    long long n = rows * (long long)Z;
+    long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        long long row = i / Z;
+        int z = (int)(i - row * Z);
+        grid[i] = (bits[row * pitch + (z >> 5)] >> (z & 31)) & 1u;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+k_popcount(const uint32_t *__restrict__ bits, long long rows, int Z, int pitch, unsigned long long *out) {
+    long long items = rows * pitch;
+    long long stride = (long long)gridDim.x * blockDim.x;
+    unsigned long long acc = 0;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < items; i += stride) {
+        int w = (int)(i % pitch);
+        acc += __popc(bits[i] & mdvc_valid_mask(w, Z));
+    }
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(MDVC_FULL, acc, o);
+    if ((threadIdx.x & 31) == 0 && acc) atomicAdd(out, acc);
+}
+
+static bool bad_dims(int X, int Y, int Z, int pitch) {
+    return X <= 0 || Y <= 0 || Z <= 0 || pitch < mdvc_words(Z) ||
+           (long long)X * Y * Z >= (1ll << 31);
+}
+
+extern "C" int mdvc_pack_bool(const uint8_t *grid, int X, int Y, int Z, uint32_t *bits, int pitch, void *stream) {
+    if (!grid || !bits || bad_dims(X, Y, Z, pitch)) return MDVC_ERR_BADARG;
+    long long rows = (long long)X * Y;
+    k_pack_bool<<<mdvc_grid(rows * pitch * 32, 256), 256, 0, (cudaStream_t)stream>>>(grid, rows, Z, pitch, bits);
+    MDVC_LAUNCH_CHECK();
+    return MDVC_OK;
+}
+
+extern "C" int mdvc_unpack_bool(const uint32_t *bits, int X, int Y, int Z, int pitch, uint8_t *grid, void *stream) {
+    if (!grid || !bits || bad_dims(X, Y, Z, pitch)) return MDVC_ERR_BADARG;
+    long long rows = (long long)X * Y;
+    k_unpack_bool<<<mdvc_grid(rows * Z, 256), 256, 0, (cudaStream_t)stream>>>(bits, rows, Z, pitch, grid);
+    MDVC_LAUNCH_CHECK();
+    return MDVC_OK;
+}
+
+extern "C" int mdvc_popcount(const uint32_t *bits, int X, int Y, int Z, int pitch, unsigned long long *count_dev, void *stream) {
+    if (!bits || !count_dev || bad_dims(X, Y, Z, pitch)) return MDVC_ERR_BADARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    MDVC_CUDA_CHECK(cudaMemsetAsync(count_dev, 0, sizeof(unsigned long long), st));
+    long long rows = (long long)X * Y;
+    k_popcount<<<mdvc_grid(rows * pitch, 256, 8), 256, 0, st>>>(bits, rows, Z, pitch, count_dev);
+    MDVC_LAUNCH_CHECK();
+    return MDVC_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// A1  binning
+// ------------------------------------------------------------------------------------------
+struct BinParams {
+    double T[9];
+    double invT[9];
+    long long nbox[9];
+};
+
+__device__ __forceinline__ long long floordiv_ll(long long a, long long b) {
+    long long q = a / b, r = a % b;
+    return (r != 0 && ((r < 0) != (b < 0))) ? q - 1 : q;
+}
+
+// One thread per atom.  float64 products as the FMA chain fma(p2,T2j, fma(p1,T1j, p0*T0j)) --
+// bit-identical to the reference's NumPy/OpenBLAS dgemm; __dmul_rn/__fma_rn keep
+// the compiler from contracting differently.  Lanes of a warp that hit the same occupancy word
+// are merged with __match_any_sync so one lane issues the atomicOr.
+__global__ void __launch_bounds__(256)
+k_bin_atoms(const float *__restrict__ pos, long long n, BinParams P, uint32_t *__restrict__ occ, int pitch,
+            int32_t *__restrict__ vox_out, float *pos_out) {
+    long long stride = (long long)gridDim.x * blockDim.x;
+    long long nround = ((n + 31) / 32) * 32;             // keep warps converged for the match
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nround; i += stride) {
+        bool live = i < n;
+        long long v[3] = {0, 0, 0};
+        double f[3];
+        if (live) {
+            double p0 = (double)pos[3 * i], p1 = (double)pos[3 * i + 1], p2 = (double)pos[3 * i + 2];
+#pragma unroll
+            for (int j = 0; j < 3; ++j) {
+                double fj = __fma_rn(p2, P.T[6 + j], __fma_rn(p1, P.T[3 + j], __dmul_rn(p0, P.T[j])));
+                double fl = floor(fj);
+                v[j] = (long long)fl;
+                f[j] = __dsub_rn(fj, (double)v[j]);
+            }
+#pragma unroll
+            for (int dim = 2; dim >= 0; --dim) {
+                long long s = floordiv_ll(v[dim], P.nbox[4 * dim]);
+#pragma unroll
+                for (int j = 0; j < 3; ++j) v[j] -= s * P.nbox[3 * dim + j];
+            }
+            if (vox_out) {
+                vox_out[3 * i] = (int32_t)v[0]; vox_out[3 * i + 1] = (int32_t)v[1]; vox_out[3 * i + 2] = (int32_t)v[2];
+            }
+            if (pos_out) {
+                double g0 = __dadd_rn((double)v[0], f[0]), g1 = __dadd_rn((double)v[1], f[1]),
+                       g2 = __dadd_rn((double)v[2], f[2]);
+#pragma unroll
+                for (int j = 0; j < 3; ++j)
+                    pos_out[3 * i + j] = (float)__fma_rn(g2, P.invT[6 + j],
+                                                __fma_rn(g1, P.invT[3 + j], __dmul_rn(g0, P.invT[j])));
+            }
+        }
+        if (occ) {
+            long long X = P.nbox[0], Y = P.nbox[4], Z = P.nbox[8];
+            bool inside = live && v[0] >= 0 && v[0] < X && v[1] >= 0 && v[1] < Y && v[2] >= 0 && v[2] < Z;
+            long long word = inside ? ((v[0] * Y + v[1]) * pitch + (v[2] >> 5)) : -1;
+            uint32_t bit = inside ? (1u << (v[2] & 31)) : 0u;
+            unsigned peers = __match_any_sync(MDVC_FULL, word);
+            // OR the bits of all peers into the leader
+            uint32_t merged = 0;
+            unsigned rem = peers;
+            while (rem) {
+                int src = __ffs(rem) - 1;
+                merged |= __shfl_sync(peers, bit, src);
+                rem &= rem - 1;
+            }
+            int leader = __ffs(peers) - 1;
+            if (inside && (threadIdx.x & 31) == leader) atomicOr(&occ[word], merged);
+        }
+    }
+}
+
+extern "C" int mdvc_bin_atoms(const float *pos, long long n, const double *T_host, const double *invT_host,
+                              const long long *nbox_host, uint32_t *occ_bits, int pitch,
+                              int32_t *vox_out, float *pos_out, void *stream) {
+    if (n < 0 || !T_host || !invT_host || !nbox_host || (n > 0 && !pos)) return MDVC_ERR_BADARG;
+    if (nbox_host[0] <= 0 || nbox_host[4] <= 0 || nbox_host[8] <= 0) return MDVC_ERR_BADARG;
+    if (occ_bits && pitch < mdvc_words((int)nbox_host[8])) return MDVC_ERR_BADARG;
+    if (n == 0) return MDVC_OK;
+    BinParams P;
+    memcpy(P.T, T_host, sizeof(P.T));
+    memcpy(P.invT, invT_host, sizeof(P.invT));
+    memcpy(P.nbox, nbox_host, sizeof(P.nbox));
+    k_bin_atoms<<<mdvc_grid(n, 256), 256, 0, (cudaStream_t)stream>>>(pos, n, P, occ_bits, pitch, vox_out, pos_out);
+    MDVC_LAUNCH_CHECK();
+    return MDVC_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// A3/A4  morphology (periodic 3x3x3), one output word per thread
+// ------------------------------------------------------------------------------------------
+// z-dilation of word w of one row, periodic in z.  invert: operate on the complement (erosion).
+__device__ __forceinline__ uint32_t dilate_z_word(const uint32_t *__restrict__ row, int w, int nw, int Z, bool invert) {
+    uint32_t flip = invert ? 0xffffffffu : 0u;
+    int wp = (w > 0) ? w - 1 : nw - 1;
+    int wn = (w < nw - 1) ? w + 1 : 0;
+    uint32_t cur = (row[w] ^ flip) & mdvc_valid_mask(w, Z);
+    uint32_t prv = (row[wp] ^ flip) & mdvc_valid_mask(wp, Z);
+    uint32_t nxt = (row[wn] ^ flip) & mdvc_valid_mask(wn, Z);
+    int last = (Z - 1) & 31;                              // bit index of z = Z-1 inside word nw-1
+    uint32_t down_in = (w > 0) ? (prv >> 31) : ((prv >> last) & 1u);     // value at z-1 for bit 0
+    uint32_t up_in = nxt & 1u;                                            // value at z+1 for the top bit
+    int top = (w == nw - 1) ? last : 31;
+    uint32_t d = cur | (cur << 1) | down_in | (cur >> 1) | (up_in << top);
+    return d & mdvc_valid_mask(w, Z);
+}
+
+__global__ void __launch_bounds__(256)
+k_morph_step(const uint32_t *__restrict__ in, uint32_t *__restrict__ out, int X, int Y, int Z, int pitch, int erode) {
+    int nw = mdvc_words(Z);
+    long long items = (long long)X * Y * pitch;
+    long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < items; i += stride) {
+        int w = (int)(i % pitch);
+        long long r = i / pitch;
+        if (w >= nw) { out[i] = 0; continue; }
+        int y = (int)(r % Y), x = (int)(r / Y);
+        uint32_t acc = 0;
+#pragma unroll
+        for (int dx = -1; dx <= 1; ++dx) {
+            int xx = x + dx; xx = xx < 0 ? X - 1 : (xx >= X ? 0 : xx);
+#pragma unroll
+            for (int dy = -1; dy <= 1; ++dy) {
+                int yy = y + dy; yy = yy < 0 ? Y - 1 : (yy >= Y ? 0 : yy);
+                acc |= dilate_z_word(in + ((long long)xx * Y + yy) * pitch, w, nw, Z, erode != 0);
+            }
+        }
+        out[i] = erode ? (~acc & mdvc_valid_mask(w, Z)) : acc;
+    }
+}
+
+extern "C" int mdvc_morph(const uint32_t *bits_in, uint32_t *bits_out, uint32_t *tmp, int X, int Y, int Z,
+                          int pitch, const char *ops, void *stream) {
+    if (!bits_in || !bits_out || !ops || bad_dims(X, Y, Z, pitch) || bits_in == bits_out) return MDVC_ERR_BADARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    size_t n_ops = strlen(ops);
+    for (size_t i = 0; i < n_ops; ++i)
+        if (ops[i] != 'd' && ops[i] != 'e') { mdvc_set_error_msg("unknown morph operation"); return MDVC_ERR_BADARG; }
+    size_t bytes = (size_t)X * Y * pitch * sizeof(uint32_t);
+    if (n_ops == 0) {
+        MDVC_CUDA_CHECK(cudaMemcpyAsync(bits_out, bits_in, bytes, cudaMemcpyDeviceToDevice, st));
+        return MDVC_OK;
+    }
+    if (n_ops > 1 && (!tmp || tmp == bits_in || tmp == bits_out)) return MDVC_ERR_BADARG;
+    // ping-pong so that the last step lands in bits_out
+    const uint32_t *src = bits_in;
+    long long items = (long long)X * Y * pitch;
+    for (size_t i = 0; i < n_ops; ++i) {
+        bool to_out = ((n_ops - 1 - i) % 2) == 0;
+        uint32_t *dst = to_out ? bits_out : tmp;
+        k_morph_step<<<mdvc_grid(items, 256), 256, 0, st>>>(src, dst, X, Y, Z, pitch, ops[i] == 'e');
+        MDVC_LAUNCH_CHECK();
+        src = dst;
+    }
+    return MDVC_OK;
+}

@@ -1,0 +1,851 @@
+// frame.cu -- run-based connected components, contacts, bridges, periodic components and the
+// single dense write pass ("expand") on the bit-packed occupancy grid.
+//
+// Reference behaviour restated (file:line relative to /root/reference/mdvcontainment/):
+//   labels      label.py:4-19 (scipy.ndimage.label, 26-connectivity, both polarities, no wrap;
+//               numbering = C-order of each component's first voxel)
+//   contacts    find_label_contacts.pyx:5-77
+//   bridges     find_bridges.pyx:4-89
+//   components  graph_logic.py:101-162 + rank_logic.py:112-134 (numbering rule SURVEY.md A.6)
+//   relabel     label.py:21-38, counts containment_main.py:510-512
+//
+// Data model.  A *run* is a maximal stretch of equal voxels along z inside one row (x,y).  Runs are
+// numbered in raster order (row-major, then z), so "smallest run id" == "first voxel in C-order":
+// a union-find that hooks larger roots under smaller ones yields the reference's canonical
+// numbering without ever touching a per-voxel parent array.  All graph work (union-find, pair
+// detection, periodic merge) is done on runs; the dense int32 grids are written exactly once by
+// k_expand, which is the only HBM-heavy kernel of the path.
+#include "common.cuh"
+#include "scan.cuh"
+
+#include <string.h>
+
+// ------------------------------------------------------------------------------------------
+// workspace layout
+// ------------------------------------------------------------------------------------------
+struct Hdr {                       // overlays mdvc_frame_header (64 x uint32)
+    uint32_t total_runs, n_true, n_false, flags, n_contacts, n_bridges, n_comp_pos, n_comp_neg;
+    uint32_t run_eff;              // runs actually stored (0 when the capacity overflowed)
+    uint32_t n_labels;             // n_false + n_true + 1, 0 when the label capacity overflowed
+    uint32_t pad0[2];
+    unsigned long long tot_roots;  // hi32 = False roots, lo32 = True roots
+    unsigned long long tot_comps;  // hi32 = negative components, lo32 = positive components
+    uint32_t pad1[48];
+};
+static_assert(sizeof(Hdr) == 256, "header must be 64 words");
+static_assert(sizeof(mdvc_frame_header) == 256, "public header must be 64 words");
+
+struct Dims {
+    int X, Y, Z, pitch, nw;
+    long long rows;
+    unsigned long long N;
+};
+
+struct Layout {
+    size_t hdr, rowoff, tile32, tile64, runstart, parent, lab, runcomp, scan64, vol, lparent, lut, lscan,
+        ccount, cset, bset, ckeys, bkeys, crows, brows, total;
+};
+
+static inline size_t align_up(size_t v) { return (v + 255) & ~(size_t)255; }
+
+static bool caps_ok(const mdvc_frame_caps *c) {
+    auto pow2 = [](uint32_t v) { return v >= 64 && (v & (v - 1)) == 0; };
+    return c && c->max_runs >= 1 && c->max_labels >= 3 && pow2(c->contact_slots) && pow2(c->bridge_slots);
+}
+
+static Layout make_layout(long long rows, const mdvc_frame_caps *c) {
+    Layout L;
+    size_t o = 0;
+    auto take = [&](size_t bytes) { size_t at = o; o = align_up(o + bytes); return at; };
+    size_t M = c->max_runs, NL = c->max_labels;
+    size_t scan_cap = M > (size_t)rows + 1 ? M : (size_t)rows + 1;
+    if (NL > scan_cap) scan_cap = NL;
+    L.hdr = take(sizeof(Hdr));
+    L.rowoff = take(((size_t)rows + 2) * 4);
+    L.tile32 = take(mdvc_scan_scratch_elems((uint32_t)scan_cap) * 4);
+    L.tile64 = take(mdvc_scan_scratch_elems((uint32_t)scan_cap) * 8);
+    L.runstart = take((M + 1) * 4);
+    L.parent = take(M * 4);
+    L.lab = take(M * 4);
+    L.runcomp = take(M * 4);
+    L.scan64 = take(M * 8);
+    L.vol = take(NL * 8);
+    L.lparent = take(NL * 4);
+    L.lut = take(NL * 4);
+    L.lscan = take(NL * 8);
+    L.ccount = take(NL * 8);
+    L.cset = take((size_t)c->contact_slots * 8);
+    L.bset = take((size_t)c->bridge_slots * 8);
+    L.ckeys = take((size_t)c->contact_slots * 8);
+    L.bkeys = take((size_t)c->bridge_slots * 8);
+    L.crows = take((size_t)c->contact_slots * 8);
+    L.brows = take((size_t)c->bridge_slots * 20);
+    L.total = o;
+    return L;
+}
+
+static bool make_dims(int X, int Y, int Z, int pitch, Dims &D) {
+    if (X <= 0 || Y <= 0 || Z <= 0 || pitch < mdvc_words(Z)) return false;
+    unsigned long long N = (unsigned long long)X * Y * Z;
+    if (N >= (1ull << 31)) return false;
+    D.X = X; D.Y = Y; D.Z = Z; D.pitch = pitch; D.nw = mdvc_words(Z);
+    D.rows = (long long)X * Y; D.N = N;
+    return true;
+}
+
+template <typename T>
+static inline T *at(void *ws, size_t off) { return reinterpret_cast<T *>(reinterpret_cast<char *>(ws) + off); }
+template <typename T>
+static inline const T *at(const void *ws, size_t off) { return reinterpret_cast<const T *>(reinterpret_cast<const char *>(ws) + off); }
+
+extern "C" size_t mdvc_frame_workspace_bytes(int X, int Y, int Z, const mdvc_frame_caps *caps) {
+    if (!caps_ok(caps) || X <= 0 || Y <= 0 || Z <= 0) return 0;
+    return make_layout((long long)X * Y, caps).total;
+}
+
+// ------------------------------------------------------------------------------------------
+// row-group helpers: G lanes (power of two) cooperate on one row, lanes walk the row's words
+// ------------------------------------------------------------------------------------------
+template <int G>
+struct RowWalker {
+    uint32_t carry_msb;   // bit Z-1.. : MSB of the last word of the previous chunk
+    uint32_t run_carry;   // starts seen in previous chunks
+    __device__ __forceinline__ void begin() { carry_msb = 0; run_carry = 0; }
+
+    // B: this lane's (masked) word w.  Returns the start mask S (bit k set <=> a run starts at z=32w+k)
+    __device__ __forceinline__ uint32_t starts(uint32_t B, int w, int Z, int gl) {
+        uint32_t prev = __shfl_up_sync(MDVC_FULL, B, 1, G) >> 31;
+        if (gl == 0) prev = carry_msb;
+        carry_msb = __shfl_sync(MDVC_FULL, B, G - 1, G) >> 31;
+        uint32_t S = B ^ ((B << 1) | prev);
+        if (w == 0) S |= 1u;
+        return S & mdvc_valid_mask(w, Z);
+    }
+    // exclusive count of starts before this lane's word (whole row so far); advances the carry
+    __device__ __forceinline__ uint32_t exclusive(uint32_t S, int gl) {
+        uint32_t cnt = __popc(S), inc = cnt;
+#pragma unroll
+        for (int o = 1; o < G; o <<= 1) {
+            uint32_t t = __shfl_up_sync(MDVC_FULL, inc, o, G);
+            if (gl >= o) inc += t;
+        }
+        uint32_t ex = run_carry + inc - cnt;
+        run_carry += __shfl_sync(MDVC_FULL, inc, G - 1, G);
+        return ex;
+    }
+};
+
+static int pick_group(int nw) {
+    int g = 4;
+    while (g < 32 && g < nw) g <<= 1;
+    return g;
+}
+
+#define MDVC_DISPATCH_G(g, CALL)            \
+    switch (g) {                            \
+        case 4: { constexpr int G = 4; CALL; } break;   \
+        case 8: { constexpr int G = 8; CALL; } break;   \
+        case 16: { constexpr int G = 16; CALL; } break; \
+        default: { constexpr int G = 32; CALL; } break; \
+    }
+
+// ------------------------------------------------------------------------------------------
+// stage 1a: runs per row
+// ------------------------------------------------------------------------------------------
+template <int G>
+__global__ void __launch_bounds__(256)
+k_count_runs(const uint32_t *__restrict__ bits, Dims D, uint32_t *__restrict__ runcount) {
+    const int lane = threadIdx.x & 31, gl = lane & (G - 1), gi = lane / G;
+    constexpr int GPW = 32 / G;
+    long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    int nchunks = (D.nw + G - 1) / G;
+    for (long long rb = warp * GPW; rb < D.rows; rb += nwarps * GPW) {
+        long long row = rb + gi;
+        bool rv = row < D.rows;
+        const uint32_t *rp = bits + (rv ? row : 0) * D.pitch;
+        RowWalker<G> rw; rw.begin();
+        uint32_t total = 0;
+        for (int c = 0; c < nchunks; ++c) {
+            int w = c * G + gl;
+            uint32_t B = (rv && w < D.nw) ? (rp[w] & mdvc_valid_mask(w, D.Z)) : 0u;
+            uint32_t S = rw.starts(B, w, D.Z, gl);
+            total += __popc(S);
+        }
+#pragma unroll
+        for (int o = G / 2; o > 0; o >>= 1) total += __shfl_down_sync(MDVC_FULL, total, o, G);
+        if (rv && gl == 0) runcount[row] = total;
+    }
+}
+
+// after the row scan: publish the totals, raise the overflow flag, sentinel runstart[R] = N
+__global__ void k_after_row_scan(Hdr *h, const uint32_t *rowoff, long long rows, uint32_t max_runs,
+                                 uint32_t *runstart, unsigned long long N) {
+    uint32_t R = rowoff[rows];
+    h->total_runs = R;
+    if (R > max_runs) { h->flags |= MDVC_OVERFLOW_RUNS; h->run_eff = 0; }
+    else { h->run_eff = R; runstart[R] = (uint32_t)N; }
+}
+
+// stage 1b: run start positions (linear voxel index) + union-find init
+template <int G>
+__global__ void __launch_bounds__(256)
+k_fill_runs(const uint32_t *__restrict__ bits, Dims D, const Hdr *__restrict__ h, const uint32_t *__restrict__ rowoff,
+            uint32_t *__restrict__ runstart, uint32_t *__restrict__ parent) {
+    if (h->run_eff == 0) return;
+    const int lane = threadIdx.x & 31, gl = lane & (G - 1), gi = lane / G;
+    constexpr int GPW = 32 / G;
+    long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    int nchunks = (D.nw + G - 1) / G;
+    for (long long rb = warp * GPW; rb < D.rows; rb += nwarps * GPW) {
+        long long row = rb + gi;
+        bool rv = row < D.rows;
+        const uint32_t *rp = bits + (rv ? row : 0) * D.pitch;
+        uint32_t base = rv ? rowoff[row] : 0u;
+        RowWalker<G> rw; rw.begin();
+        for (int c = 0; c < nchunks; ++c) {
+            int w = c * G + gl;
+            uint32_t B = (rv && w < D.nw) ? (rp[w] & mdvc_valid_mask(w, D.Z)) : 0u;
+            uint32_t S = rw.starts(B, w, D.Z, gl);
+            uint32_t ex = rw.exclusive(S, gl);
+            uint32_t id = base + ex;
+            uint32_t lin0 = (uint32_t)(row * D.Z) + (uint32_t)(w << 5);
+            while (S) {
+                int k = __ffs(S) - 1;
+                S &= S - 1;
+                runstart[id] = lin0 + k;
+                parent[id] = id;
+                ++id;
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// run lookups
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t bit_at(const uint32_t *__restrict__ bits, const Dims &D, uint32_t row, int z) {
+    return (bits[(size_t)row * D.pitch + (z >> 5)] >> (z & 31)) & 1u;
+}
+
+// id of the run of `row` that contains voxel z (largest start <= row*Z + z)
+__device__ __forceinline__ uint32_t run_at(const uint32_t *__restrict__ runstart, const uint32_t *__restrict__ rowoff,
+                                           const Dims &D, uint32_t row, int z) {
+    uint32_t lo = rowoff[row], hi = rowoff[row + 1];
+    uint32_t target = row * (uint32_t)D.Z + (uint32_t)z;
+    while (hi - lo > 1) {
+        uint32_t mid = (lo + hi) >> 1;
+        if (runstart[mid] <= target) lo = mid; else hi = mid;
+    }
+    return lo;
+}
+
+// ------------------------------------------------------------------------------------------
+// stage 1c: link runs of equal value that are 26-adjacent (no wrap)
+// Two runs [a,b] (row r) and [c,d] (neighbour row r') touch iff c <= b+1 and d >= a-1.  Every such
+// pair is seen from the start of one of the two runs looking at positions s-1, s, s+1 of the other
+// row, so each run only inspects its own start.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_link_runs(const uint32_t *__restrict__ bits, Dims D, const Hdr *__restrict__ h, const uint32_t *__restrict__ rowoff,
+            const uint32_t *__restrict__ runstart, uint32_t *parent) {
+    uint32_t R = h->run_eff;
+    uint32_t stride = gridDim.x * blockDim.x;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < R; i += stride) {
+        uint32_t lin = runstart[i];
+        uint32_t r = lin / (uint32_t)D.Z;
+        int z = (int)(lin - r * (uint32_t)D.Z);
+        int y = (int)(r % (uint32_t)D.Y), x = (int)(r / (uint32_t)D.Y);
+        uint32_t v = bit_at(bits, D, r, z);
+        for (int dx = -1; dx <= 1; ++dx) {
+            int nx = x + dx;
+            if (nx < 0 || nx >= D.X) continue;
+            for (int dy = -1; dy <= 1; ++dy) {
+                int ny = y + dy;
+                if ((dx == 0 && dy == 0) || ny < 0 || ny >= D.Y) continue;
+                uint32_t r2 = (uint32_t)nx * D.Y + ny;
+                if (bit_at(bits, D, r2, z) == v) {
+                    mdvc_uf_union(parent, i, run_at(runstart, rowoff, D, r2, z));
+                } else {
+                    if (z > 0 && bit_at(bits, D, r2, z - 1) == v)
+                        mdvc_uf_union(parent, i, run_at(runstart, rowoff, D, r2, z - 1));
+                    if (z + 1 < D.Z && bit_at(bits, D, r2, z + 1) == v)
+                        mdvc_uf_union(parent, i, run_at(runstart, rowoff, D, r2, z + 1));
+                }
+            }
+        }
+    }
+}
+
+// stage 1d: flatten + root flags (lo32: True root, hi32: False root)
+__global__ void __launch_bounds__(256)
+k_flatten_flags(const uint32_t *__restrict__ bits, Dims D, const Hdr *__restrict__ h,
+                const uint32_t *__restrict__ runstart, uint32_t *parent, unsigned long long *__restrict__ flags) {
+    uint32_t R = h->run_eff;
+    uint32_t stride = gridDim.x * blockDim.x;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < R; i += stride) {
+        uint32_t root = mdvc_uf_find(parent, i);
+        unsigned long long f = 0;
+        if (root == i) {
+            uint32_t lin = runstart[i];
+            uint32_t r = lin / (uint32_t)D.Z;
+            f = bit_at(bits, D, r, (int)(lin - r * (uint32_t)D.Z)) ? 1ull : (1ull << 32);
+        } else {
+            parent[i] = root;
+        }
+        flags[i] = f;
+    }
+}
+
+__global__ void k_after_root_scan(Hdr *h, uint32_t max_labels) {
+    if (h->run_eff == 0) { h->n_labels = 0; return; }
+    uint32_t nt = (uint32_t)(h->tot_roots & 0xffffffffu), nf = (uint32_t)(h->tot_roots >> 32);
+    h->n_true = nt; h->n_false = nf;
+    unsigned long long nl = (unsigned long long)nt + nf + 1;
+    if (nl > max_labels || nt >= MDVC_LABEL_BIAS || nf >= MDVC_LABEL_BIAS) { h->flags |= MDVC_OVERFLOW_LABELS; h->n_labels = 0; }
+    else h->n_labels = (uint32_t)nl;
+}
+
+// stage 1e: canonical label per run + label volumes
+__global__ void __launch_bounds__(256)
+k_assign_labels(const uint32_t *__restrict__ bits, Dims D, const Hdr *__restrict__ h,
+                const uint32_t *__restrict__ runstart, const uint32_t *__restrict__ parent,
+                const unsigned long long *__restrict__ rootrank, int32_t *__restrict__ lab,
+                unsigned long long *vol) {
+    uint32_t R = h->run_eff;
+    if (h->n_labels == 0) return;
+    uint32_t nf = h->n_false;
+    uint32_t stride = gridDim.x * blockDim.x;
+    uint32_t rounds = (R + stride - 1) / stride;
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    for (uint32_t it = 0; it < rounds; ++it, i += stride) {
+        bool live = i < R;
+        int label = 0;
+        uint32_t len = 0;
+        if (live) {
+            uint32_t lin = runstart[i];
+            uint32_t r = lin / (uint32_t)D.Z;
+            uint32_t v = bit_at(bits, D, r, (int)(lin - r * (uint32_t)D.Z));
+            unsigned long long e = rootrank[parent[i]];
+            label = v ? (int)((uint32_t)(e & 0xffffffffu) + 1u) : -(int)((uint32_t)(e >> 32) + 1u);
+            lab[i] = label;
+            len = runstart[i + 1] - lin;
+        }
+        // warp-aggregated volume accumulation (consecutive runs share very few labels)
+        unsigned peers = __match_any_sync(MDVC_FULL, label);
+        uint32_t sum = __reduce_add_sync(peers, len);
+        if (live && (threadIdx.x & 31) == (__ffs(peers) - 1))
+            atomicAdd(&vol[(long long)label + nf], (unsigned long long)sum);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// stage 2: contacts and bridges on runs
+// ------------------------------------------------------------------------------------------
+#define BLOCKSET_SLOTS 512
+struct BlockSet {
+    unsigned long long slot[BLOCKSET_SLOTS];
+    __device__ void clear() {
+        for (int i = threadIdx.x; i < BLOCKSET_SLOTS; i += blockDim.x) slot[i] = MDVC_KEY_EMPTY;
+    }
+    // true if the key was not yet known to this block (or the block cache is full)
+    __device__ bool add(unsigned long long key) {
+        uint32_t h = (uint32_t)mdvc_mix64(key) & (BLOCKSET_SLOTS - 1);
+        for (int probe = 0; probe < 16; ++probe) {
+            unsigned long long cur = slot[h];
+            if (cur == key) return false;
+            if (cur == MDVC_KEY_EMPTY) {
+                unsigned long long old = atomicCAS(&slot[h], MDVC_KEY_EMPTY, key);
+                if (old == MDVC_KEY_EMPTY) return true;
+                if (old == key) return false;
+            }
+            h = (h + 1) & (BLOCKSET_SLOTS - 1);
+        }
+        return true;
+    }
+};
+
+struct PairSink {
+    BlockSet *cache;
+    unsigned long long *slots;
+    uint32_t n_slots;
+    uint32_t *flags;
+    uint32_t overflow_bit;
+    unsigned long long last;
+    __device__ __forceinline__ void put(unsigned long long key) {
+        if (key == last) return;
+        last = key;
+        if (!cache->add(key)) return;
+        if (!mdvc_set_insert(slots, n_slots, key)) atomicOr(flags, overflow_bit);
+    }
+};
+
+__device__ __forceinline__ void emit_contact(PairSink &s, int a, int b) {
+    if (a == b) return;
+    s.put(a < b ? mdvc_pack_key(a, b, 0) : mdvc_pack_key(b, a, 0));
+}
+// bridge seen from a voxel labelled la stepping by image shift (sx,sy,sz) onto a voxel labelled lb;
+// the reverse step is emitted too when the labels are equal (find_bridges.pyx:84-87)
+__device__ __forceinline__ void emit_bridge(PairSink &s, int la, int lb, int sx, int sy, int sz) {
+    if (la < lb) s.put(mdvc_pack_key(la, lb, mdvc_shift_code(sx, sy, sz)));
+    else if (la > lb) s.put(mdvc_pack_key(lb, la, mdvc_shift_code(-sx, -sy, -sz)));
+    else {
+        s.put(mdvc_pack_key(la, la, mdvc_shift_code(sx, sy, sz)));
+        s.put(mdvc_pack_key(la, la, mdvc_shift_code(-sx, -sy, -sz)));
+    }
+}
+
+__global__ void __launch_bounds__(256)
+k_run_pairs(const uint32_t *__restrict__ bits, Dims D, Hdr *h, const uint32_t *__restrict__ rowoff,
+            const uint32_t *__restrict__ runstart, const int32_t *__restrict__ lab,
+            unsigned long long *cset, uint32_t c_slots, unsigned long long *bset, uint32_t b_slots, int periodic) {
+    __shared__ BlockSet c_cache, b_cache;
+    c_cache.clear(); b_cache.clear();
+    __syncthreads();
+    if (h->n_labels == 0) return;
+    uint32_t R = h->run_eff;
+    PairSink cs{&c_cache, cset, c_slots, &h->flags, MDVC_OVERFLOW_CONTACTS, MDVC_KEY_EMPTY};
+    PairSink bs{&b_cache, bset, b_slots, &h->flags, MDVC_OVERFLOW_BRIDGES, MDVC_KEY_EMPTY};
+    uint32_t stride = gridDim.x * blockDim.x;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < R; i += stride) {
+        uint32_t lin = runstart[i];
+        uint32_t r = lin / (uint32_t)D.Z;
+        int z = (int)(lin - r * (uint32_t)D.Z);
+        int y = (int)(r % (uint32_t)D.Y), x = (int)(r / (uint32_t)D.Y);
+        uint32_t v = bit_at(bits, D, r, z);
+        int la = lab[i];
+        if (z > 0) emit_contact(cs, lab[i - 1], la);              // previous run of the same row
+        bool last_in_row = runstart[i + 1] >= (r + 1) * (uint32_t)D.Z;
+        for (int dx = -1; dx <= 1; ++dx) {
+            int nx = x + dx, sx = 0;
+            if (nx < 0) { nx = D.X - 1; sx = -1; } else if (nx >= D.X) { nx = 0; sx = 1; }
+            for (int dy = -1; dy <= 1; ++dy) {
+                int ny = y + dy, sy = 0;
+                if (ny < 0) { ny = D.Y - 1; sy = -1; } else if (ny >= D.Y) { ny = 0; sy = 1; }
+                uint32_t r2 = (uint32_t)nx * D.Y + ny;
+                if (!(sx | sy)) {
+                    if (dx | dy) {                                    // in-box neighbour row: contacts
+                        if (bit_at(bits, D, r2, z) != v) {
+                            emit_contact(cs, la, lab[run_at(runstart, rowoff, D, r2, z)]);
+                        } else {
+                            if (z > 0 && bit_at(bits, D, r2, z - 1) != v)
+                                emit_contact(cs, la, lab[run_at(runstart, rowoff, D, r2, z - 1)]);
+                            if (z + 1 < D.Z && bit_at(bits, D, r2, z + 1) != v)
+                                emit_contact(cs, la, lab[run_at(runstart, rowoff, D, r2, z + 1)]);
+                        }
+                    }
+                } else if (periodic) {                                // row reached through an x/y face
+                    uint32_t j0 = run_at(runstart, rowoff, D, r2, z);
+                    emit_bridge(bs, la, lab[j0], sx, sy, 0);
+                    if (z > 0) {
+                        uint32_t j = run_at(runstart, rowoff, D, r2, z - 1);
+                        if (j != j0) emit_bridge(bs, la, lab[j], sx, sy, 0);
+                    }
+                    if (z + 1 < D.Z) {
+                        uint32_t j = run_at(runstart, rowoff, D, r2, z + 1);
+                        if (j != j0) emit_bridge(bs, la, lab[j], sx, sy, 0);
+                    }
+                }
+                if (periodic && last_in_row)                          // step through the z-max face
+                    emit_bridge(bs, la, lab[rowoff[r2]], sx, sy, 1);
+            }
+        }
+    }
+}
+
+// compact a hash set into a dense key list
+__global__ void __launch_bounds__(256)
+k_compact_set(const unsigned long long *__restrict__ slots, uint32_t n_slots, unsigned long long *__restrict__ keys,
+              uint32_t *count) {
+    uint32_t stride = gridDim.x * blockDim.x;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_slots; i += stride) {
+        unsigned long long k = slots[i];
+        if (k != MDVC_KEY_EMPTY) keys[atomicAdd(count, 1u)] = k;
+    }
+}
+
+// single-block bitonic sort of keys[0..*count): shared memory when it fits, global memory otherwise
+#define SORT_SMEM_KEYS 4096
+__global__ void __launch_bounds__(1024)
+k_sort_keys(unsigned long long *keys, const uint32_t *count, uint32_t cap) {
+    __shared__ unsigned long long sk[SORT_SMEM_KEYS];
+    uint32_t n = *count;
+    if (n > cap) n = cap;
+    if (n < 2) return;
+    uint32_t P = 1;
+    while (P < n) P <<= 1;
+    if (P > cap) return;   // cannot pad (cap is a power of two >= n, so this does not happen)
+    bool in_smem = P <= SORT_SMEM_KEYS;
+    unsigned long long *a = in_smem ? sk : keys;
+    if (in_smem) {
+        for (uint32_t i = threadIdx.x; i < P; i += blockDim.x) sk[i] = i < n ? keys[i] : MDVC_KEY_EMPTY;
+    } else {
+        for (uint32_t i = n + threadIdx.x; i < P; i += blockDim.x) keys[i] = MDVC_KEY_EMPTY;
+    }
+    __syncthreads();
+    for (uint32_t k = 2; k <= P; k <<= 1) {
+        for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+            for (uint32_t i = threadIdx.x; i < P; i += blockDim.x) {
+                uint32_t ixj = i ^ j;
+                if (ixj > i) {
+                    unsigned long long u = a[i], w = a[ixj];
+                    bool up = (i & k) == 0;
+                    if ((u > w) == up) { a[i] = w; a[ixj] = u; }
+                }
+            }
+            __syncthreads();
+        }
+    }
+    if (in_smem)
+        for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) keys[i] = sk[i];
+}
+
+__global__ void __launch_bounds__(256)
+k_decode_rows(const unsigned long long *__restrict__ keys, const uint32_t *count, uint32_t cap, int with_shift,
+              int32_t *__restrict__ rows) {
+    uint32_t n = min(*count, cap);
+    uint32_t stride = gridDim.x * blockDim.x;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        int l1, l2, code;
+        mdvc_unpack_key(keys[i], l1, l2, code);
+        if (with_shift) {
+            int32_t *o = rows + (size_t)i * 5;
+            o[0] = l1; o[1] = l2; o[2] = code / 9 - 1; o[3] = (code / 3) % 3 - 1; o[4] = code % 3 - 1;
+        } else {
+            rows[2 * (size_t)i] = l1; rows[2 * (size_t)i + 1] = l2;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// stage 3: periodic components on the device
+// ------------------------------------------------------------------------------------------
+__global__ void k_label_uf_init(const Hdr *__restrict__ h, uint32_t *lparent) {
+    uint32_t n = h->n_labels, stride = gridDim.x * blockDim.x;
+    for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += stride) lparent[j] = j;
+}
+
+__global__ void k_label_uf_link(const Hdr *__restrict__ h, const unsigned long long *__restrict__ bkeys, uint32_t cap,
+                                uint32_t *lparent) {
+    if (h->n_labels == 0) return;
+    uint32_t n = min(h->n_bridges, cap), nf = h->n_false, stride = gridDim.x * blockDim.x;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        int l1, l2, code;
+        mdvc_unpack_key(bkeys[i], l1, l2, code);
+        if (l1 != l2 && ((l1 < 0) == (l2 < 0))) mdvc_uf_union(lparent, (uint32_t)(l1 + (int)nf), (uint32_t)(l2 + (int)nf));
+    }
+}
+
+__global__ void k_label_flags(const Hdr *__restrict__ h, uint32_t *lparent, unsigned long long *__restrict__ flags) {
+    uint32_t n = h->n_labels, nf = h->n_false, stride = gridDim.x * blockDim.x;
+    for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += stride) {
+        uint32_t root = mdvc_uf_find(lparent, j);
+        unsigned long long f = 0;
+        if (root == j) f = j < nf ? (1ull << 32) : (j > nf ? 1ull : 0ull);
+        else lparent[j] = root;
+        flags[j] = f;
+    }
+}
+
+__global__ void k_after_comp_scan(Hdr *h) {
+    h->n_comp_pos = (uint32_t)(h->tot_comps & 0xffffffffu);
+    h->n_comp_neg = (uint32_t)(h->tot_comps >> 32);
+}
+
+// lut[j] = component of label (j - n_false): negative components ordered by their most negative
+// label, positive ones by their smallest label
+__global__ void k_label_lut(const Hdr *__restrict__ h, const uint32_t *__restrict__ lparent,
+                            const unsigned long long *__restrict__ rank, int32_t *__restrict__ lut,
+                            const unsigned long long *__restrict__ vol, unsigned long long *ccount, int periodic) {
+    uint32_t n = h->n_labels, nf = h->n_false, stride = gridDim.x * blockDim.x;
+    uint32_t ncn = periodic ? h->n_comp_neg : nf;
+    for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += stride) {
+        int comp;
+        if (!periodic) comp = (int)j - (int)nf;
+        else {
+            unsigned long long e = rank[lparent[j]];
+            comp = j < nf ? -(int)((uint32_t)(e >> 32) + 1u) : (j > nf ? (int)((uint32_t)(e & 0xffffffffu) + 1u) : 0);
+        }
+        lut[j] = comp;
+        if (j != nf) atomicAdd(&ccount[(long long)comp + ncn], vol[j]);
+    }
+}
+
+__global__ void k_run_components(const Hdr *__restrict__ h, const int32_t *__restrict__ lab, const int32_t *__restrict__ lut,
+                                 uint32_t lut_n, int32_t *__restrict__ runcomp) {
+    if (h->n_labels == 0) return;
+    uint32_t R = h->run_eff, nf = h->n_false, stride = gridDim.x * blockDim.x;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < R; i += stride) {
+        uint32_t j = (uint32_t)(lab[i] + (int)nf);
+        runcomp[i] = j < lut_n ? lut[j] : 0;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// stage 4: expand -- the one pass over the dense int32 grids
+// Each row group recomputes the start mask of its row from the bits (L2-resident), turns it into
+// run ordinals by popcount, looks the per-run value up (L1-resident: consecutive voxels share runs)
+// and streams the row out with 16-byte stores.
+// ------------------------------------------------------------------------------------------
+template <int G, bool VEC>
+__global__ void __launch_bounds__(256)
+k_expand(const uint32_t *__restrict__ bits, Dims D, const Hdr *__restrict__ h, const uint32_t *__restrict__ rowoff,
+         const int32_t *__restrict__ lab, const int32_t *__restrict__ runcomp,
+         int32_t *__restrict__ out_lab, int32_t *__restrict__ out_comp) {
+    if (h->n_labels == 0) return;
+    const int lane = threadIdx.x & 31, gl = lane & (G - 1), gi = lane / G;
+    constexpr int GPW = 32 / G;
+    long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    int nchunks = (D.nw + G - 1) / G;
+    for (long long rb = warp * GPW; rb < D.rows; rb += nwarps * GPW) {
+        long long row = rb + gi;
+        bool rv = row < D.rows;
+        const uint32_t *rp = bits + (rv ? row : 0) * D.pitch;
+        uint32_t base = rv ? rowoff[row] : 0u;
+        const int32_t *lrow = lab + base;
+        const int32_t *crow = runcomp + base;
+        size_t obase = (size_t)(rv ? row : 0) * D.Z;
+        RowWalker<G> rw; rw.begin();
+        for (int c = 0; c < nchunks; ++c) {
+            int w = c * G + gl;
+            uint32_t B = (rv && w < D.nw) ? (rp[w] & mdvc_valid_mask(w, D.Z)) : 0u;
+            uint32_t S = rw.starts(B, w, D.Z, gl);
+            uint32_t ex = rw.exclusive(S, gl);
+            if (VEC) {
+#pragma unroll
+                for (int it = 0; it < 8; ++it) {
+                    int q = it * G + gl;                       // quad (4 voxels) inside the chunk
+                    int src = q >> 3;
+                    uint32_t Sw = __shfl_sync(MDVC_FULL, S, src, G);
+                    uint32_t Ew = __shfl_sync(MDVC_FULL, ex, src, G);
+                    int k0 = (q & 7) << 2;
+                    int z0 = ((c * G + src) << 5) + k0;
+                    if (rv && z0 < D.Z) {
+                        uint32_t o0 = Ew + __popc(Sw & ((2u << k0) - 1u)) - 1u;
+                        uint32_t nib = (Sw >> k0) & 0xfu;
+                        uint32_t o1 = o0 + ((nib >> 1) & 1u), o2 = o1 + ((nib >> 2) & 1u), o3 = o2 + ((nib >> 3) & 1u);
+                        if (out_lab) {
+                            int4 val;
+                            val.x = __ldg(lrow + o0);
+                            if (nib >> 1) { val.y = __ldg(lrow + o1); val.z = __ldg(lrow + o2); val.w = __ldg(lrow + o3); }
+                            else { val.y = val.x; val.z = val.x; val.w = val.x; }
+                            __stcs(reinterpret_cast<int4 *>(out_lab + obase + z0), val);
+                        }
+                        if (out_comp) {
+                            int4 val;
+                            val.x = __ldg(crow + o0);
+                            if (nib >> 1) { val.y = __ldg(crow + o1); val.z = __ldg(crow + o2); val.w = __ldg(crow + o3); }
+                            else { val.y = val.x; val.z = val.x; val.w = val.x; }
+                            __stcs(reinterpret_cast<int4 *>(out_comp + obase + z0), val);
+                        }
+                    }
+                }
+            } else {
+#pragma unroll 4
+                for (int it = 0; it < 32; ++it) {
+                    int vix = it * G + gl;
+                    int src = vix >> 5, k = vix & 31;
+                    uint32_t Sw = __shfl_sync(MDVC_FULL, S, src, G);
+                    uint32_t Ew = __shfl_sync(MDVC_FULL, ex, src, G);
+                    int z = ((c * G + src) << 5) + k;
+                    if (rv && z < D.Z) {
+                        uint32_t o = Ew + __popc(Sw & ((2u << k) - 1u)) - 1u;
+                        if (out_lab) __stcs(out_lab + obase + z, __ldg(lrow + o));
+                        if (out_comp) __stcs(out_comp + obase + z, __ldg(crow + o));
+                    }
+                }
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// host entry points
+// ------------------------------------------------------------------------------------------
+static int check_ws(void *ws, size_t ws_bytes, const mdvc_frame_caps *caps, long long rows, Layout &L) {
+    if (!ws || !caps_ok(caps)) return MDVC_ERR_BADARG;
+    L = make_layout(rows, caps);
+    if (ws_bytes < L.total) return MDVC_ERR_WORKSPACE;
+    if ((reinterpret_cast<uintptr_t>(ws) & 255) != 0) return MDVC_ERR_BADARG;
+    return MDVC_OK;
+}
+
+extern "C" int mdvc_frame_label(const uint32_t *bits, int X, int Y, int Z, int pitch, void *ws, size_t ws_bytes,
+                                const mdvc_frame_caps *caps, void *stream) {
+    Dims D; Layout L;
+    if (!bits || !make_dims(X, Y, Z, pitch, D)) return MDVC_ERR_BADARG;
+    int rc = check_ws(ws, ws_bytes, caps, D.rows, L);
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    Hdr *h = at<Hdr>(ws, L.hdr);
+    uint32_t *rowoff = at<uint32_t>(ws, L.rowoff);
+    uint32_t *runstart = at<uint32_t>(ws, L.runstart);
+    uint32_t *parent = at<uint32_t>(ws, L.parent);
+    int32_t *lab = at<int32_t>(ws, L.lab);
+    unsigned long long *scan64 = at<unsigned long long>(ws, L.scan64);
+    unsigned long long *vol = at<unsigned long long>(ws, L.vol);
+
+    MDVC_CUDA_CHECK(cudaMemsetAsync(h, 0, sizeof(Hdr), st));
+    MDVC_CUDA_CHECK(cudaMemsetAsync(vol, 0, (size_t)caps->max_labels * 8, st));
+    int g = pick_group(D.nw);
+    long long row_threads = D.rows * g;
+    unsigned row_grid = mdvc_grid(row_threads, 256, 8);
+    MDVC_DISPATCH_G(g, (k_count_runs<G><<<row_grid, 256, 0, st>>>(bits, D, rowoff)));
+    MDVC_LAUNCH_CHECK();
+    rc = mdvc_exclusive_scan<uint32_t>(rowoff, rowoff, nullptr, (uint32_t)D.rows, at<uint32_t>(ws, L.tile32),
+                                       rowoff + D.rows, nullptr, st);
+    if (rc) return rc;
+    k_after_row_scan<<<1, 1, 0, st>>>(h, rowoff, D.rows, caps->max_runs, runstart, D.N);
+    MDVC_LAUNCH_CHECK();
+    MDVC_DISPATCH_G(g, (k_fill_runs<G><<<row_grid, 256, 0, st>>>(bits, D, h, rowoff, runstart, parent)));
+    MDVC_LAUNCH_CHECK();
+    unsigned run_grid = mdvc_grid(caps->max_runs, 256, 8);
+    k_link_runs<<<run_grid, 256, 0, st>>>(bits, D, h, rowoff, runstart, parent);
+    MDVC_LAUNCH_CHECK();
+    k_flatten_flags<<<run_grid, 256, 0, st>>>(bits, D, h, runstart, parent, scan64);
+    MDVC_LAUNCH_CHECK();
+    rc = mdvc_exclusive_scan<unsigned long long>(scan64, scan64, &h->run_eff, caps->max_runs,
+                                                 at<unsigned long long>(ws, L.tile64), &h->tot_roots, nullptr, st);
+    if (rc) return rc;
+    k_after_root_scan<<<1, 1, 0, st>>>(h, caps->max_labels);
+    MDVC_LAUNCH_CHECK();
+    k_assign_labels<<<run_grid, 256, 0, st>>>(bits, D, h, runstart, parent, scan64, lab, vol);
+    MDVC_LAUNCH_CHECK();
+    return MDVC_OK;
+}
+
+extern "C" int mdvc_frame_pairs(const uint32_t *bits, int X, int Y, int Z, int pitch, void *ws, size_t ws_bytes,
+                                const mdvc_frame_caps *caps, int periodic, void *stream) {
+    Dims D; Layout L;
+    if (!bits || !make_dims(X, Y, Z, pitch, D)) return MDVC_ERR_BADARG;
+    int rc = check_ws(ws, ws_bytes, caps, D.rows, L);
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    Hdr *h = at<Hdr>(ws, L.hdr);
+    unsigned long long *cset = at<unsigned long long>(ws, L.cset), *bset = at<unsigned long long>(ws, L.bset);
+    unsigned long long *ckeys = at<unsigned long long>(ws, L.ckeys), *bkeys = at<unsigned long long>(ws, L.bkeys);
+    MDVC_CUDA_CHECK(cudaMemsetAsync(cset, 0xff, (size_t)caps->contact_slots * 8, st));
+    MDVC_CUDA_CHECK(cudaMemsetAsync(bset, 0xff, (size_t)caps->bridge_slots * 8, st));
+    MDVC_CUDA_CHECK(cudaMemsetAsync(&h->n_contacts, 0, 2 * sizeof(uint32_t), st));
+    unsigned run_grid = mdvc_grid(caps->max_runs, 256, 8);
+    k_run_pairs<<<run_grid, 256, 0, st>>>(bits, D, h, at<uint32_t>(ws, L.rowoff), at<uint32_t>(ws, L.runstart),
+                                          at<int32_t>(ws, L.lab), cset, caps->contact_slots, bset,
+                                          caps->bridge_slots, periodic);
+    MDVC_LAUNCH_CHECK();
+    k_compact_set<<<mdvc_grid(caps->contact_slots, 256, 4), 256, 0, st>>>(cset, caps->contact_slots, ckeys, &h->n_contacts);
+    MDVC_LAUNCH_CHECK();
+    k_sort_keys<<<1, 1024, 0, st>>>(ckeys, &h->n_contacts, caps->contact_slots);
+    MDVC_LAUNCH_CHECK();
+    k_decode_rows<<<mdvc_grid(caps->contact_slots, 256, 4), 256, 0, st>>>(ckeys, &h->n_contacts, caps->contact_slots, 0,
+                                                                          at<int32_t>(ws, L.crows));
+    MDVC_LAUNCH_CHECK();
+    if (periodic) {
+        k_compact_set<<<mdvc_grid(caps->bridge_slots, 256, 4), 256, 0, st>>>(bset, caps->bridge_slots, bkeys, &h->n_bridges);
+        MDVC_LAUNCH_CHECK();
+        k_sort_keys<<<1, 1024, 0, st>>>(bkeys, &h->n_bridges, caps->bridge_slots);
+        MDVC_LAUNCH_CHECK();
+        k_decode_rows<<<mdvc_grid(caps->bridge_slots, 256, 4), 256, 0, st>>>(bkeys, &h->n_bridges, caps->bridge_slots, 1,
+                                                                             at<int32_t>(ws, L.brows));
+        MDVC_LAUNCH_CHECK();
+    }
+    return MDVC_OK;
+}
+
+extern "C" int mdvc_frame_components(int X, int Y, int Z, void *ws, size_t ws_bytes, const mdvc_frame_caps *caps,
+                                          int periodic, void *stream) {
+    Dims D; Layout L;
+    if (!make_dims(X, Y, Z, mdvc_words(Z), D)) return MDVC_ERR_BADARG;
+    int rc = check_ws(ws, ws_bytes, caps, D.rows, L);
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    Hdr *h = at<Hdr>(ws, L.hdr);
+    uint32_t *lparent = at<uint32_t>(ws, L.lparent);
+    int32_t *lut = at<int32_t>(ws, L.lut);
+    unsigned long long *lscan = at<unsigned long long>(ws, L.lscan);
+    unsigned long long *ccount = at<unsigned long long>(ws, L.ccount);
+    MDVC_CUDA_CHECK(cudaMemsetAsync(ccount, 0, (size_t)caps->max_labels * 8, st));
+    unsigned lgrid = mdvc_grid(caps->max_labels, 256, 4);
+    if (periodic) {
+        k_label_uf_init<<<lgrid, 256, 0, st>>>(h, lparent);
+        MDVC_LAUNCH_CHECK();
+        k_label_uf_link<<<mdvc_grid(caps->bridge_slots, 256, 4), 256, 0, st>>>(h, at<unsigned long long>(ws, L.bkeys),
+                                                                                caps->bridge_slots, lparent);
+        MDVC_LAUNCH_CHECK();
+        k_label_flags<<<lgrid, 256, 0, st>>>(h, lparent, lscan);
+        MDVC_LAUNCH_CHECK();
+        rc = mdvc_exclusive_scan<unsigned long long>(lscan, lscan, &h->n_labels, caps->max_labels,
+                                                     at<unsigned long long>(ws, L.tile64), &h->tot_comps, nullptr, st);
+        if (rc) return rc;
+        k_after_comp_scan<<<1, 1, 0, st>>>(h);
+        MDVC_LAUNCH_CHECK();
+    } else {
+        MDVC_CUDA_CHECK(cudaMemcpyAsync(&h->n_comp_pos, &h->n_true, sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));
+        MDVC_CUDA_CHECK(cudaMemcpyAsync(&h->n_comp_neg, &h->n_false, sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));
+    }
+    k_label_lut<<<lgrid, 256, 0, st>>>(h, lparent, lscan, lut, at<unsigned long long>(ws, L.vol), ccount, periodic);
+    MDVC_LAUNCH_CHECK();
+    k_run_components<<<mdvc_grid(caps->max_runs, 256, 8), 256, 0, st>>>(h, at<int32_t>(ws, L.lab), lut, caps->max_labels,
+                                                                        at<int32_t>(ws, L.runcomp));
+    MDVC_LAUNCH_CHECK();
+    return MDVC_OK;
+}
+
+extern "C" int mdvc_frame_set_lut(int X, int Y, int Z, void *ws, size_t ws_bytes, const mdvc_frame_caps *caps,
+                                       const int32_t *lut_dev, uint32_t n_entries, void *stream) {
+    Dims D; Layout L;
+    if (!lut_dev || !make_dims(X, Y, Z, mdvc_words(Z), D)) return MDVC_ERR_BADARG;
+    int rc = check_ws(ws, ws_bytes, caps, D.rows, L);
+    if (rc) return rc;
+    if (n_entries > caps->max_labels) return MDVC_ERR_BADARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    MDVC_CUDA_CHECK(cudaMemcpyAsync(at<int32_t>(ws, L.lut), lut_dev, (size_t)n_entries * 4, cudaMemcpyDeviceToDevice, st));
+    k_run_components<<<mdvc_grid(caps->max_runs, 256, 8), 256, 0, st>>>(at<Hdr>(ws, L.hdr), at<int32_t>(ws, L.lab),
+                                                                        at<int32_t>(ws, L.lut), n_entries,
+                                                                        at<int32_t>(ws, L.runcomp));
+    MDVC_LAUNCH_CHECK();
+    return MDVC_OK;
+}
+
+extern "C" int mdvc_frame_expand(const uint32_t *bits, int X, int Y, int Z, int pitch, void *ws, size_t ws_bytes,
+                                 const mdvc_frame_caps *caps, int32_t *labels_out, int32_t *components_out, void *stream) {
+    Dims D; Layout L;
+    if (!bits || !make_dims(X, Y, Z, pitch, D)) return MDVC_ERR_BADARG;
+    int rc = check_ws(ws, ws_bytes, caps, D.rows, L);
+    if (rc) return rc;
+    if (!labels_out && !components_out) return MDVC_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    int g = pick_group(D.nw);
+    bool vec = (Z % 4 == 0) && ((reinterpret_cast<uintptr_t>(labels_out) & 15) == 0) &&
+               ((reinterpret_cast<uintptr_t>(components_out) & 15) == 0);
+    unsigned grid = mdvc_grid(D.rows * g, 256, 8);
+    const Hdr *h = at<Hdr>(ws, L.hdr);
+    const uint32_t *rowoff = at<uint32_t>(ws, L.rowoff);
+    const int32_t *lab = at<int32_t>(ws, L.lab), *rc_ = at<int32_t>(ws, L.runcomp);
+    if (vec) { MDVC_DISPATCH_G(g, (k_expand<G, true><<<grid, 256, 0, st>>>(bits, D, h, rowoff, lab, rc_, labels_out, components_out))); }
+    else { MDVC_DISPATCH_G(g, (k_expand<G, false><<<grid, 256, 0, st>>>(bits, D, h, rowoff, lab, rc_, labels_out, components_out))); }
+    MDVC_LAUNCH_CHECK();
+    return MDVC_OK;
+}
+
+extern "C" int mdvc_frame_read_header(const void *ws, mdvc_frame_header *header_host, void *stream) {
+    if (!ws || !header_host) return MDVC_ERR_BADARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    MDVC_CUDA_CHECK(cudaMemcpyAsync(header_host, ws, sizeof(mdvc_frame_header), cudaMemcpyDeviceToHost, st));
+    MDVC_CUDA_CHECK(cudaStreamSynchronize(st));
+    memset(header_host->reserved, 0, sizeof(header_host->reserved));
+    return (int)header_host->flags;
+}
+
+#define PTR_GETTER(name, type, field)                                                                         \
+    extern "C" const type *name(const void *ws, int X, int Y, int Z, const mdvc_frame_caps *caps) {           \
+        if (!ws || !caps_ok(caps) || X <= 0 || Y <= 0 || Z <= 0) return nullptr;                              \
+        Layout L = make_layout((long long)X * Y, caps);                                                       \
+        return at<type>(ws, L.field);                                                                         \
+    }
+PTR_GETTER(mdvc_frame_contacts_ptr, int32_t, crows)
+PTR_GETTER(mdvc_frame_bridges_ptr, int32_t, brows)
+PTR_GETTER(mdvc_frame_label_volumes_ptr, long long, vol)
+PTR_GETTER(mdvc_frame_lut_ptr, int32_t, lut)
+PTR_GETTER(mdvc_frame_component_counts_ptr, long long, ccount)

@@ -1,0 +1,174 @@
+"""Host model of the run-based algorithm implemented in csrc/frame.cu (test infrastructure).
+
+It mirrors, step by step and in plain Python, what the kernels do on runs -- start masks, raster
+numbering, the "inspect s-1, s, s+1 from each run start" adjacency rule of k_link_runs and
+k_run_pairs, the min-root union-find numbering and the periodic-component numbering of
+k_label_lut -- so the *rules* can be validated against the oracle on the CPU box, where no
+kernel can run.  It is not a fallback: the product never imports it.
+"""
+import numpy as np
+
+
+def runs_of(grid):
+    """(runstart lin index array incl. sentinel, rowoff)."""
+    X, Y, Z = grid.shape
+    g = grid.reshape(X * Y, Z)
+    start = np.ones_like(g, dtype=bool)
+    start[:, 1:] = g[:, 1:] != g[:, :-1]
+    rowcnt = start.sum(1)
+    rowoff = np.concatenate([[0], np.cumsum(rowcnt)]).astype(np.int64)
+    runstart = np.flatnonzero(start.reshape(-1)).astype(np.int64)
+    return np.concatenate([runstart, [X * Y * Z]]), rowoff
+
+
+class UF:
+    def __init__(self, n):
+        self.p = list(range(n))
+
+    def find(self, v):
+        while self.p[v] != v:
+            self.p[v] = self.p[self.p[v]]
+            v = self.p[v]
+        return v
+
+    def union(self, a, b):
+        a, b = self.find(a), self.find(b)
+        if a == b:
+            return
+        if a < b:
+            a, b = b, a
+        self.p[a] = b
+
+
+def run_at(runstart, rowoff, Z, row, z):
+    lo, hi = rowoff[row], rowoff[row + 1]
+    target = row * Z + z
+    return lo + int(np.searchsorted(runstart[lo:hi], target, side="right")) - 1
+
+
+def label_runs(grid):
+    X, Y, Z = grid.shape
+    flat = grid.reshape(-1)
+    runstart, rowoff = runs_of(grid)
+    R = len(runstart) - 1
+    uf = UF(R)
+    bit = lambda row, z: flat[row * Z + z]
+    for i in range(R):
+        lin = runstart[i]; r, z = divmod(int(lin), Z); x, y = divmod(r, Y); v = flat[lin]
+        for dx in (-1, 0, 1):
+            nx = x + dx
+            if nx < 0 or nx >= X:
+                continue
+            for dy in (-1, 0, 1):
+                ny = y + dy
+                if (dx == 0 and dy == 0) or ny < 0 or ny >= Y:
+                    continue
+                r2 = nx * Y + ny
+                if bit(r2, z) == v:
+                    uf.union(i, run_at(runstart, rowoff, Z, r2, z))
+                else:
+                    if z > 0 and bit(r2, z - 1) == v:
+                        uf.union(i, run_at(runstart, rowoff, Z, r2, z - 1))
+                    if z + 1 < Z and bit(r2, z + 1) == v:
+                        uf.union(i, run_at(runstart, rowoff, Z, r2, z + 1))
+    lab = np.zeros(R, dtype=np.int64)
+    nt = nf = 0
+    rank = {}
+    for i in range(R):
+        if uf.find(i) == i:
+            if flat[runstart[i]]:
+                nt += 1; rank[i] = nt
+            else:
+                nf += 1; rank[i] = -nf
+    for i in range(R):
+        lab[i] = rank[uf.find(i)]
+    return runstart, rowoff, lab, nt, nf
+
+
+def expand(grid, runstart, lab):
+    out = np.empty(grid.size, dtype=np.int32)
+    for i in range(len(lab)):
+        out[runstart[i]:runstart[i + 1]] = lab[i]
+    return out.reshape(grid.shape)
+
+
+def pairs(grid, runstart, rowoff, lab, periodic=True):
+    X, Y, Z = grid.shape
+    flat = grid.reshape(-1)
+    bit = lambda row, z: flat[row * Z + z]
+    contacts, bridges = set(), set()
+
+    def emit_c(a, b):
+        if a != b:
+            contacts.add((min(a, b), max(a, b)))
+
+    def emit_b(la, lb, s):
+        neg = tuple(-c for c in s)
+        if la < lb:
+            bridges.add((la, lb) + s)
+        elif la > lb:
+            bridges.add((lb, la) + neg)
+        else:
+            bridges.add((la, la) + s); bridges.add((la, la) + neg)
+
+    R = len(lab)
+    for i in range(R):
+        lin = int(runstart[i]); r, z = divmod(lin, Z); x, y = divmod(r, Y); v = flat[lin]; la = int(lab[i])
+        if z > 0:
+            emit_c(int(lab[i - 1]), la)
+        last_in_row = runstart[i + 1] >= (r + 1) * Z
+        for dx in (-1, 0, 1):
+            nx, sx = x + dx, 0
+            if nx < 0: nx, sx = X - 1, -1
+            elif nx >= X: nx, sx = 0, 1
+            for dy in (-1, 0, 1):
+                ny, sy = y + dy, 0
+                if ny < 0: ny, sy = Y - 1, -1
+                elif ny >= Y: ny, sy = 0, 1
+                r2 = nx * Y + ny
+                if not (sx or sy):
+                    if dx or dy:
+                        if bit(r2, z) != v:
+                            emit_c(la, int(lab[run_at(runstart, rowoff, Z, r2, z)]))
+                        else:
+                            if z > 0 and bit(r2, z - 1) != v:
+                                emit_c(la, int(lab[run_at(runstart, rowoff, Z, r2, z - 1)]))
+                            if z + 1 < Z and bit(r2, z + 1) != v:
+                                emit_c(la, int(lab[run_at(runstart, rowoff, Z, r2, z + 1)]))
+                elif periodic:
+                    j0 = run_at(runstart, rowoff, Z, r2, z)
+                    emit_b(la, int(lab[j0]), (sx, sy, 0))
+                    if z > 0:
+                        j = run_at(runstart, rowoff, Z, r2, z - 1)
+                        if j != j0: emit_b(la, int(lab[j]), (sx, sy, 0))
+                    if z + 1 < Z:
+                        j = run_at(runstart, rowoff, Z, r2, z + 1)
+                        if j != j0: emit_b(la, int(lab[j]), (sx, sy, 0))
+                if periodic and last_in_row:
+                    emit_b(la, int(lab[rowoff[r2]]), (sx, sy, 1))
+    c = np.array(sorted(contacts), dtype=np.int32).reshape(-1, 2)
+    b = np.array(sorted(bridges), dtype=np.int32)
+    return c, b
+
+
+def component_lut(bridges, nt, nf):
+    """lut[label + nf] -> component id, numbering rule of SURVEY.md A.6."""
+    n = nt + nf + 1
+    uf = UF(n)
+    for row in np.asarray(bridges).reshape(-1, 5):
+        l1, l2 = int(row[0]), int(row[1])
+        if l1 != l2 and (l1 < 0) == (l2 < 0):
+            uf.union(l1 + nf, l2 + nf)
+    lut = np.zeros(n, dtype=np.int32)
+    kn = kp = 0
+    rank = {}
+    for j in range(n):
+        if j != nf and uf.find(j) == j:
+            if j < nf:
+                kn += 1; rank[j] = -kn
+            else:
+                kp += 1; rank[j] = kp
+    for j in range(n):
+        if j != nf:
+            lut[j] = rank[uf.find(j)]
+    return lut, kp, kn

@@ -1,0 +1,302 @@
+"""Parity of the CUDA path (through the C-ABI) with the oracle and the golden vectors. Needs a GPU."""
+import numpy as np
+import pytest
+
+import run_model as rm
+import voxel_oracle as vo
+from golden_util import binning_cases, sha, voxel_cases
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+
+CASES = voxel_cases()
+
+
+@pytest.fixture(scope="module")
+def dev():
+    from mdvcontainment_b200 import device
+    return device
+
+
+def rand_grids(n, seed, maxdim=12, big_z=True):
+    rng = np.random.default_rng(seed)
+    for i in range(n):
+        shape = [int(v) for v in rng.integers(1, maxdim, 3)]
+        if big_z and i % 3 == 0:
+            shape[2] = int(rng.integers(30, 140))
+        yield rng.random(shape) < rng.choice([0.1, 0.3, 0.5, 0.7, 0.9])
+
+
+# ------------------------------------------------------------------------------------------ T1
+def test_pack_unpack_popcount(dev):
+    for g in rand_grids(40, 1):
+        b = dev.BitGrid.from_bool(g)
+        assert np.array_equal(b.to_bool().cpu().numpy(), g)
+        assert b.count() == int(g.sum())
+        words = b.words.cpu().numpy().view(np.uint32)
+        Z = g.shape[2]
+        # tail bits and pad words are zero
+        for w in range(b.pitch):
+            nbits = min(max(Z - 32 * w, 0), 32)
+            mask = np.uint32(0xFFFFFFFF if nbits == 32 else (1 << nbits) - 1)
+            assert not (words[:, :, w] & ~mask).any()
+
+
+# ------------------------------------------------------------------------------------------ A3/A4
+@pytest.mark.parametrize("ops", ["d", "e", "de", "ed", "dde", "deed", ""])
+def test_morph_matches_oracle(dev, ops):
+    for g in rand_grids(25, 2):
+        got = dev.morph(dev.BitGrid.from_bool(g), ops).to_bool().cpu().numpy()
+        assert np.array_equal(got, vo.morph(g, ops)), (g.shape, ops)
+
+
+def test_morph_golden_closings(dev):
+    for name, c in CASES.items():
+        if name.endswith("_closed") and name[:-7] in CASES:
+            got = dev.morph(dev.BitGrid.from_bool(CASES[name[:-7]]["grid"]), "de").to_bool().cpu().numpy()
+            assert sha(got, np.uint8) == c["sha_grid"]
+
+
+def test_morph_rejects_unknown_op(dev):
+    from mdvcontainment_b200._lib import MdvcError
+    with pytest.raises(MdvcError):
+        dev.morph(dev.BitGrid.from_bool(np.zeros((3, 3, 3), bool)), "dx")
+
+
+# ------------------------------------------------------------------------------------------ A1
+@pytest.mark.parametrize("name", sorted(binning_cases()))
+def test_binning_matches_golden(dev, name):
+    c = binning_cases()[name]
+    _, nbox, T, invT = vo.voxel_transform(c["dimensions"], c["resolution"])
+    pos = torch.from_numpy(c["positions"]).cuda()
+    shape = tuple(int(v) for v in np.diagonal(nbox))
+    for p in (1, 2, 3):
+        bits = dev.BitGrid(shape)
+        vox, newpos = dev.bin_atoms(pos, T, invT, nbox, bits, want_voxels=True, want_positions=True)
+        assert np.array_equal(vox.cpu().numpy(), c[f"pass{p}_voxels"])
+        assert np.array_equal(newpos.cpu().numpy().view(np.uint32), c[f"pass{p}_positions"].view(np.uint32))
+        assert np.array_equal(bits.to_bool().cpu().numpy(), c[f"pass{p}_grid"])
+        pos = newpos
+
+
+def test_binning_large_random_vs_oracle(dev):
+    rng = np.random.default_rng(8)
+    dims = np.array([400.0, 380.0, 255.0, 80, 95, 70], dtype=np.float32)
+    n = 300_000
+    pos = ((rng.random((n, 3)) * 2.5 - 0.7) * dims[:3]).astype(np.float32)
+    pos[::2] = np.round(pos[::2] / 5.0) * 5.0
+    vox_o, nbox, new_o = vo.voxelate_fma(pos, dims, 0.5)
+    _, _, T, invT = vo.voxel_transform(dims, 0.5)
+    shape = tuple(int(v) for v in np.diagonal(nbox))
+    bits = dev.BitGrid(shape)
+    p = torch.from_numpy(pos).cuda()
+    vox, newpos = dev.bin_atoms(p, T, invT, nbox, bits, True, True)
+    assert np.array_equal(vox.cpu().numpy().astype(np.int64), vox_o)
+    assert np.array_equal(newpos.cpu().numpy().view(np.uint32), new_o.view(np.uint32))
+    assert np.array_equal(bits.to_bool().cpu().numpy(), vo.occupancy(vox_o, nbox))
+    # in-place write-back (pos_out aliasing pos) gives the same answer
+    from mdvcontainment_b200 import _lib
+    import ctypes
+    lib = _lib.load()
+    p2 = torch.from_numpy(pos).cuda()
+    Tc, iTc, nb = (np.ascontiguousarray(a) for a in (T, invT, nbox.astype(np.int64)))
+    rc = lib.mdvc_bin_atoms(p2.data_ptr(), n, Tc.ctypes.data, iTc.ctypes.data, nb.ctypes.data, None, 0, None,
+                            p2.data_ptr(), ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+    assert rc == 0
+    assert np.array_equal(p2.cpu().numpy().view(np.uint32), new_o.view(np.uint32))
+
+
+# ------------------------------------------------------------------------------------------ A5-A8 on runs
+def run_frame(dev, g, periodic=True, **plan_kw):
+    bits = dev.BitGrid.from_bool(g)
+    plan = dev.FramePlan(g.shape, **plan_kw) if plan_kw else None
+    plan, h = dev.label_with_retry(bits, plan, periodic=periodic)
+    labels = torch.empty(g.shape, dtype=torch.int32, device="cuda")
+    plan.expand(bits, labels, None)
+    return bits, plan, h, labels
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_frame_matches_golden(dev, name):
+    c = CASES[name]
+    g = c["grid"]
+    bits, plan, h, labels = run_frame(dev, g)
+    assert (h.n_true, h.n_false) == (c["n_pos"], c["n_neg"])
+    lab = labels.cpu().numpy()
+    assert sha(lab) == c["sha_labels"]
+    contacts, bridges = plan.contacts(), plan.bridges()
+    assert contacts.shape == c["contacts"].shape and np.array_equal(contacts, c["contacts"])
+    assert bridges.shape == c["bridges"].shape and np.array_equal(bridges, c["bridges"])
+    vol = plan.label_volumes()
+    if c["label_volumes"] is not None:
+        for k, v in c["label_volumes"].items():
+            assert vol[int(k) + h.n_false] == v
+    assert vol.sum() == g.size and vol[h.n_false] == 0
+    # components through a host-supplied LUT (the reference's numbering is decided on the host)
+    if c["has_arrays"]:
+        lut = np.zeros(h.n_true + h.n_false + 1, dtype=np.int32)
+        lut[c["labels"].reshape(-1) + h.n_false] = c["components"].reshape(-1)
+        plan.set_lut(torch.from_numpy(lut).cuda())
+        comps = torch.empty(g.shape, dtype=torch.int32, device="cuda")
+        both = torch.empty(g.shape, dtype=torch.int32, device="cuda")
+        plan.expand(bits, None, comps)
+        assert np.array_equal(comps.cpu().numpy(), c["components"])
+        plan.expand(bits, both, comps)          # fused double write
+        assert np.array_equal(both.cpu().numpy(), lab) and np.array_equal(comps.cpu().numpy(), c["components"])
+    # device-side periodic merge: same partition and counts; numbering by the documented rule
+    plan.components(True)
+    h2 = plan.read_header()
+    lut_dev = plan.lut()
+    want_lut, kp, kn = rm.component_lut(bridges, h.n_true, h.n_false)
+    assert (h2.n_comp_pos, h2.n_comp_neg) == (kp, kn)
+    assert np.array_equal(lut_dev, want_lut)
+    cc = plan.component_counts()
+    assert cc.sum() == g.size
+    assert sorted(cc[cc > 0].tolist()) == sorted(c["counts"].values())
+
+
+def test_frame_random_shapes_vs_oracle(dev):
+    for g in rand_grids(60, 3):
+        bits, plan, h, labels = run_frame(dev, g)
+        want = vo.label_3d_grid(g).astype(np.int32)
+        assert np.array_equal(labels.cpu().numpy(), want), g.shape
+        assert np.array_equal(plan.contacts(), vo.find_label_contacts_c(want)), g.shape
+        wb = vo.find_bridges_c(want)
+        gb = plan.bridges()
+        assert gb.shape == wb.shape and np.array_equal(gb, wb), g.shape
+
+
+def test_frame_slab_mode_skips_bridges(dev):
+    g = CASES["complex3D_roll11"]["grid"]
+    bits, plan, h, labels = run_frame(dev, g, periodic=False)
+    assert h.n_bridges == 0 and plan.bridges().shape == (0,)
+    assert np.array_equal(plan.contacts(), CASES["complex3D_roll11"]["contacts"])
+    plan.components(False)
+    h2 = plan.read_header()
+    assert (h2.n_comp_pos, h2.n_comp_neg) == (h.n_true, h.n_false)
+    comps = torch.empty(g.shape, dtype=torch.int32, device="cuda")
+    plan.expand(bits, None, comps)
+    assert np.array_equal(comps.cpu().numpy(), labels.cpu().numpy())
+
+
+def test_frame_capacity_overflow_is_reported_and_retried(dev):
+    g = CASES["salt48"]["grid"]
+    bits = dev.BitGrid.from_bool(g)
+    tiny = dev.FramePlan(g.shape, max_runs=100, max_labels=8, contact_slots=64, bridge_slots=64)
+    tiny.label(bits)
+    tiny.pairs(bits)
+    h = tiny.read_header()
+    assert h.flags & 1 and h.total_runs > 100          # MDVC_OVERFLOW_RUNS with the required size
+    plan, h = dev.label_with_retry(bits, tiny)
+    assert h.flags == 0
+    labels = torch.empty(g.shape, dtype=torch.int32, device="cuda")
+    plan.expand(bits, labels, None)
+    assert sha(labels.cpu().numpy()) == CASES["salt48"]["sha_labels"]
+    assert np.array_equal(plan.contacts(), CASES["salt48"]["contacts"])
+    assert np.array_equal(plan.bridges(), CASES["salt48"]["bridges"])
+
+
+def test_frame_is_deterministic(dev):
+    g = CASES["salt_40x24x72"]["grid"]
+    out = []
+    for _ in range(3):
+        bits, plan, h, labels = run_frame(dev, g)
+        out.append((sha(labels.cpu().numpy()), sha(plan.contacts()), sha(plan.bridges())))
+    assert out[0] == out[1] == out[2]
+
+
+@pytest.mark.parametrize("n,closing", [(128, True), (256, True)])
+def test_hollow_cylinder_vs_oracle(dev, n, closing):
+    from mdvcontainment_b200 import synth
+    g0 = synth.hollow_cylinder_grid(n)
+    bits = dev.morph(dev.BitGrid.from_bool(g0), "de")
+    g = bits.to_bool().cpu().numpy()
+    assert np.array_equal(g, vo.morph(g0, "de"))
+    plan, h = dev.label_with_retry(bits)
+    labels = torch.empty(g.shape, dtype=torch.int32, device="cuda")
+    plan.expand(bits, labels, None)
+    want = vo.label_3d_grid(g).astype(np.int32)
+    assert np.array_equal(labels.cpu().numpy(), want)
+    assert np.array_equal(plan.contacts(), vo.find_label_contacts_c(want))
+    assert np.array_equal(plan.bridges(), vo.find_bridges_c(want))
+
+
+def test_noise_grid_vs_oracle(dev):
+    from mdvcontainment_b200 import synth
+    g = synth.salt_noise_grid((96, 80, 160), salt=0.03, seed=9)
+    bits, plan, h, labels = run_frame(dev, g)
+    want = vo.label_3d_grid(g).astype(np.int32)
+    assert np.array_equal(labels.cpu().numpy(), want)
+    assert np.array_equal(plan.contacts(), vo.find_label_contacts_c(want))
+    assert np.array_equal(plan.bridges(), vo.find_bridges_c(want))
+    vals, cnt = np.unique(want, return_counts=True)
+    vol = plan.label_volumes()
+    assert np.array_equal(vol[vals + h.n_false], cnt)
+
+
+# ------------------------------------------------------------------------------------------ seam-level grid functions
+@pytest.mark.parametrize("name", [n for n in sorted(CASES) if CASES[n]["has_arrays"]])
+def test_grid_contacts_bridges_match_golden(dev, name):
+    c = CASES[name]
+    got_c = dev.grid_pairs(c["labels"], bridges=False)
+    got_b = dev.grid_pairs(c["labels"], bridges=True)
+    assert got_c.shape == c["contacts"].shape and np.array_equal(got_c, c["contacts"])
+    assert got_b.shape == c["bridges"].shape and np.array_equal(got_b, c["bridges"])
+
+
+def test_grid_pairs_on_arbitrary_label_grids_with_zeros(dev):
+    rng = np.random.default_rng(12)
+    for _ in range(20):
+        shape = tuple(int(v) for v in rng.integers(1, 9, 3))
+        L = rng.integers(-4, 5, shape).astype(np.int32)        # zeros are ignored by the reference
+        wc, wb = vo.find_label_contacts_c(L), vo.find_bridges_c(L)
+        gc, gb = dev.grid_pairs(L, False), dev.grid_pairs(L, True)
+        assert gc.shape == wc.shape and np.array_equal(gc, wc)
+        assert gb.shape == wb.shape and np.array_equal(gb, wb)
+
+
+def test_grid_relabel_count_select(dev):
+    rng = np.random.default_rng(13)
+    for shape in [(5, 6, 7), (16, 16, 64), (3, 1, 129), (40, 33, 50)]:
+        L = rng.integers(-6, 7, shape).astype(np.int32)
+        c2l = {3: (1, 2, 5), -1: (-6, -2), 2: (4,), -2: (-1,)}
+        want = vo.create_components_grid(L, c2l)
+        lut = np.zeros(13, dtype=np.int32)
+        for comp, labs in c2l.items():
+            for l in labs:
+                lut[l + 6] = comp
+        got = dev.grid_relabel(L, lut, -6)
+        assert np.array_equal(got.cpu().numpy(), want)
+        cnt = dev.grid_count(got, -2, 6)
+        vals, n = np.unique(want, return_counts=True)
+        assert np.array_equal(cnt[vals + 2], n) and cnt.sum() == want.size
+        for nodes in ([3], [-1, 2], [0], [3, -2, 2, -1, 0], [9]):
+            pos, mask = dev.grid_select(got, nodes, -2, 6, want_mask=True)
+            wmask = np.isin(want, nodes)
+            assert np.array_equal(mask.cpu().numpy(), wmask)
+            assert pos.dtype == np.int64 and np.array_equal(pos, np.array(np.where(wmask)).T.reshape(-1, 3))
+
+
+# ------------------------------------------------------------------------------------------ atoms
+def test_atom_components_and_csr(dev):
+    rng = np.random.default_rng(14)
+    shape = (20, 17, 40)
+    n = 50_000
+    vox = np.stack([rng.integers(0, s, n) for s in shape], 1).astype(np.int32)
+    comps = rng.integers(-3, 4, shape).astype(np.int32)
+    ix = rng.permutation(3 * n)[:n].astype(np.int64)
+    vd, cd = torch.from_numpy(vox).cuda(), torch.from_numpy(comps).cuda()
+    beta = dev.atom_components(vd, cd).cpu().numpy()
+    assert np.array_equal(beta, vo.atom_components(comps, vox))
+    csr = dev.AtomCSR(vd, shape)
+    lin = (vox[:, 0].astype(np.int64) * shape[1] + vox[:, 1]) * shape[2] + vox[:, 2]
+    order = np.argsort(lin, kind="stable")
+    assert np.array_equal(csr.order.cpu().numpy(), order.astype(np.int32))
+    assert np.array_equal(csr.keys.cpu().numpy(), lin[order])
+    mapping = vo.create_mapping(vox, ix)
+    for nodes in ([1], [-3, 2], [0, 1, 2, 3, -1, -2, -3], [7]):
+        q = vo.voxel_positions(comps, nodes)
+        want = vo.voxels2atoms(q, mapping)
+        got = csr.select(cd, nodes, -3, 7, torch.from_numpy(ix).cuda())
+        assert got.dtype == np.int64 and np.array_equal(got, want)

@@ -1,0 +1,39 @@
+"""The run-level rules used by csrc/frame.cu, validated on the CPU against the oracle/goldens."""
+import numpy as np
+import pytest
+
+import run_model as rm
+import voxel_oracle as vo
+from golden_util import voxel_cases
+
+CASES = voxel_cases()
+SMALL = sorted(n for n, c in CASES.items() if np.prod(c["shape"]) <= 12000)
+
+
+@pytest.mark.parametrize("name", SMALL)
+def test_run_model_matches_golden(name):
+    c = CASES[name]
+    g = c["grid"]
+    runstart, rowoff, lab, nt, nf = rm.label_runs(g)
+    assert (nt, nf) == (c["n_pos"], c["n_neg"])
+    labels = rm.expand(g, runstart, lab)
+    assert np.array_equal(labels, c["labels"])
+    contacts, bridges = rm.pairs(g, runstart, rowoff, lab)
+    assert np.array_equal(contacts, c["contacts"].reshape(-1, 2))
+    assert np.array_equal(bridges, c["bridges"])
+    lut, kp, kn = rm.component_lut(bridges, nt, nf)
+    comps = lut[labels + nf]
+    assert np.array_equal(comps, c["components"])
+
+
+def test_run_model_random_shapes():
+    rng = np.random.default_rng(123)
+    for _ in range(150):
+        shape = tuple(int(v) for v in rng.integers(1, 8, 3))
+        g = rng.random(shape) < rng.choice([0.2, 0.5, 0.8])
+        runstart, rowoff, lab, nt, nf = rm.label_runs(g)
+        want = vo.label_3d_grid(g).astype(np.int32)
+        assert np.array_equal(rm.expand(g, runstart, lab), want)
+        contacts, bridges = rm.pairs(g, runstart, rowoff, lab)
+        assert np.array_equal(contacts, vo.find_label_contacts_c(want))
+        assert np.array_equal(bridges, vo.find_bridges_c(want))
