@@ -211,6 +211,7 @@ k_fill_runs(const uint32_t *__restrict__ bits, Dims D, const Hdr *__restrict__ h
             uint32_t ex = rw.exclusive(S, gl);
             uint32_t id = base + ex;
             uint32_t lin0 = (uint32_t)(row * D.Z) + (uint32_t)(w << 5);
+            if (!rv) S = 0;
             while (S) {
                 int k = __ffs(S) - 1;
                 S &= S - 1;
