@@ -141,6 +141,9 @@ const int32_t *mdvc_frame_bridges_ptr(const void *workspace, int X, int Y, int Z
 const long long *mdvc_frame_label_volumes_ptr(const void *workspace, int X, int Y, int Z, const mdvc_frame_caps *caps);
 const int32_t *mdvc_frame_lut_ptr(const void *workspace, int X, int Y, int Z, const mdvc_frame_caps *caps);
 const long long *mdvc_frame_component_counts_ptr(const void *workspace, int X, int Y, int Z, const mdvc_frame_caps *caps);
+/* run tables, for tests: which = 0 row offsets (uint32[X*Y+1]), 1 run starts (uint32[runs+1], linear voxel index),
+ * 2 union-find parents (uint32[runs]), 3 label per run (int32[runs]), 4 component per run (int32[runs]) */
+const void *mdvc_frame_debug_ptr(const void *workspace, int X, int Y, int Z, const mdvc_frame_caps *caps, int which);
 
 /* ---------------------------------------------------------------------------------------
  * Seam-level functions on dense int32 grids (one-to-one with the reference's functions, for

@@ -61,6 +61,7 @@ SIGNATURES = {
     "mdvc_frame_label_volumes_ptr": (_P, [_P, _I, _I, _I, _CAPS]),
     "mdvc_frame_lut_ptr": (_P, [_P, _I, _I, _I, _CAPS]),
     "mdvc_frame_component_counts_ptr": (_P, [_P, _I, _I, _I, _CAPS]),
+    "mdvc_frame_debug_ptr": (_P, [_P, _I, _I, _I, _CAPS, _I]),
     "mdvc_grid_contacts": (_I, [_P, _I, _I, _I, _P, _U32, _P, _U32, _P, _P, _P]),
     "mdvc_grid_bridges": (_I, [_P, _I, _I, _I, _P, _U32, _P, _U32, _P, _P, _P]),
     "mdvc_grid_relabel": (_I, [_P, _LL, _P, _I, _I, _P, _P]),

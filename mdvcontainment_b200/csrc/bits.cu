@@ -228,6 +228,92 @@ k_morph_step(const uint32_t *__restrict__ in, uint32_t *__restrict__ out, int X,
     }
 }
 
+// Tiled sweep: a CTA owns a tile of TY rows (plus one halo row on each side) x all words of a row and
+// walks along x.  Per plane every thread loads one word (coalesced), parks it in shared memory and
+// forms the y/z-dilated word P[x] from its 3x3 word neighbourhood; a 3-deep register window over x
+// finishes the 3x3x3 OR.  Each input word is read (TY+2)/TY * (TX+2)/TX times, each output written once.
+#define MORPH_MAX_THREADS 512
+template <bool ERODE>
+__global__ void __launch_bounds__(MORPH_MAX_THREADS)
+k_morph_sweep(const uint32_t *__restrict__ in, uint32_t *__restrict__ out, int X, int Y, int Z, int pitch, int nw,
+              int JT, int TX) {
+    __shared__ uint32_t raw[2][MORPH_MAX_THREADS];
+    const int t = threadIdx.x;
+    const int j = t / nw, w = t - j * nw;
+    const bool active = j < JT;
+    const int TY = JT - 2;
+    const int y0 = blockIdx.x * TY;
+    int yy = y0 - 1 + j;
+    yy %= Y; if (yy < 0) yy += Y;
+    const int yout = y0 + j - 1;
+    const bool is_out = active && j >= 1 && j <= TY && yout < Y;
+    const int xs = blockIdx.y * TX, xe = min(xs + TX, X);
+    const uint32_t vmask = mdvc_valid_mask(w, Z);
+    const int last = (Z - 1) & 31;
+    const int wp = w > 0 ? w - 1 : nw - 1, wn = w < nw - 1 ? w + 1 : 0;
+    const int top = (w == nw - 1) ? last : 31;
+    auto load = [&](int x) -> uint32_t {
+        int xw = x < 0 ? x + X : (x >= X ? x - X : x);
+        uint32_t v = active ? in[((size_t)xw * Y + yy) * pitch + w] : 0u;
+        if (ERODE) v = ~v;
+        return v & vmask;
+    };
+    uint32_t Pm2 = 0, Pm1 = 0;
+    uint32_t v = load(xs - 1);
+    for (int s = 0, x = xs - 1; x <= xe; ++x, ++s) {
+        uint32_t vnext = (x < xe) ? load(x + 1) : 0u;      // prefetch the next plane
+        uint32_t *buf = raw[s & 1];
+        if (active) buf[t] = v;
+        __syncthreads();
+        uint32_t P = 0;
+        if (is_out) {
+            const uint32_t *r0 = buf + (j - 1) * nw, *r1 = r0 + nw, *r2 = r1 + nw;
+            uint32_t c = r0[w] | r1[w] | r2[w];
+            uint32_t pw = r0[wp] | r1[wp] | r2[wp];
+            uint32_t nx = r0[wn] | r1[wn] | r2[wn];
+            uint32_t down_in = (w > 0) ? (pw >> 31) : ((pw >> last) & 1u);
+            P = (c | (c << 1) | down_in | (c >> 1) | ((nx & 1u) << top)) & vmask;
+            if (s >= 2) {
+                uint32_t o = Pm2 | Pm1 | P;
+                if (ERODE) o = ~o & vmask;
+                size_t at = ((size_t)(x - 1) * Y + yout) * pitch;
+                out[at + w] = o;
+                if (w == nw - 1) for (int k = nw; k < pitch; ++k) out[at + k] = 0u;
+            }
+        }
+        Pm2 = Pm1; Pm1 = P;
+        v = vnext;
+    }
+}
+
+static int launch_morph(const uint32_t *src, uint32_t *dst, int X, int Y, int Z, int pitch, bool erode, cudaStream_t st) {
+    int nw = mdvc_words(Z);
+    if (nw * 3 > MORPH_MAX_THREADS) {      // very long rows: the simple kernel
+        long long items = (long long)X * Y * pitch;
+        k_morph_step<<<mdvc_grid(items, 256), 256, 0, st>>>(src, dst, X, Y, Z, pitch, erode);
+        MDVC_LAUNCH_CHECK();
+        return MDVC_OK;
+    }
+    int JT = MORPH_MAX_THREADS / nw;
+    if (JT > Y + 2) JT = Y + 2;
+    if (JT < 3) JT = 3;
+    int TY = JT - 2;
+    int ny = (Y + TY - 1) / TY;
+    int target = mdvc_num_sms() * 8;
+    int xchunks = (target + ny - 1) / ny;
+    if (xchunks > (X + 3) / 4) xchunks = (X + 3) / 4;
+    if (xchunks < 1) xchunks = 1;
+    if (xchunks > 65535) xchunks = 65535;
+    int TX = (X + xchunks - 1) / xchunks;
+    xchunks = (X + TX - 1) / TX;
+    int threads = ((JT * nw + 31) / 32) * 32;
+    dim3 grid(ny, xchunks);
+    if (erode) k_morph_sweep<true><<<grid, threads, 0, st>>>(src, dst, X, Y, Z, pitch, nw, JT, TX);
+    else k_morph_sweep<false><<<grid, threads, 0, st>>>(src, dst, X, Y, Z, pitch, nw, JT, TX);
+    MDVC_LAUNCH_CHECK();
+    return MDVC_OK;
+}
+
 extern "C" int mdvc_morph(const uint32_t *bits_in, uint32_t *bits_out, uint32_t *tmp, int X, int Y, int Z,
                           int pitch, const char *ops, void *stream) {
     if (!bits_in || !bits_out || !ops || bad_dims(X, Y, Z, pitch) || bits_in == bits_out) return MDVC_ERR_BADARG;
@@ -243,12 +329,11 @@ extern "C" int mdvc_morph(const uint32_t *bits_in, uint32_t *bits_out, uint32_t 
     if (n_ops > 1 && (!tmp || tmp == bits_in || tmp == bits_out)) return MDVC_ERR_BADARG;
     // ping-pong so that the last step lands in bits_out
     const uint32_t *src = bits_in;
-    long long items = (long long)X * Y * pitch;
     for (size_t i = 0; i < n_ops; ++i) {
         bool to_out = ((n_ops - 1 - i) % 2) == 0;
         uint32_t *dst = to_out ? bits_out : tmp;
-        k_morph_step<<<mdvc_grid(items, 256), 256, 0, st>>>(src, dst, X, Y, Z, pitch, ops[i] == 'e');
-        MDVC_LAUNCH_CHECK();
+        int rc = launch_morph(src, dst, X, Y, Z, pitch, ops[i] == 'e', st);
+        if (rc) return rc;
         src = dst;
     }
     return MDVC_OK;

@@ -160,6 +160,29 @@ k_count_runs(const uint32_t *__restrict__ bits, Dims D, uint32_t *__restrict__ r
     long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
     int nchunks = (D.nw + G - 1) / G;
+    if (nchunks == 1) {
+        // rows of at most G words: four rows per group and iteration keep four loads in flight
+        constexpr int U = 4;
+        const uint32_t vm = mdvc_valid_mask(gl, D.Z);
+        for (long long rb = warp * (GPW * U); rb < D.rows; rb += nwarps * (GPW * U)) {
+            uint32_t B[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                long long row = rb + u * GPW + gi;
+                B[u] = (row < D.rows && gl < D.nw) ? (bits[row * D.pitch + gl] & vm) : 0u;
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                long long row = rb + u * GPW + gi;
+                RowWalker<G> rw; rw.begin();
+                uint32_t total = __popc(rw.starts(B[u], gl, D.Z, gl));
+#pragma unroll
+                for (int o = G / 2; o > 0; o >>= 1) total += __shfl_down_sync(MDVC_FULL, total, o, G);
+                if (row < D.rows && gl == 0) runcount[row] = total;
+            }
+        }
+        return;
+    }
     for (long long rb = warp * GPW; rb < D.rows; rb += nwarps * GPW) {
         long long row = rb + gi;
         bool rv = row < D.rows;
@@ -198,6 +221,37 @@ k_fill_runs(const uint32_t *__restrict__ bits, Dims D, const Hdr *__restrict__ h
     long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
     int nchunks = (D.nw + G - 1) / G;
+    if (nchunks == 1) {
+        constexpr int U = 4;
+        const uint32_t vm = mdvc_valid_mask(gl, D.Z);
+        for (long long rb = warp * (GPW * U); rb < D.rows; rb += nwarps * (GPW * U)) {
+            uint32_t B[U], base[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                long long row = rb + u * GPW + gi;
+                bool rv = row < D.rows;
+                B[u] = (rv && gl < D.nw) ? (bits[row * D.pitch + gl] & vm) : 0u;
+                base[u] = rv ? rowoff[row] : 0u;
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                long long row = rb + u * GPW + gi;
+                RowWalker<G> rw; rw.begin();
+                uint32_t S = rw.starts(B[u], gl, D.Z, gl);
+                uint32_t id = base[u] + rw.exclusive(S, gl);
+                uint32_t lin0 = (uint32_t)(row * D.Z) + (uint32_t)(gl << 5);
+                if (row >= D.rows) S = 0;
+                while (S) {
+                    int k = __ffs(S) - 1;
+                    S &= S - 1;
+                    runstart[id] = lin0 + k;
+                    parent[id] = id;
+                    ++id;
+                }
+            }
+        }
+        return;
+    }
     for (long long rb = warp * GPW; rb < D.rows; rb += nwarps * GPW) {
         long long row = rb + gi;
         bool rv = row < D.rows;
@@ -244,9 +298,10 @@ __device__ __forceinline__ uint32_t run_at(const uint32_t *__restrict__ runstart
 
 // ------------------------------------------------------------------------------------------
 // stage 1c: link runs of equal value that are 26-adjacent (no wrap)
-// Two runs [a,b] (row r) and [c,d] (neighbour row r') touch iff c <= b+1 and d >= a-1.  Every such
-// pair is seen from the start of one of the two runs looking at positions s-1, s, s+1 of the other
-// row, so each run only inspects its own start.
+// Two runs [a,b] (row r) and [c,d] (neighbour row r') touch iff c <= b+1 and d >= a-1.  Every
+// unordered pair of neighbouring rows is visited once, from the later row towards its four
+// raster-order predecessors (x-1,y-1) (x-1,y) (x-1,y+1) (x,y-1); the thread of run A walks the runs
+// of the other row that intersect [a-1, b+1] (every second one has A's value).
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 k_link_runs(const uint32_t *__restrict__ bits, Dims D, const Hdr *__restrict__ h, const uint32_t *__restrict__ rowoff,
@@ -256,24 +311,23 @@ k_link_runs(const uint32_t *__restrict__ bits, Dims D, const Hdr *__restrict__ h
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < R; i += stride) {
         uint32_t lin = runstart[i];
         uint32_t r = lin / (uint32_t)D.Z;
-        int z = (int)(lin - r * (uint32_t)D.Z);
+        int a = (int)(lin - r * (uint32_t)D.Z);
+        int b = (int)(runstart[i + 1] - r * (uint32_t)D.Z) - 1;
         int y = (int)(r % (uint32_t)D.Y), x = (int)(r / (uint32_t)D.Y);
-        uint32_t v = bit_at(bits, D, r, z);
-        for (int dx = -1; dx <= 1; ++dx) {
-            int nx = x + dx;
-            if (nx < 0 || nx >= D.X) continue;
-            for (int dy = -1; dy <= 1; ++dy) {
-                int ny = y + dy;
-                if ((dx == 0 && dy == 0) || ny < 0 || ny >= D.Y) continue;
-                uint32_t r2 = (uint32_t)nx * D.Y + ny;
-                if (bit_at(bits, D, r2, z) == v) {
-                    mdvc_uf_union(parent, i, run_at(runstart, rowoff, D, r2, z));
-                } else {
-                    if (z > 0 && bit_at(bits, D, r2, z - 1) == v)
-                        mdvc_uf_union(parent, i, run_at(runstart, rowoff, D, r2, z - 1));
-                    if (z + 1 < D.Z && bit_at(bits, D, r2, z + 1) == v)
-                        mdvc_uf_union(parent, i, run_at(runstart, rowoff, D, r2, z + 1));
-                }
+        uint32_t v = bit_at(bits, D, r, a);
+        int lo = a > 0 ? a - 1 : 0, hi = b + 1 < D.Z ? b + 1 : D.Z - 1;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            int nx = x + (k < 3 ? -1 : 0), ny = y + (k < 3 ? k - 1 : -1);
+            if (nx < 0 || ny < 0 || ny >= D.Y) continue;
+            uint32_t r2 = (uint32_t)nx * D.Y + ny;
+            uint32_t j = run_at(runstart, rowoff, D, r2, lo);
+            if (bit_at(bits, D, r2, lo) != v) ++j;             // runs alternate: the next one has value v
+            uint32_t end = rowoff[r2 + 1], limit = r2 * (uint32_t)D.Z + (uint32_t)hi;
+            for (; j < end && runstart[j] <= limit; j += 2) {
+                // fast path: both already point at the same node (no trip to the hot root's cache line)
+                if (__ldcg(&parent[i]) == __ldcg(&parent[j])) continue;
+                mdvc_uf_union(parent, i, j);
             }
         }
     }
@@ -286,7 +340,11 @@ k_flatten_flags(const uint32_t *__restrict__ bits, Dims D, const Hdr *__restrict
     uint32_t R = h->run_eff;
     uint32_t stride = gridDim.x * blockDim.x;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < R; i += stride) {
-        uint32_t root = mdvc_uf_find(parent, i);
+        // read-only climb: in this kernel parent[i] is written by thread i alone, so after the kernel
+        // every entry holds a root (a pointer-jumping find here could overwrite a neighbour's
+        // finished entry with a non-root ancestor)
+        uint32_t root = i, up;
+        while ((up = __ldcg(&parent[root])) != root) root = up;
         unsigned long long f = 0;
         if (root == i) {
             uint32_t lin = runstart[i];
@@ -397,6 +455,10 @@ __device__ __forceinline__ void emit_bridge(PairSink &s, int la, int lb, int sx,
     }
 }
 
+// One thread per run A = [a,b] of row r.  Row relations are visited once each: the four raster-order
+// predecessor offsets for x/y neighbours (in-box -> contacts, through a face -> bridges with shift
+// (sx,sy,0)), and all nine (dx,dy) for the step through the z-max face (shift (sx,sy,+1)) taken by the
+// last run of the row.  The reverse steps give the same normalised rows (emit_bridge).
 __global__ void __launch_bounds__(256)
 k_run_pairs(const uint32_t *__restrict__ bits, Dims D, Hdr *h, const uint32_t *__restrict__ rowoff,
             const uint32_t *__restrict__ runstart, const int32_t *__restrict__ lab,
@@ -412,44 +474,41 @@ k_run_pairs(const uint32_t *__restrict__ bits, Dims D, Hdr *h, const uint32_t *_
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < R; i += stride) {
         uint32_t lin = runstart[i];
         uint32_t r = lin / (uint32_t)D.Z;
-        int z = (int)(lin - r * (uint32_t)D.Z);
+        int a = (int)(lin - r * (uint32_t)D.Z);
+        uint32_t next = runstart[i + 1];
+        int b = (int)(next - r * (uint32_t)D.Z) - 1;
         int y = (int)(r % (uint32_t)D.Y), x = (int)(r / (uint32_t)D.Y);
-        uint32_t v = bit_at(bits, D, r, z);
+        uint32_t v = bit_at(bits, D, r, a);
         int la = lab[i];
-        if (z > 0) emit_contact(cs, lab[i - 1], la);              // previous run of the same row
-        bool last_in_row = runstart[i + 1] >= (r + 1) * (uint32_t)D.Z;
-        for (int dx = -1; dx <= 1; ++dx) {
-            int nx = x + dx, sx = 0;
-            if (nx < 0) { nx = D.X - 1; sx = -1; } else if (nx >= D.X) { nx = 0; sx = 1; }
-            for (int dy = -1; dy <= 1; ++dy) {
-                int ny = y + dy, sy = 0;
-                if (ny < 0) { ny = D.Y - 1; sy = -1; } else if (ny >= D.Y) { ny = 0; sy = 1; }
-                uint32_t r2 = (uint32_t)nx * D.Y + ny;
-                if (!(sx | sy)) {
-                    if (dx | dy) {                                    // in-box neighbour row: contacts
-                        if (bit_at(bits, D, r2, z) != v) {
-                            emit_contact(cs, la, lab[run_at(runstart, rowoff, D, r2, z)]);
-                        } else {
-                            if (z > 0 && bit_at(bits, D, r2, z - 1) != v)
-                                emit_contact(cs, la, lab[run_at(runstart, rowoff, D, r2, z - 1)]);
-                            if (z + 1 < D.Z && bit_at(bits, D, r2, z + 1) != v)
-                                emit_contact(cs, la, lab[run_at(runstart, rowoff, D, r2, z + 1)]);
-                        }
-                    }
-                } else if (periodic) {                                // row reached through an x/y face
-                    uint32_t j0 = run_at(runstart, rowoff, D, r2, z);
-                    emit_bridge(bs, la, lab[j0], sx, sy, 0);
-                    if (z > 0) {
-                        uint32_t j = run_at(runstart, rowoff, D, r2, z - 1);
-                        if (j != j0) emit_bridge(bs, la, lab[j], sx, sy, 0);
-                    }
-                    if (z + 1 < D.Z) {
-                        uint32_t j = run_at(runstart, rowoff, D, r2, z + 1);
-                        if (j != j0) emit_bridge(bs, la, lab[j], sx, sy, 0);
-                    }
+        if (a > 0) emit_contact(cs, lab[i - 1], la);              // previous run of the same row
+        bool last_in_row = b == D.Z - 1;
+        int lo = a > 0 ? a - 1 : 0, hi = b + 1 < D.Z ? b + 1 : D.Z - 1;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            int nx = x + (k < 3 ? -1 : 0), ny = y + (k < 3 ? k - 1 : -1), sx = 0, sy = 0;
+            if (nx < 0) { nx = D.X - 1; sx = -1; }
+            if (ny < 0) { ny = D.Y - 1; sy = -1; } else if (ny >= D.Y) { ny = 0; sy = 1; }
+            bool wraps = (sx | sy) != 0;
+            if (wraps && !periodic) continue;
+            uint32_t r2 = (uint32_t)nx * D.Y + ny;
+            uint32_t j = run_at(runstart, rowoff, D, r2, lo);
+            uint32_t end = rowoff[r2 + 1], limit = r2 * (uint32_t)D.Z + (uint32_t)hi;
+            if (!wraps) {                                          // contacts: runs of the other value
+                if (bit_at(bits, D, r2, lo) == v) ++j;
+                for (; j < end && runstart[j] <= limit; j += 2) emit_contact(cs, la, lab[j]);
+            } else {                                               // bridges: every run in reach
+                for (; j < end && runstart[j] <= limit; ++j) emit_bridge(bs, la, lab[j], sx, sy, 0);
+            }
+        }
+        if (periodic && last_in_row) {                             // steps through the z-max face
+            for (int dx = -1; dx <= 1; ++dx) {
+                int nx = x + dx, sx = 0;
+                if (nx < 0) { nx = D.X - 1; sx = -1; } else if (nx >= D.X) { nx = 0; sx = 1; }
+                for (int dy = -1; dy <= 1; ++dy) {
+                    int ny = y + dy, sy = 0;
+                    if (ny < 0) { ny = D.Y - 1; sy = -1; } else if (ny >= D.Y) { ny = 0; sy = 1; }
+                    emit_bridge(bs, la, lab[rowoff[(uint32_t)nx * D.Y + ny]], sx, sy, 1);
                 }
-                if (periodic && last_in_row)                          // step through the z-max face
-                    emit_bridge(bs, la, lab[rowoff[r2]], sx, sy, 1);
             }
         }
     }
@@ -541,7 +600,8 @@ __global__ void k_label_uf_link(const Hdr *__restrict__ h, const unsigned long l
 __global__ void k_label_flags(const Hdr *__restrict__ h, uint32_t *lparent, unsigned long long *__restrict__ flags) {
     uint32_t n = h->n_labels, nf = h->n_false, stride = gridDim.x * blockDim.x;
     for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += stride) {
-        uint32_t root = mdvc_uf_find(lparent, j);
+        uint32_t root = j, up;                       // read-only climb, see k_flatten_flags
+        while ((up = __ldcg(&lparent[root])) != root) root = up;
         unsigned long long f = 0;
         if (root == j) f = j < nf ? (1ull << 32) : (j > nf ? 1ull : 0ull);
         else lparent[j] = root;
@@ -850,3 +910,12 @@ PTR_GETTER(mdvc_frame_bridges_ptr, int32_t, brows)
 PTR_GETTER(mdvc_frame_label_volumes_ptr, long long, vol)
 PTR_GETTER(mdvc_frame_lut_ptr, int32_t, lut)
 PTR_GETTER(mdvc_frame_component_counts_ptr, long long, ccount)
+
+// test/debug access to the run tables: 0 rowoff(u32) 1 runstart(u32) 2 parent(u32) 3 lab(i32) 4 runcomp(i32)
+extern "C" const void *mdvc_frame_debug_ptr(const void *ws, int X, int Y, int Z, const mdvc_frame_caps *caps, int which) {
+    if (!ws || !caps_ok(caps) || X <= 0 || Y <= 0 || Z <= 0) return nullptr;
+    Layout L = make_layout((long long)X * Y, caps);
+    const size_t offs[5] = {L.rowoff, L.runstart, L.parent, L.lab, L.runcomp};
+    if (which < 0 || which > 4) return nullptr;
+    return at<char>(ws, offs[which]);
+}

@@ -193,6 +193,13 @@ class FramePlan:
         t = self.ws[off: off + n * itemsize].view(dtype)
         return t.view(count, cols) if cols else t
 
+    def run_table(self, which: int, count: int) -> np.ndarray:
+        """Test access to the run tables (see mdvc_frame_debug_ptr)."""
+        X, Y, Z = self.shape
+        ptr = self.lib.mdvc_frame_debug_ptr(_ptr(self.ws), X, Y, Z, ctypes.byref(self.caps), which)
+        off = ptr - self.ws.data_ptr()
+        return self.ws[off: off + 4 * count].view(torch.int32).cpu().numpy()
+
     def contacts(self) -> np.ndarray:
         h = self.header
         return self._view(self.lib.mdvc_frame_contacts_ptr, torch.int32, h.n_contacts, 2).cpu().numpy()

@@ -46,31 +46,30 @@ def run_at(runstart, rowoff, Z, row, z):
     return lo + int(np.searchsorted(runstart[lo:hi], target, side="right")) - 1
 
 
+BACKWARD = ((-1, -1), (-1, 0), (-1, 1), (0, -1))     # raster-order predecessors among the 8 neighbour rows
+
+
 def label_runs(grid):
     X, Y, Z = grid.shape
     flat = grid.reshape(-1)
     runstart, rowoff = runs_of(grid)
     R = len(runstart) - 1
     uf = UF(R)
-    bit = lambda row, z: flat[row * Z + z]
     for i in range(R):
-        lin = runstart[i]; r, z = divmod(int(lin), Z); x, y = divmod(r, Y); v = flat[lin]
-        for dx in (-1, 0, 1):
-            nx = x + dx
-            if nx < 0 or nx >= X:
+        lin = int(runstart[i]); r, a = divmod(lin, Z); x, y = divmod(r, Y); v = flat[lin]
+        b = int(runstart[i + 1]) - r * Z - 1
+        lo, hi = max(a - 1, 0), min(b + 1, Z - 1)
+        for dx, dy in BACKWARD:
+            nx, ny = x + dx, y + dy
+            if nx < 0 or ny < 0 or ny >= Y:
                 continue
-            for dy in (-1, 0, 1):
-                ny = y + dy
-                if (dx == 0 and dy == 0) or ny < 0 or ny >= Y:
-                    continue
-                r2 = nx * Y + ny
-                if bit(r2, z) == v:
-                    uf.union(i, run_at(runstart, rowoff, Z, r2, z))
-                else:
-                    if z > 0 and bit(r2, z - 1) == v:
-                        uf.union(i, run_at(runstart, rowoff, Z, r2, z - 1))
-                    if z + 1 < Z and bit(r2, z + 1) == v:
-                        uf.union(i, run_at(runstart, rowoff, Z, r2, z + 1))
+            r2 = nx * Y + ny
+            j = run_at(runstart, rowoff, Z, r2, lo)
+            if flat[r2 * Z + lo] != v:
+                j += 1
+            while j < rowoff[r2 + 1] and runstart[j] <= r2 * Z + hi:
+                uf.union(i, j)
+                j += 2
     lab = np.zeros(R, dtype=np.int64)
     nt = nf = 0
     rank = {}
@@ -113,39 +112,39 @@ def pairs(grid, runstart, rowoff, lab, periodic=True):
 
     R = len(lab)
     for i in range(R):
-        lin = int(runstart[i]); r, z = divmod(lin, Z); x, y = divmod(r, Y); v = flat[lin]; la = int(lab[i])
-        if z > 0:
+        lin = int(runstart[i]); r, a = divmod(lin, Z); x, y = divmod(r, Y); v = flat[lin]; la = int(lab[i])
+        b = int(runstart[i + 1]) - r * Z - 1
+        if a > 0:
             emit_c(int(lab[i - 1]), la)
-        last_in_row = runstart[i + 1] >= (r + 1) * Z
-        for dx in (-1, 0, 1):
-            nx, sx = x + dx, 0
+        lo, hi = max(a - 1, 0), min(b + 1, Z - 1)
+        for dx, dy in BACKWARD:
+            nx, ny, sx, sy = x + dx, y + dy, 0, 0
             if nx < 0: nx, sx = X - 1, -1
-            elif nx >= X: nx, sx = 0, 1
-            for dy in (-1, 0, 1):
-                ny, sy = y + dy, 0
-                if ny < 0: ny, sy = Y - 1, -1
-                elif ny >= Y: ny, sy = 0, 1
-                r2 = nx * Y + ny
-                if not (sx or sy):
-                    if dx or dy:
-                        if bit(r2, z) != v:
-                            emit_c(la, int(lab[run_at(runstart, rowoff, Z, r2, z)]))
-                        else:
-                            if z > 0 and bit(r2, z - 1) != v:
-                                emit_c(la, int(lab[run_at(runstart, rowoff, Z, r2, z - 1)]))
-                            if z + 1 < Z and bit(r2, z + 1) != v:
-                                emit_c(la, int(lab[run_at(runstart, rowoff, Z, r2, z + 1)]))
-                elif periodic:
-                    j0 = run_at(runstart, rowoff, Z, r2, z)
-                    emit_b(la, int(lab[j0]), (sx, sy, 0))
-                    if z > 0:
-                        j = run_at(runstart, rowoff, Z, r2, z - 1)
-                        if j != j0: emit_b(la, int(lab[j]), (sx, sy, 0))
-                    if z + 1 < Z:
-                        j = run_at(runstart, rowoff, Z, r2, z + 1)
-                        if j != j0: emit_b(la, int(lab[j]), (sx, sy, 0))
-                if periodic and last_in_row:
-                    emit_b(la, int(lab[rowoff[r2]]), (sx, sy, 1))
+            if ny < 0: ny, sy = Y - 1, -1
+            elif ny >= Y: ny, sy = 0, 1
+            wraps = bool(sx or sy)
+            if wraps and not periodic:
+                continue
+            r2 = nx * Y + ny
+            j = run_at(runstart, rowoff, Z, r2, lo)
+            if not wraps:
+                if flat[r2 * Z + lo] == v:
+                    j += 1
+                while j < rowoff[r2 + 1] and runstart[j] <= r2 * Z + hi:
+                    emit_c(la, int(lab[j])); j += 2
+            else:
+                while j < rowoff[r2 + 1] and runstart[j] <= r2 * Z + hi:
+                    emit_b(la, int(lab[j]), (sx, sy, 0)); j += 1
+        if periodic and b == Z - 1:
+            for dx in (-1, 0, 1):
+                nx, sx = x + dx, 0
+                if nx < 0: nx, sx = X - 1, -1
+                elif nx >= X: nx, sx = 0, 1
+                for dy in (-1, 0, 1):
+                    ny, sy = y + dy, 0
+                    if ny < 0: ny, sy = Y - 1, -1
+                    elif ny >= Y: ny, sy = 0, 1
+                    emit_b(la, int(lab[rowoff[nx * Y + ny]]), (sx, sy, 1))
     c = np.array(sorted(contacts), dtype=np.int32).reshape(-1, 2)
     b = np.array(sorted(bridges), dtype=np.int32)
     return c, b

@@ -21,9 +21,11 @@ def test_run_model_matches_golden(name):
     contacts, bridges = rm.pairs(g, runstart, rowoff, lab)
     assert np.array_equal(contacts, c["contacts"].reshape(-1, 2))
     assert np.array_equal(bridges, c["bridges"])
+    # the device-side numbering rule yields the reference's partition (numbering itself is the host's)
     lut, kp, kn = rm.component_lut(bridges, nt, nf)
     comps = lut[labels + nf]
-    assert np.array_equal(comps, c["components"])
+    pairs = np.unique(np.stack([comps.reshape(-1), c["components"].reshape(-1)], 1), axis=0)
+    assert len(pairs) == kp + kn == len(np.unique(c["components"]))
 
 
 def test_run_model_random_shapes():
