@@ -296,40 +296,145 @@ __device__ __forceinline__ uint32_t run_at(const uint32_t *__restrict__ runstart
     return lo;
 }
 
+// per-CTA cache of 64-bit keys in shared memory (dedup in front of global structures)
+#define BLOCKSET_SLOTS 512
+struct BlockSet {
+    unsigned long long slot[BLOCKSET_SLOTS];
+    __device__ void clear() {
+        for (int i = threadIdx.x; i < BLOCKSET_SLOTS; i += blockDim.x) slot[i] = MDVC_KEY_EMPTY;
+    }
+    // true if the key was not yet known to this block (or the block cache is full)
+    __device__ bool add(unsigned long long key) {
+        uint32_t h = (uint32_t)mdvc_mix64(key) & (BLOCKSET_SLOTS - 1);
+        for (int probe = 0; probe < 16; ++probe) {
+            unsigned long long cur = slot[h];
+            if (cur == key) return false;
+            if (cur == MDVC_KEY_EMPTY) {
+                unsigned long long old = atomicCAS(&slot[h], MDVC_KEY_EMPTY, key);
+                if (old == MDVC_KEY_EMPTY) return true;
+                if (old == key) return false;
+            }
+            h = (h + 1) & (BLOCKSET_SLOTS - 1);
+        }
+        return true;
+    }
+};
+
 // ------------------------------------------------------------------------------------------
 // stage 1c: link runs of equal value that are 26-adjacent (no wrap)
 // Two runs [a,b] (row r) and [c,d] (neighbour row r') touch iff c <= b+1 and d >= a-1.  Every
 // unordered pair of neighbouring rows is visited once, from the later row towards its four
 // raster-order predecessors (x-1,y-1) (x-1,y) (x-1,y+1) (x,y-1); the thread of run A walks the runs
-// of the other row that intersect [a-1, b+1] (every second one has A's value).
+// of the other row that intersect [a-1, b+1] (every second one has A's value).  The row pairs are
+// processed in hierarchical rounds (k_link_round) rather than all at once.
 // ------------------------------------------------------------------------------------------
+// Interleaved climb (Rem's scheme): always step the cursor with the larger id; the two paths meet at
+// their lowest common ancestor, so runs that are already connected never travel to the (hot) root of
+// a huge component.  A root is hooked under the smaller cursor with atomicCAS.  Afterwards both start
+// nodes are pointed at the meeting node (valid: it is an ancestor of both, and only non-roots are
+// written with plain stores).
+__device__ __forceinline__ void rem_union(uint32_t *parent, uint32_t a, uint32_t b) {
+    uint32_t x = a, y = b;
+    while (x != y) {
+        if (x > y) {
+            uint32_t px = __ldcg(&parent[x]);
+            if (px == x) {
+                uint32_t old = atomicCAS(&parent[x], x, y);
+                if (old == x) { x = y; break; }
+                px = old;
+            }
+            x = px;
+        } else {
+            uint32_t py = __ldcg(&parent[y]);
+            if (py == y) {
+                uint32_t old = atomicCAS(&parent[y], y, x);
+                if (old == y) { y = x; break; }
+                py = old;
+            }
+            y = py;
+        }
+    }
+    if (a != x && __ldcg(&parent[a]) != x) parent[a] = x;
+    if (b != x && __ldcg(&parent[b]) != x) parent[b] = x;
+}
+
+// One linking round.  phase 0 joins rows (x,y-1) and (x,y), phase 1 joins plane x-1 and plane x
+// (offsets (-1,-1) (-1,0) (-1,+1)).  A round with stride s handles the borders at coordinates c with
+// c % s == 0 and c % (s * LINK_RADIX) != 0, i.e. it merges aligned blocks of s rows / planes in
+// groups of LINK_RADIX, which bounds the tree depth a round can add and keeps the contended roots of
+// a round in disjoint groups.
+// Most adjacent run pairs are redundant (same two trees as their neighbours): each thread climbs
+// read-only to the current roots, and a per-CTA key cache lets only the first (root,root) pair of a
+// CTA go on to the atomic union.
+#define LINK_RADIX 32
+__device__ __forceinline__ uint32_t climb_ro(const uint32_t *parent, uint32_t v) {
+    uint32_t up;
+    while ((up = __ldcg(&parent[v])) != v) v = up;
+    return v;
+}
+
 __global__ void __launch_bounds__(256)
-k_link_runs(const uint32_t *__restrict__ bits, Dims D, const Hdr *__restrict__ h, const uint32_t *__restrict__ rowoff,
-            const uint32_t *__restrict__ runstart, uint32_t *parent) {
+k_link_round(const uint32_t *__restrict__ bits, Dims D, const Hdr *__restrict__ h, const uint32_t *__restrict__ rowoff,
+             const uint32_t *__restrict__ runstart, uint32_t *parent, int phase, int s) {
+    __shared__ BlockSet seen;
+    seen.clear();
+    __syncthreads();
+    if (h->run_eff == 0) return;
+    // few runs per row: one thread per border row; many: 8 lanes share a row
+    const int lpr = h->total_runs > 4ull * (unsigned long long)D.rows ? 8 : 1;
+    const long long gtid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int sub = (int)(gtid % lpr);
+    const long long t = gtid / lpr, nt = ((long long)gridDim.x * blockDim.x) / lpr;
+    const int extent = phase == 0 ? D.Y : D.X;
+    const int cnt = (extent - 1) / s;                       // multiples of s in [s, extent)
+    const long long n_items = phase == 0 ? (long long)D.X * cnt : (long long)cnt * D.Y;
+    for (long long item = t; item < n_items; item += nt) {
+        int x, y, m;
+        if (phase == 0) { x = (int)(item / cnt); m = (int)(item % cnt) + 1; y = m * s; }
+        else { m = (int)(item / D.Y) + 1; x = m * s; y = (int)(item % D.Y); }
+        if (m % LINK_RADIX == 0) continue;                  // border of a later round
+        const uint32_t r = (uint32_t)x * D.Y + y;
+        const uint32_t i1 = rowoff[r + 1];
+        for (uint32_t i = rowoff[r] + sub; i < i1; i += lpr) {
+            uint32_t lin = runstart[i];
+            int a = (int)(lin - r * (uint32_t)D.Z);
+            int b = (int)(runstart[i + 1] - r * (uint32_t)D.Z) - 1;
+            uint32_t v = bit_at(bits, D, r, a);
+            int lo = a > 0 ? a - 1 : 0, hi = b + 1 < D.Z ? b + 1 : D.Z - 1;
+            int dy1 = phase == 0 ? -1 : 1;
+            int nx = phase == 0 ? x : x - 1;
+            uint32_t ra = climb_ro(parent, i);
+            for (int dy = -1; dy <= dy1; ++dy) {
+                int ny = y + dy;
+                if (ny < 0 || ny >= D.Y) continue;
+                uint32_t r2 = (uint32_t)nx * D.Y + ny;
+                uint32_t j = run_at(runstart, rowoff, D, r2, lo);
+                if (bit_at(bits, D, r2, lo) != v) ++j;         // runs alternate: the next one has value v
+                uint32_t end = rowoff[r2 + 1], limit = r2 * (uint32_t)D.Z + (uint32_t)hi;
+                for (; j < end && runstart[j] <= limit; j += 2) {
+                    uint32_t rb = climb_ro(parent, j);
+                    if (ra == rb) continue;
+                    unsigned long long key = ra < rb ? ((unsigned long long)ra << 32) | rb : ((unsigned long long)rb << 32) | ra;
+                    if (!seen.add(key)) continue;              // another thread of this CTA joins these two trees
+                    rem_union(parent, ra, rb);
+                    ra = ra < rb ? ra : rb;                    // still a node of the merged tree; good enough as a start
+                }
+            }
+        }
+    }
+}
+
+// depth -> 1.  Read-only climb; parent[i] is written by thread i alone (see k_flatten_flags).
+__global__ void __launch_bounds__(256)
+k_flatten(const Hdr *__restrict__ h, uint32_t *parent) {
     uint32_t R = h->run_eff;
     uint32_t stride = gridDim.x * blockDim.x;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < R; i += stride) {
-        uint32_t lin = runstart[i];
-        uint32_t r = lin / (uint32_t)D.Z;
-        int a = (int)(lin - r * (uint32_t)D.Z);
-        int b = (int)(runstart[i + 1] - r * (uint32_t)D.Z) - 1;
-        int y = (int)(r % (uint32_t)D.Y), x = (int)(r / (uint32_t)D.Y);
-        uint32_t v = bit_at(bits, D, r, a);
-        int lo = a > 0 ? a - 1 : 0, hi = b + 1 < D.Z ? b + 1 : D.Z - 1;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            int nx = x + (k < 3 ? -1 : 0), ny = y + (k < 3 ? k - 1 : -1);
-            if (nx < 0 || ny < 0 || ny >= D.Y) continue;
-            uint32_t r2 = (uint32_t)nx * D.Y + ny;
-            uint32_t j = run_at(runstart, rowoff, D, r2, lo);
-            if (bit_at(bits, D, r2, lo) != v) ++j;             // runs alternate: the next one has value v
-            uint32_t end = rowoff[r2 + 1], limit = r2 * (uint32_t)D.Z + (uint32_t)hi;
-            for (; j < end && runstart[j] <= limit; j += 2) {
-                // fast path: both already point at the same node (no trip to the hot root's cache line)
-                if (__ldcg(&parent[i]) == __ldcg(&parent[j])) continue;
-                mdvc_uf_union(parent, i, j);
-            }
-        }
+        uint32_t p = __ldcg(&parent[i]);
+        if (p == i) continue;
+        uint32_t root = p, up;
+        while ((up = __ldcg(&parent[root])) != root) root = up;
+        if (root != p) parent[i] = root;
     }
 }
 
@@ -402,29 +507,6 @@ k_assign_labels(const uint32_t *__restrict__ bits, Dims D, const Hdr *__restrict
 // ------------------------------------------------------------------------------------------
 // stage 2: contacts and bridges on runs
 // ------------------------------------------------------------------------------------------
-#define BLOCKSET_SLOTS 512
-struct BlockSet {
-    unsigned long long slot[BLOCKSET_SLOTS];
-    __device__ void clear() {
-        for (int i = threadIdx.x; i < BLOCKSET_SLOTS; i += blockDim.x) slot[i] = MDVC_KEY_EMPTY;
-    }
-    // true if the key was not yet known to this block (or the block cache is full)
-    __device__ bool add(unsigned long long key) {
-        uint32_t h = (uint32_t)mdvc_mix64(key) & (BLOCKSET_SLOTS - 1);
-        for (int probe = 0; probe < 16; ++probe) {
-            unsigned long long cur = slot[h];
-            if (cur == key) return false;
-            if (cur == MDVC_KEY_EMPTY) {
-                unsigned long long old = atomicCAS(&slot[h], MDVC_KEY_EMPTY, key);
-                if (old == MDVC_KEY_EMPTY) return true;
-                if (old == key) return false;
-            }
-            h = (h + 1) & (BLOCKSET_SLOTS - 1);
-        }
-        return true;
-    }
-};
-
 struct PairSink {
     BlockSet *cache;
     unsigned long long *slots;
@@ -763,8 +845,18 @@ extern "C" int mdvc_frame_label(const uint32_t *bits, int X, int Y, int Z, int p
     MDVC_DISPATCH_G(g, (k_fill_runs<G><<<row_grid, 256, 0, st>>>(bits, D, h, rowoff, runstart, parent)));
     MDVC_LAUNCH_CHECK();
     unsigned run_grid = mdvc_grid(caps->max_runs, 256, 8);
-    k_link_runs<<<run_grid, 256, 0, st>>>(bits, D, h, rowoff, runstart, parent);
-    MDVC_LAUNCH_CHECK();
+    for (int phase = 0; phase < 2; ++phase) {
+        int extent = phase == 0 ? D.Y : D.X, other = phase == 0 ? D.X : D.Y;
+        for (long long s = 1; s < extent; s *= LINK_RADIX) {
+            long long items = (long long)other * ((extent - 1) / s);
+            k_link_round<<<mdvc_grid(items, 256, 8), 256, 0, st>>>(bits, D, h, rowoff, runstart, parent, phase, (int)s);
+            MDVC_LAUNCH_CHECK();
+        }
+        if (phase == 0 && D.X > 1 && D.Y > 1) {
+            k_flatten<<<run_grid, 256, 0, st>>>(h, parent);
+            MDVC_LAUNCH_CHECK();
+        }
+    }
     k_flatten_flags<<<run_grid, 256, 0, st>>>(bits, D, h, runstart, parent, scan64);
     MDVC_LAUNCH_CHECK();
     rc = mdvc_exclusive_scan<unsigned long long>(scan64, scan64, &h->run_eff, caps->max_runs,
