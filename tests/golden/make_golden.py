@@ -143,41 +143,23 @@ def dump_binning_cases():
 
 # ---------------------------------------------------------------------------
 def e2e_universes():
-    """name -> (builder returning (universe, selection), kwargs list)."""
+    """name -> (builder returning (universe, selection), kwargs list); inputs shared with the tests."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import e2e_inputs
+
     def complex3d():
-        u = voxels_to_universe(make_complex_3D(11), 1.0)
+        u, sel = e2e_inputs.build("complex3D", make_complex_3D(11))
         gro = os.path.join(refshim.REF_ROOT, "examples/structures/complex3D.gro")
         ug = read_gro(gro)                       # the bundled fixture is exactly this universe
         assert np.array_equal(ug.atoms.positions, u.atoms.positions)
         assert list(ug.atoms.names) == list(u.atoms.names)
         assert np.array_equal(ug.dimensions, u.dimensions)
-        return u, u.select_atoms("name True")
+        return u, sel
 
-    def vesicle(box):
-        def build():
-            pos, dims = synth.vesicle_scene(box_nm=box, seed=7)
-            rng = np.random.default_rng(99)
-            water = np.round(rng.random((len(pos) // 2, 3)) * dims[:3], 2).astype(np.float32)
-            names = ["C"] * len(pos) + ["W"] * len(water)
-            u = Universe(np.concatenate([pos, water]), dims, names)
-            return u, u.select_atoms("name C")
-        return build
-
-    def bicelle():
-        pos, dims, names = synth.bicelle_scene()
-        u = Universe(pos, dims, names)
-        return u, u.select_atoms("name C")
-
-    return {
-        "complex3D": (complex3d, [dict(resolution=1, closing=False), dict(resolution=1, closing=True),
-                                  dict(resolution=0.5, closing=True), dict(resolution=1, morph="dde"),
-                                  dict(resolution=1, closing=False, no_mapping=True, betafactors=False),
-                                  dict(resolution=1, slab=True)]),
-        "vesicle32": (vesicle(32.0), [dict(resolution=0.5, closing=True), dict(resolution=0.5, closing=False),
-                                      dict(resolution=1.0, closing=False)]),
-        "vesicle64": (vesicle(64.0), [dict(resolution=0.5, closing=True)]),
-        "bicelle": (bicelle, [dict(resolution=0.5, closing=True), dict(resolution=1.0)]),
-    }
+    out = {}
+    for name, runs in e2e_inputs.RUNS.items():
+        out[name] = (complex3d if name == "complex3D" else (lambda n=name: e2e_inputs.build(n)), runs)
+    return out
 
 
 def dump_e2e_cases():
