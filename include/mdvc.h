@@ -43,6 +43,8 @@ int mdvc_version(void);
 /* last CUDA error string seen by the calling thread's most recent failing call */
 const char *mdvc_last_error(void);
 int mdvc_row_pitch_words(int Z);
+/* number of CUDA kernels this library has launched so far in the calling process (for benchmarks) */
+unsigned long long mdvc_launch_count(void);
 
 /* ---------------------------------------------------------------------------------------
  * T1  bool grid <-> bit grid        (reference type: dense bool ndarray,

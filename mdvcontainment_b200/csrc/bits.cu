@@ -16,6 +16,8 @@ void mdvc_set_error(const char *where, cudaError_t e) {
 }
 void mdvc_set_error_msg(const char *msg) { snprintf(g_err, sizeof(g_err), "%s", msg); }
 
+unsigned long long g_mdvc_launches = 0;
+extern "C" unsigned long long mdvc_launch_count(void) { return g_mdvc_launches; }
 extern "C" int mdvc_version(void) { return 100; }
 extern "C" const char *mdvc_last_error(void) { return g_err; }
 extern "C" int mdvc_row_pitch_words(int Z) { return ((mdvc_words(Z) + 3) / 4) * 4; }

@@ -22,7 +22,12 @@ void mdvc_set_error_msg(const char *msg);
         }                                                       \
     } while (0)
 
-#define MDVC_LAUNCH_CHECK() MDVC_CUDA_CHECK(cudaGetLastError())
+extern unsigned long long g_mdvc_launches;     // kernels launched by this library (host-side counter)
+#define MDVC_LAUNCH_CHECK()                      \
+    do {                                         \
+        ++g_mdvc_launches;                       \
+        MDVC_CUDA_CHECK(cudaGetLastError());     \
+    } while (0)
 
 static inline int mdvc_num_sms() {
     static int sms = 0;

@@ -1,0 +1,176 @@
+"""Reusable per-shape frame pipeline: bin -> close -> label -> contacts/bridges -> host graph ->
+components/counts, with every device buffer allocated once.
+
+This is what a trajectory driver calls per frame; ``Containment`` builds the same
+stages one object at a time.  Frames are independent, so one pipeline per GPU (one process per GPU)
+shards a trajectory with no cross-GPU traffic.
+"""
+from __future__ import annotations
+
+import ctypes
+import time
+
+import numpy as np
+import torch
+
+from . import _lib, device as dev
+from . import host_graph as hg
+from .atomgroup_to_voxels import voxel_transform
+
+
+class FrameOutput:
+    __slots__ = ("containment_graph", "component_ranks", "voxel_counts", "contacts", "bridges", "n_true", "n_false",
+                 "labels_dev", "components_dev", "bits", "timings")
+
+    def __str__(self):
+        return hg.format_dag_structure(self.containment_graph, self.component_ranks, self.voxel_counts)
+
+
+class FramePipeline:
+    """All device buffers for frames of one box/resolution.
+
+    ``dimensions`` float32[6] (A, deg), ``resolution`` nm.  ``closing`` applies 'de' before ``morph``."""
+
+    HEAD_CONTACT_ROWS = 2048
+    HEAD_BRIDGE_ROWS = 8192
+    HEAD_VOLUMES = 8192
+
+    def __init__(self, dimensions, resolution, closing=True, morph="", periodic=True, max_atoms=0,
+                 write_labels=True, device="cuda"):
+        self.device = torch.device(device)
+        self.dimensions = np.asarray(dimensions, dtype=np.float32)
+        self.resolution = resolution
+        self.ops = ("de" if closing else "") + morph
+        self.periodic = periodic
+        self.write_labels = write_labels
+        _, self.nbox, self.T, self.invT = voxel_transform(self.dimensions, resolution)
+        self.shape = tuple(int(v) for v in np.diagonal(self.nbox))
+        self.bits_a = dev.BitGrid(self.shape, device=self.device)
+        self.bits_b = dev.BitGrid(self.shape, device=self.device) if self.ops else None
+        self.bits_tmp = dev.BitGrid(self.shape, device=self.device) if len(self.ops) > 1 else None
+        self.plan = dev.FramePlan(self.shape, device=self.device)
+        self.labels = torch.empty(self.shape, dtype=torch.int32, device=self.device) if write_labels else None
+        self.components = torch.empty(self.shape, dtype=torch.int32, device=self.device)
+        self.pos_dev = torch.empty((max_atoms, 3), dtype=torch.float32, device=self.device) if max_atoms else None
+        self.lut_dev = None
+        self.lib = _lib.load()
+        self._alloc_host()
+        self.ev = {k: torch.cuda.Event(enable_timing=True) for k in ("e0", "e1")}
+
+    # ---------------------------------------------------------------------------------------
+    def _alloc_host(self):
+        c = self.plan.caps
+        self.n_head_c = min(self.HEAD_CONTACT_ROWS, c.contact_slots)
+        self.n_head_b = min(self.HEAD_BRIDGE_ROWS, c.bridge_slots)
+        self.n_head_v = min(self.HEAD_VOLUMES, c.max_labels)
+        self.h_header = torch.empty(64, dtype=torch.int32).pin_memory()
+        self.h_contacts = torch.empty((self.n_head_c, 2), dtype=torch.int32).pin_memory()
+        self.h_bridges = torch.empty((self.n_head_b, 5), dtype=torch.int32).pin_memory()
+        self.h_volumes = torch.empty(self.n_head_v, dtype=torch.int64).pin_memory()
+        self.h_lut = torch.empty(c.max_labels if c.max_labels < (1 << 20) else (1 << 20), dtype=torch.int32).pin_memory()
+        p = self.plan
+        self.d_header = p.ws[:256].view(torch.int32)
+        self.d_contacts = p._view(p.lib.mdvc_frame_contacts_ptr, torch.int32, self.n_head_c, 2)
+        self.d_bridges = p._view(p.lib.mdvc_frame_bridges_ptr, torch.int32, self.n_head_b, 5)
+        self.d_volumes = p._view(p.lib.mdvc_frame_label_volumes_ptr, torch.int64, self.n_head_v)
+        self.lut_dev = torch.empty(self.h_lut.numel(), dtype=torch.int32, device=self.device)
+
+    def _regrow(self, header):
+        self.plan = self.plan.grown(header)
+        self._alloc_host()
+
+    # ---------------------------------------------------------------------------------------
+    def voxelize(self, positions_dev: torch.Tensor) -> dev.BitGrid:
+        """bin + morph; returns the final bit grid (device)."""
+        self.bits_a.words.zero_()
+        dev.bin_atoms(positions_dev, self.T, self.invT, self.nbox, self.bits_a)
+        if not self.ops:
+            return self.bits_a
+        X, Y, Z = self.shape
+        rc = self.lib.mdvc_morph(self.bits_a.words.data_ptr(), self.bits_b.words.data_ptr(),
+                                 self.bits_tmp.words.data_ptr() if self.bits_tmp is not None else None,
+                                 X, Y, Z, self.bits_a.pitch, self.ops.encode(),
+                                 ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+        _lib.check(rc, "mdvc_morph")
+        return self.bits_b
+
+    def analyse(self, bits: dev.BitGrid) -> FrameOutput:
+        """label -> pairs -> (one sync) host graph -> LUT -> dense write."""
+        t0 = time.perf_counter()
+        while True:
+            self.plan.label(bits)
+            self.plan.pairs(bits, self.periodic)
+            # small results: four async copies into pinned memory, one synchronisation
+            self.h_header.copy_(self.d_header, non_blocking=True)
+            self.h_contacts.copy_(self.d_contacts, non_blocking=True)
+            self.h_bridges.copy_(self.d_bridges, non_blocking=True)
+            self.h_volumes.copy_(self.d_volumes, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+            hdr = self.h_header.numpy()
+            total_runs, n_true, n_false, flags, n_c, n_b = (int(v) for v in hdr[:6].view(np.uint32))
+            if flags == 0:
+                break
+            h = _lib.FrameHeader(total_runs, n_true, n_false, flags, n_c, n_b, 0, 0)
+            self._regrow(h)
+        t1 = time.perf_counter()
+        self.plan.header = _lib.FrameHeader(total_runs, n_true, n_false, 0, n_c, n_b, 0, 0)
+        contacts = self.h_contacts.numpy()[:n_c].copy() if n_c <= self.n_head_c else self.plan.contacts()
+        if not self.periodic:
+            bridges = None
+        elif n_b <= self.n_head_b:
+            bridges = self.h_bridges.numpy()[:n_b].copy() if n_b else np.array([], dtype=np.int32)
+        else:
+            bridges = self.plan.bridges()
+        nl = n_true + n_false + 1
+        volumes = self.h_volumes.numpy()[:nl].copy() if nl <= self.n_head_v else self.plan.label_volumes()
+        uniq = np.concatenate([np.arange(-n_false, 0, dtype=np.int32), np.arange(1, n_true + 1, dtype=np.int32)])
+
+        out = FrameOutput()
+        if self.periodic:
+            sol = hg.solve_periodic(uniq, contacts, bridges)
+            c2l = sol["component2labels"]
+            lut = np.zeros(nl, dtype=np.int32)
+            for comp, labs in c2l.items():
+                lut[np.asarray(labs, dtype=np.int64) + n_false] = comp
+            unique_components = np.array(sorted(int(c) for c in c2l), dtype=np.int32)
+            ccg = sol["component_contact_graph"]
+        else:
+            raise NotImplementedError("slab frames go through VoxelContainment(slab=True)")
+        # LUT to the device and the single dense write
+        if nl <= self.h_lut.numel():
+            self.h_lut[:nl].copy_(torch.from_numpy(lut))
+            self.lut_dev[:nl].copy_(self.h_lut[:nl], non_blocking=True)
+            lut_dev = self.lut_dev[:nl]
+        else:
+            lut_dev = torch.from_numpy(lut).to(self.device)
+        self.plan.set_lut(lut_dev)
+        self.ev["e0"].record()
+        self.plan.expand(bits, self.labels, self.components)
+        self.ev["e1"].record()
+        t2 = time.perf_counter()
+        lo = int(lut.min())
+        acc = np.zeros(int(lut.max()) - lo + 1, dtype=np.int64)
+        np.add.at(acc, lut.astype(np.int64) - lo, volumes)
+        out.voxel_counts = {np.int32(lo + k): np.int64(v) for k, v in enumerate(acc) if v}
+        out.containment_graph = hg.containment_graph(sol["is_contained"], unique_components, ccg)
+        out.component_ranks = sol["component_ranks"]
+        out.contacts, out.bridges, out.n_true, out.n_false = contacts, bridges, n_true, n_false
+        out.labels_dev, out.components_dev, out.bits = self.labels, self.components, bits
+        out.timings = {"device_label_pairs_s": t1 - t0, "host_lut_s": t2 - t1, "host_dag_s": time.perf_counter() - t2}
+        return out
+
+    def run(self, positions_dev: torch.Tensor) -> FrameOutput:
+        return self.analyse(self.voxelize(positions_dev))
+
+    def run_host(self, positions_pinned: torch.Tensor) -> FrameOutput:
+        """Host-resident positions (pinned float32 [n,3]): H2D copy, frame, results on the host."""
+        n = positions_pinned.shape[0]
+        if self.pos_dev is None or self.pos_dev.shape[0] < n:
+            self.pos_dev = torch.empty((n, 3), dtype=torch.float32, device=self.device)
+        self.pos_dev[:n].copy_(positions_pinned, non_blocking=True)
+        return self.run(self.pos_dev[:n])
+
+    def expand_elapsed_ms(self) -> float:
+        """Device time of the last dense write (CUDA events on the launching stream)."""
+        self.ev["e1"].synchronize()
+        return self.ev["e0"].elapsed_time(self.ev["e1"])
