@@ -18,6 +18,7 @@
 #include "common.cuh"
 #include "scan.cuh"
 
+#include <stdlib.h>
 #include <string.h>
 
 // ------------------------------------------------------------------------------------------
@@ -27,7 +28,8 @@ struct Hdr {                       // overlays mdvc_frame_header (64 x uint32)
     uint32_t total_runs, n_true, n_false, flags, n_contacts, n_bridges, n_comp_pos, n_comp_neg;
     uint32_t run_eff;              // runs actually stored (0 when the capacity overflowed)
     uint32_t n_labels;             // n_false + n_true + 1, 0 when the label capacity overflowed
-    uint32_t pad0[2];
+    uint32_t n_strip_roots;        // entries of the strip-root list (interior nodes of the trees)
+    uint32_t pad0[1];
     unsigned long long tot_roots;  // hi32 = False roots, lo32 = True roots
     unsigned long long tot_comps;  // hi32 = negative components, lo32 = positive components
     uint32_t pad1[48];
@@ -375,7 +377,7 @@ __device__ __forceinline__ uint32_t climb_ro(const uint32_t *parent, uint32_t v)
 
 __global__ void __launch_bounds__(256)
 k_link_round(const uint32_t *__restrict__ bits, Dims D, const Hdr *__restrict__ h, const uint32_t *__restrict__ rowoff,
-             const uint32_t *__restrict__ runstart, uint32_t *parent, int phase, int s) {
+             const uint32_t *__restrict__ runstart, uint32_t *parent, int phase, int s, int radix) {
     __shared__ BlockSet seen;
     seen.clear();
     __syncthreads();
@@ -392,7 +394,7 @@ k_link_round(const uint32_t *__restrict__ bits, Dims D, const Hdr *__restrict__ 
         int x, y, m;
         if (phase == 0) { x = (int)(item / cnt); m = (int)(item % cnt) + 1; y = m * s; }
         else { m = (int)(item / D.Y) + 1; x = m * s; y = (int)(item % D.Y); }
-        if (m % LINK_RADIX == 0) continue;                  // border of a later round
+        if (m % radix == 0) continue;                       // border of a later round
         const uint32_t r = (uint32_t)x * D.Y + y;
         const uint32_t i1 = rowoff[r + 1];
         for (uint32_t i = rowoff[r] + sub; i < i1; i += lpr) {
@@ -438,6 +440,247 @@ k_flatten(const Hdr *__restrict__ h, uint32_t *parent) {
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// stage 1c', tile kernels: run lists and union-find of a strip in shared memory
+// ------------------------------------------------------------------------------------------
+// A strip = STRIP_TY consecutive rows of one plane.  Its runs are contiguous in run-id space, so the
+// whole strip is loaded with coalesced reads, linked with a shared-memory union-find (no global
+// round trips) and written back flattened.  Strips whose run count exceeds the shared capacity
+// (noise-like input) fall back to the global-memory walk.  Strip roots are appended to a list: they
+// are the only runs that can become interior tree nodes later, so flattening that short list
+// (k_flatten_list) after each merging round keeps every run within two hops of its root.
+#define STRIP_TY 64
+#define STRIP_CAP 3072
+#define ZMASK 0xffffffu            // packed run entry: (local row << 24) | z   (Z < 2^24, STRIP_TY + 2 < 256)
+
+__device__ __forceinline__ void smem_union(volatile uint32_t *par, uint32_t a, uint32_t b) {
+    uint32_t x = a, y = b;
+    while (x != y) {
+        if (x > y) {
+            uint32_t px = par[x];
+            if (px == x) {
+                uint32_t old = atomicCAS((uint32_t *)&par[x], x, y);
+                if (old == x) break;
+                px = old;
+            }
+            x = px;
+        } else {
+            uint32_t py = par[y];
+            if (py == y) {
+                uint32_t old = atomicCAS((uint32_t *)&par[y], y, x);
+                if (old == y) break;
+                py = old;
+            }
+            y = py;
+        }
+    }
+}
+
+// last index in [n0, n1) whose z-start is <= z (n0 always qualifies: every row starts at z = 0)
+__device__ __forceinline__ uint32_t tile_run_at(const uint32_t *tz, uint32_t n0, uint32_t n1, uint32_t z) {
+    uint32_t lo = n0, hi = n1;
+    while (hi - lo > 1) {
+        uint32_t mid = (lo + hi) >> 1;
+        if ((tz[mid] & ZMASK) <= z) lo = mid; else hi = mid;
+    }
+    return lo;
+}
+
+// global-memory walk of one run against one neighbour row (fallback path and strip borders)
+__device__ __forceinline__ void link_run_vs_row(const uint32_t *__restrict__ bits, const Dims &D,
+                                                const uint32_t *__restrict__ rowoff, const uint32_t *__restrict__ runstart,
+                                                uint32_t *parent, BlockSet &seen, uint32_t i, uint32_t &ra, uint32_t v,
+                                                int lo, int hi, uint32_t r2) {
+    uint32_t j = run_at(runstart, rowoff, D, r2, lo);
+    if (bit_at(bits, D, r2, lo) != v) ++j;
+    uint32_t end = rowoff[r2 + 1], limit = r2 * (uint32_t)D.Z + (uint32_t)hi;
+    for (; j < end && runstart[j] <= limit; j += 2) {
+        uint32_t rb = climb_ro(parent, j);
+        if (ra == rb) continue;
+        unsigned long long key = ra < rb ? ((unsigned long long)ra << 32) | rb : ((unsigned long long)rb << 32) | ra;
+        if (!seen.add(key)) continue;
+        rem_union(parent, ra, rb);
+        ra = ra < rb ? ra : rb;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+k_strip_link(const uint32_t *__restrict__ bits, Dims D, Hdr *h, const uint32_t *__restrict__ rowoff,
+             const uint32_t *__restrict__ runstart, uint32_t *parent, uint32_t *rootlist) {
+    __shared__ uint32_t srow[STRIP_TY + 1];
+    __shared__ uint32_t spol[STRIP_TY];
+    __shared__ uint32_t sz[STRIP_CAP];
+    __shared__ uint32_t spar[STRIP_CAP];
+    __shared__ BlockSet seen;
+    if (h->run_eff == 0) return;
+    const int spp = (D.Y + STRIP_TY - 1) / STRIP_TY;
+    const long long n_strips = (long long)D.X * spp;
+    for (long long sid = blockIdx.x; sid < n_strips; sid += gridDim.x) {
+        const int x = (int)(sid / spp), y0 = (int)(sid % spp) * STRIP_TY;
+        const int ny = min(STRIP_TY, D.Y - y0);
+        const uint32_t r0 = (uint32_t)x * D.Y + y0;
+        __syncthreads();                                   // previous strip fully consumed
+        for (int t = threadIdx.x; t <= ny; t += blockDim.x) {
+            srow[t] = rowoff[r0 + t];
+            if (t < ny) spol[t] = bits[(size_t)(r0 + t) * D.pitch] & 1u;
+        }
+        __syncthreads();
+        const uint32_t gbase = srow[0], nloc = srow[ny] - gbase;
+        if (nloc <= STRIP_CAP) {
+            for (uint32_t k = threadIdx.x; k < nloc; k += blockDim.x) {
+                uint32_t off = runstart[gbase + k] - r0 * (uint32_t)D.Z;
+                uint32_t lr = off / (uint32_t)D.Z;
+                sz[k] = (lr << 24) | (off - lr * (uint32_t)D.Z);
+                spar[k] = k;
+            }
+            __syncthreads();
+            for (uint32_t k = threadIdx.x; k < nloc; k += blockDim.x) {
+                uint32_t e = sz[k], lr = e >> 24;
+                if (lr == 0) continue;
+                uint32_t rb0 = srow[lr] - gbase, re0 = srow[lr + 1] - gbase;      // own row [rb0, re0)
+                int a = (int)(e & ZMASK);
+                int b = (k + 1 < re0) ? (int)(sz[k + 1] & ZMASK) - 1 : D.Z - 1;
+                uint32_t pol = spol[lr] ^ ((k - rb0) & 1u);
+                uint32_t n0 = srow[lr - 1] - gbase, n1 = rb0;                     // previous row [n0, n1)
+                uint32_t lo = a > 0 ? a - 1 : 0, hi = b + 1 < D.Z ? b + 1 : D.Z - 1;
+                uint32_t j = tile_run_at(sz, n0, n1, lo);
+                if ((spol[lr - 1] ^ ((j - n0) & 1u)) != pol) ++j;
+                for (; j < n1 && (sz[j] & ZMASK) <= hi; j += 2) smem_union(spar, k, j);
+            }
+            __syncthreads();
+            for (uint32_t k = threadIdx.x; k < nloc; k += blockDim.x) {
+                uint32_t root = k, up;
+                while ((up = spar[root]) != root) root = up;
+                parent[gbase + k] = gbase + root;
+                if (root == k) rootlist[atomicAdd(&h->n_strip_roots, 1u)] = gbase + k;
+            }
+        } else {
+            // too many runs for shared memory: link the rows of this strip through global memory
+            seen.clear();
+            __syncthreads();
+            for (uint32_t k = threadIdx.x; k < nloc; k += blockDim.x) {
+                uint32_t i = gbase + k;
+                uint32_t lin = runstart[i];
+                uint32_t r = lin / (uint32_t)D.Z;
+                if (r == r0) continue;
+                int a = (int)(lin - r * (uint32_t)D.Z);
+                int b = (int)(runstart[i + 1] - r * (uint32_t)D.Z) - 1;
+                uint32_t v = bit_at(bits, D, r, a);
+                int lo = a > 0 ? a - 1 : 0, hi = b + 1 < D.Z ? b + 1 : D.Z - 1;
+                uint32_t ra = climb_ro(parent, i);
+                link_run_vs_row(bits, D, rowoff, runstart, parent, seen, i, ra, v, lo, hi, r - 1);
+            }
+            // every run of such a strip may end up an interior node: list them all
+            __syncthreads();
+            for (uint32_t k = threadIdx.x; k < nloc; k += blockDim.x) rootlist[atomicAdd(&h->n_strip_roots, 1u)] = gbase + k;
+        }
+    }
+}
+
+// flatten the listed nodes (read-only climb, each entry written by its own thread)
+__global__ void __launch_bounds__(256)
+k_flatten_list(const Hdr *__restrict__ h, const uint32_t *__restrict__ list, uint32_t *parent) {
+    uint32_t n = h->n_strip_roots, stride = gridDim.x * blockDim.x;
+    for (uint32_t e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += stride) {
+        uint32_t g = list[e];
+        uint32_t p = __ldcg(&parent[g]);
+        if (p == g) continue;
+        uint32_t root = p, up;
+        while ((up = __ldcg(&parent[root])) != root) root = up;
+        if (root != p) parent[g] = root;
+    }
+}
+
+// x-phase tile: TY rows of plane x against rows y0-1 .. y0+TY of plane x-1, run lists and current roots
+// in shared memory; only new (root,root) pairs of the CTA reach the global union.
+__global__ void __launch_bounds__(256)
+k_tile_link_x(const uint32_t *__restrict__ bits, Dims D, const Hdr *__restrict__ h, const uint32_t *__restrict__ rowoff,
+              const uint32_t *__restrict__ runstart, uint32_t *parent, int s, int radix) {
+    __shared__ uint32_t orow[STRIP_TY + 1], brow[STRIP_TY + 3];
+    __shared__ uint32_t opol[STRIP_TY], bpol[STRIP_TY + 2];
+    __shared__ uint32_t tz[STRIP_CAP], troot[STRIP_CAP];       // own runs first, then the other plane's
+    __shared__ BlockSet seen;
+    if (h->run_eff == 0) return;
+    const int spp = (D.Y + STRIP_TY - 1) / STRIP_TY;
+    const int cnt = (D.X - 1) / s;
+    const long long n_tiles = (long long)cnt * spp;
+    seen.clear();
+    for (long long tid = blockIdx.x; tid < n_tiles; tid += gridDim.x) {
+        const int m = (int)(tid / spp) + 1, y0 = (int)(tid % spp) * STRIP_TY;
+        if (m % radix == 0) continue;
+        const int x = m * s;
+        const int ny = min(STRIP_TY, D.Y - y0);
+        const int yA = max(y0 - 1, 0), yB = min(y0 + ny, D.Y - 1);           // rows of plane x-1 in reach
+        const int nb = yB - yA + 1;
+        const uint32_t r0 = (uint32_t)x * D.Y + y0, q0 = (uint32_t)(x - 1) * D.Y + yA;
+        __syncthreads();
+        for (int t = threadIdx.x; t <= ny; t += blockDim.x) {
+            orow[t] = rowoff[r0 + t];
+            if (t < ny) opol[t] = bits[(size_t)(r0 + t) * D.pitch] & 1u;
+        }
+        for (int t = threadIdx.x; t <= nb; t += blockDim.x) {
+            brow[t] = rowoff[q0 + t];
+            if (t < nb) bpol[t] = bits[(size_t)(q0 + t) * D.pitch] & 1u;
+        }
+        __syncthreads();
+        const uint32_t go = orow[0], no = orow[ny] - go, gb = brow[0], nbr = brow[nb] - gb;
+        if (no + nbr <= STRIP_CAP) {
+            for (uint32_t k = threadIdx.x; k < no + nbr; k += blockDim.x) {
+                bool own = k < no;
+                uint32_t g = own ? go + k : gb + (k - no);
+                uint32_t base_row = own ? r0 : q0;
+                uint32_t off = runstart[g] - base_row * (uint32_t)D.Z;
+                uint32_t lr = off / (uint32_t)D.Z;
+                tz[k] = (lr << 24) | (off - lr * (uint32_t)D.Z);
+                troot[k] = climb_ro(parent, g);
+            }
+            __syncthreads();
+            for (uint32_t k = threadIdx.x; k < no; k += blockDim.x) {
+                uint32_t e = tz[k], lr = e >> 24;
+                uint32_t rb0 = orow[lr] - go, re0 = orow[lr + 1] - go;
+                int a = (int)(e & ZMASK);
+                int b = (k + 1 < re0) ? (int)(tz[k + 1] & ZMASK) - 1 : D.Z - 1;
+                uint32_t pol = opol[lr] ^ ((k - rb0) & 1u);
+                uint32_t lo = a > 0 ? a - 1 : 0, hi = b + 1 < D.Z ? b + 1 : D.Z - 1;
+                uint32_t ra = troot[k];
+                for (int dy = -1; dy <= 1; ++dy) {
+                    int yy = y0 + (int)lr + dy;
+                    if (yy < 0 || yy >= D.Y) continue;
+                    int bl = yy - yA;                                          // row slot in the other plane
+                    uint32_t n0 = no + (brow[bl] - gb), n1 = no + (brow[bl + 1] - gb);
+                    uint32_t j = tile_run_at(tz, n0, n1, lo);
+                    if ((bpol[bl] ^ ((j - n0) & 1u)) != pol) ++j;
+                    for (; j < n1 && (tz[j] & ZMASK) <= hi; j += 2) {
+                        uint32_t rb = troot[j];
+                        if (ra == rb) continue;
+                        unsigned long long key = ra < rb ? ((unsigned long long)ra << 32) | rb : ((unsigned long long)rb << 32) | ra;
+                        if (!seen.add(key)) continue;
+                        rem_union(parent, ra, rb);
+                        ra = ra < rb ? ra : rb;
+                    }
+                }
+            }
+        } else {
+            for (uint32_t k = threadIdx.x; k < no; k += blockDim.x) {
+                uint32_t i = go + k;
+                uint32_t lin = runstart[i];
+                uint32_t r = lin / (uint32_t)D.Z;
+                int y = (int)(r - (uint32_t)x * D.Y);
+                int a = (int)(lin - r * (uint32_t)D.Z);
+                int b = (int)(runstart[i + 1] - r * (uint32_t)D.Z) - 1;
+                uint32_t v = bit_at(bits, D, r, a);
+                int lo = a > 0 ? a - 1 : 0, hi = b + 1 < D.Z ? b + 1 : D.Z - 1;
+                uint32_t ra = climb_ro(parent, i);
+                for (int dy = -1; dy <= 1; ++dy) {
+                    int yy = y + dy;
+                    if (yy < 0 || yy >= D.Y) continue;
+                    link_run_vs_row(bits, D, rowoff, runstart, parent, seen, i, ra, v, lo, hi, (uint32_t)(x - 1) * D.Y + yy);
+                }
+            }
+        }
+    }
+}
+
 // stage 1d: flatten + root flags (lo32: True root, hi32: False root)
 __global__ void __launch_bounds__(256)
 k_flatten_flags(const uint32_t *__restrict__ bits, Dims D, const Hdr *__restrict__ h,
@@ -472,36 +715,45 @@ __global__ void k_after_root_scan(Hdr *h, uint32_t max_labels) {
 }
 
 // stage 1e: canonical label per run + label volumes
+// Volumes: consecutive runs share very few labels, so each CTA first accumulates into a small
+// shared-memory table (label -> voxels) and flushes it once; labels that do not fit go straight to
+// global atomics (the many-label regime, where contention is low anyway).
+#define VOL_SLOTS 256
 __global__ void __launch_bounds__(256)
 k_assign_labels(const uint32_t *__restrict__ bits, Dims D, const Hdr *__restrict__ h,
                 const uint32_t *__restrict__ runstart, const uint32_t *__restrict__ parent,
                 const unsigned long long *__restrict__ rootrank, int32_t *__restrict__ lab,
                 unsigned long long *vol) {
+    __shared__ int s_key[VOL_SLOTS];
+    __shared__ unsigned long long s_val[VOL_SLOTS];
+    for (int k = threadIdx.x; k < VOL_SLOTS; k += blockDim.x) { s_key[k] = 0; s_val[k] = 0; }
+    __syncthreads();
     uint32_t R = h->run_eff;
     if (h->n_labels == 0) return;
     uint32_t nf = h->n_false;
     uint32_t stride = gridDim.x * blockDim.x;
-    uint32_t rounds = (R + stride - 1) / stride;
-    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    for (uint32_t it = 0; it < rounds; ++it, i += stride) {
-        bool live = i < R;
-        int label = 0;
-        uint32_t len = 0;
-        if (live) {
-            uint32_t lin = runstart[i];
-            uint32_t r = lin / (uint32_t)D.Z;
-            uint32_t v = bit_at(bits, D, r, (int)(lin - r * (uint32_t)D.Z));
-            unsigned long long e = rootrank[parent[i]];
-            label = v ? (int)((uint32_t)(e & 0xffffffffu) + 1u) : -(int)((uint32_t)(e >> 32) + 1u);
-            lab[i] = label;
-            len = runstart[i + 1] - lin;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < R; i += stride) {
+        uint32_t lin = runstart[i];
+        uint32_t r = lin / (uint32_t)D.Z;
+        uint32_t v = bit_at(bits, D, r, (int)(lin - r * (uint32_t)D.Z));
+        unsigned long long e = rootrank[parent[i]];
+        int label = v ? (int)((uint32_t)(e & 0xffffffffu) + 1u) : -(int)((uint32_t)(e >> 32) + 1u);
+        lab[i] = label;
+        unsigned long long len = runstart[i + 1] - lin;
+        // shared table: key 0 = empty (labels are never 0)
+        uint32_t slot = ((uint32_t)label * 2654435761u) >> 24;
+        bool done = false;
+        for (int probe = 0; probe < 8 && !done; ++probe) {
+            int cur = s_key[slot];
+            if (cur == 0) cur = atomicCAS(&s_key[slot], 0, label);
+            if (cur == 0 || cur == label) { atomicAdd(&s_val[slot], len); done = true; }
+            slot = (slot + 1) & (VOL_SLOTS - 1);
         }
-        // warp-aggregated volume accumulation (consecutive runs share very few labels)
-        unsigned peers = __match_any_sync(MDVC_FULL, label);
-        uint32_t sum = __reduce_add_sync(peers, len);
-        if (live && (threadIdx.x & 31) == (__ffs(peers) - 1))
-            atomicAdd(&vol[(long long)label + nf], (unsigned long long)sum);
+        if (!done) atomicAdd(&vol[(long long)label + nf], len);
     }
+    __syncthreads();
+    for (int k = threadIdx.x; k < VOL_SLOTS; k += blockDim.x)
+        if (s_key[k] != 0 && s_val[k]) atomicAdd(&vol[(long long)s_key[k] + nf], s_val[k]);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -845,15 +1097,29 @@ extern "C" int mdvc_frame_label(const uint32_t *bits, int X, int Y, int Z, int p
     MDVC_DISPATCH_G(g, (k_fill_runs<G><<<row_grid, 256, 0, st>>>(bits, D, h, rowoff, runstart, parent)));
     MDVC_LAUNCH_CHECK();
     unsigned run_grid = mdvc_grid(caps->max_runs, 256, 8);
-    for (int phase = 0; phase < 2; ++phase) {
-        int extent = phase == 0 ? D.Y : D.X, other = phase == 0 ? D.X : D.Y;
-        for (long long s = 1; s < extent; s *= LINK_RADIX) {
-            long long items = (long long)other * ((extent - 1) / s);
-            k_link_round<<<mdvc_grid(items, 256, 8), 256, 0, st>>>(bits, D, h, rowoff, runstart, parent, phase, (int)s);
+    // linking: strips in shared memory -> strip borders -> plane borders in radix-LINK_RADIX rounds;
+    // the strip-root list is flattened after every merging round
+    uint32_t *rootlist = reinterpret_cast<uint32_t *>(scan64);
+    {
+        int spp = (D.Y + STRIP_TY - 1) / STRIP_TY;
+        long long n_strips = (long long)D.X * spp;
+        unsigned sgrid = (unsigned)(n_strips < (long long)mdvc_num_sms() * 16 ? n_strips : (long long)mdvc_num_sms() * 16);
+        unsigned lgrid = mdvc_grid(caps->max_runs, 256, 4);
+        k_strip_link<<<sgrid, 256, 0, st>>>(bits, D, h, rowoff, runstart, parent, rootlist);
+        MDVC_LAUNCH_CHECK();
+        if (D.Y > STRIP_TY) {
+            long long items = (long long)D.X * ((D.Y - 1) / STRIP_TY);
+            k_link_round<<<mdvc_grid(items, 256, 8), 256, 0, st>>>(bits, D, h, rowoff, runstart, parent, 0, STRIP_TY, 1 << 30);
+            MDVC_LAUNCH_CHECK();
+            k_flatten_list<<<lgrid, 256, 0, st>>>(h, rootlist, parent);
             MDVC_LAUNCH_CHECK();
         }
-        if (phase == 0 && D.X > 1 && D.Y > 1) {
-            k_flatten<<<run_grid, 256, 0, st>>>(h, parent);
+        for (long long s = 1; s < D.X; s *= LINK_RADIX) {
+            long long tiles = (long long)((D.X - 1) / s) * spp;
+            unsigned tgrid = (unsigned)(tiles < (long long)mdvc_num_sms() * 16 ? tiles : (long long)mdvc_num_sms() * 16);
+            k_tile_link_x<<<tgrid, 256, 0, st>>>(bits, D, h, rowoff, runstart, parent, (int)s, LINK_RADIX);
+            MDVC_LAUNCH_CHECK();
+            k_flatten_list<<<lgrid, 256, 0, st>>>(h, rootlist, parent);
             MDVC_LAUNCH_CHECK();
         }
     }
