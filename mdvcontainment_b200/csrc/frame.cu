@@ -299,15 +299,15 @@ __device__ __forceinline__ uint32_t run_at(const uint32_t *__restrict__ runstart
 }
 
 // per-CTA cache of 64-bit keys in shared memory (dedup in front of global structures)
-#define BLOCKSET_SLOTS 512
-struct BlockSet {
-    unsigned long long slot[BLOCKSET_SLOTS];
+template <int SLOTS>
+struct BlockSetT {
+    unsigned long long slot[SLOTS];
     __device__ void clear() {
-        for (int i = threadIdx.x; i < BLOCKSET_SLOTS; i += blockDim.x) slot[i] = MDVC_KEY_EMPTY;
+        for (int i = threadIdx.x; i < SLOTS; i += blockDim.x) slot[i] = MDVC_KEY_EMPTY;
     }
     // true if the key was not yet known to this block (or the block cache is full)
     __device__ bool add(unsigned long long key) {
-        uint32_t h = (uint32_t)mdvc_mix64(key) & (BLOCKSET_SLOTS - 1);
+        uint32_t h = (((uint32_t)key ^ (uint32_t)(key >> 31)) * 2654435761u >> 16) & (SLOTS - 1);
         for (int probe = 0; probe < 16; ++probe) {
             unsigned long long cur = slot[h];
             if (cur == key) return false;
@@ -316,11 +316,12 @@ struct BlockSet {
                 if (old == MDVC_KEY_EMPTY) return true;
                 if (old == key) return false;
             }
-            h = (h + 1) & (BLOCKSET_SLOTS - 1);
+            h = (h + 1) & (SLOTS - 1);
         }
         return true;
     }
 };
+typedef BlockSetT<256> BlockSet;
 
 // ------------------------------------------------------------------------------------------
 // stage 1c: link runs of equal value that are 26-adjacent (no wrap)
@@ -377,13 +378,13 @@ __device__ __forceinline__ uint32_t climb_ro(const uint32_t *parent, uint32_t v)
 
 __global__ void __launch_bounds__(256)
 k_link_round(const uint32_t *__restrict__ bits, Dims D, const Hdr *__restrict__ h, const uint32_t *__restrict__ rowoff,
-             const uint32_t *__restrict__ runstart, uint32_t *parent, int phase, int s, int radix) {
+             const uint32_t *__restrict__ runstart, uint32_t *parent, int phase, int s, int radix, int force_lpr) {
     __shared__ BlockSet seen;
     seen.clear();
     __syncthreads();
     if (h->run_eff == 0) return;
     // few runs per row: one thread per border row; many: 8 lanes share a row
-    const int lpr = h->total_runs > 4ull * (unsigned long long)D.rows ? 8 : 1;
+    const int lpr = force_lpr ? force_lpr : (h->total_runs > 4ull * (unsigned long long)D.rows ? 8 : 1);
     const long long gtid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const int sub = (int)(gtid % lpr);
     const long long t = gtid / lpr, nt = ((long long)gridDim.x * blockDim.x) / lpr;
@@ -450,7 +451,8 @@ k_flatten(const Hdr *__restrict__ h, uint32_t *parent) {
 // are the only runs that can become interior tree nodes later, so flattening that short list
 // (k_flatten_list) after each merging round keeps every run within two hops of its root.
 #define STRIP_TY 64
-#define STRIP_CAP 3072
+#define STRIP_CAP 2048
+#define TILE_THREADS 128
 #define ZMASK 0xffffffu            // packed run entry: (local row << 24) | z   (Z < 2^24, STRIP_TY + 2 < 256)
 
 __device__ __forceinline__ void smem_union(volatile uint32_t *par, uint32_t a, uint32_t b) {
@@ -504,13 +506,14 @@ __device__ __forceinline__ void link_run_vs_row(const uint32_t *__restrict__ bit
     }
 }
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(TILE_THREADS, 8)
 k_strip_link(const uint32_t *__restrict__ bits, Dims D, Hdr *h, const uint32_t *__restrict__ rowoff,
              const uint32_t *__restrict__ runstart, uint32_t *parent, uint32_t *rootlist) {
     __shared__ uint32_t srow[STRIP_TY + 1];
     __shared__ uint32_t spol[STRIP_TY];
     __shared__ uint32_t sz[STRIP_CAP];
     __shared__ uint32_t spar[STRIP_CAP];
+    __shared__ uint32_t s_nroots, s_base;
     __shared__ BlockSet seen;
     if (h->run_eff == 0) return;
     const int spp = (D.Y + STRIP_TY - 1) / STRIP_TY;
@@ -548,12 +551,18 @@ k_strip_link(const uint32_t *__restrict__ bits, Dims D, Hdr *h, const uint32_t *
                 for (; j < n1 && (sz[j] & ZMASK) <= hi; j += 2) smem_union(spar, k, j);
             }
             __syncthreads();
+            if (threadIdx.x == 0) s_nroots = 0;
+            __syncthreads();
             for (uint32_t k = threadIdx.x; k < nloc; k += blockDim.x) {
                 uint32_t root = k, up;
                 while ((up = spar[root]) != root) root = up;
                 parent[gbase + k] = gbase + root;
-                if (root == k) rootlist[atomicAdd(&h->n_strip_roots, 1u)] = gbase + k;
+                if (root == k) sz[atomicAdd(&s_nroots, 1u)] = gbase + k;     // sz is free again: collect the roots
             }
+            __syncthreads();
+            if (threadIdx.x == 0) s_base = atomicAdd(&h->n_strip_roots, s_nroots);
+            __syncthreads();
+            for (uint32_t k = threadIdx.x; k < s_nroots; k += blockDim.x) rootlist[s_base + k] = sz[k];
         } else {
             // too many runs for shared memory: link the rows of this strip through global memory
             seen.clear();
@@ -593,7 +602,7 @@ k_flatten_list(const Hdr *__restrict__ h, const uint32_t *__restrict__ list, uin
 
 // x-phase tile: TY rows of plane x against rows y0-1 .. y0+TY of plane x-1, run lists and current roots
 // in shared memory; only new (root,root) pairs of the CTA reach the global union.
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(TILE_THREADS, 8)
 k_tile_link_x(const uint32_t *__restrict__ bits, Dims D, const Hdr *__restrict__ h, const uint32_t *__restrict__ rowoff,
               const uint32_t *__restrict__ runstart, uint32_t *parent, int s, int radix) {
     __shared__ uint32_t orow[STRIP_TY + 1], brow[STRIP_TY + 3];
@@ -625,14 +634,26 @@ k_tile_link_x(const uint32_t *__restrict__ bits, Dims D, const Hdr *__restrict__
         __syncthreads();
         const uint32_t go = orow[0], no = orow[ny] - go, gb = brow[0], nbr = brow[nb] - gb;
         if (no + nbr <= STRIP_CAP) {
-            for (uint32_t k = threadIdx.x; k < no + nbr; k += blockDim.x) {
-                bool own = k < no;
-                uint32_t g = own ? go + k : gb + (k - no);
-                uint32_t base_row = own ? r0 : q0;
-                uint32_t off = runstart[g] - base_row * (uint32_t)D.Z;
-                uint32_t lr = off / (uint32_t)D.Z;
-                tz[k] = (lr << 24) | (off - lr * (uint32_t)D.Z);
-                troot[k] = climb_ro(parent, g);
+            // current representative of every run: two hops without verification (after k_flatten_list the
+            // trees are at most two deep; any node of the right tree is a valid union argument anyway)
+            for (uint32_t k0 = threadIdx.x; k0 < no + nbr; k0 += 4 * blockDim.x) {
+                uint32_t g[4], p1[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    uint32_t k = k0 + u * blockDim.x;
+                    g[u] = k < no ? go + k : gb + (k - no);
+                    p1[u] = k < no + nbr ? __ldcg(&parent[g[u]]) : 0u;
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    uint32_t k = k0 + u * blockDim.x;
+                    if (k >= no + nbr) continue;
+                    uint32_t base_row = k < no ? r0 : q0;
+                    uint32_t off = runstart[g[u]] - base_row * (uint32_t)D.Z;
+                    uint32_t lr = off / (uint32_t)D.Z;
+                    tz[k] = (lr << 24) | (off - lr * (uint32_t)D.Z);
+                    troot[k] = __ldcg(&parent[p1[u]]);
+                }
             }
             __syncthreads();
             for (uint32_t k = threadIdx.x; k < no; k += blockDim.x) {
@@ -732,24 +753,35 @@ k_assign_labels(const uint32_t *__restrict__ bits, Dims D, const Hdr *__restrict
     if (h->n_labels == 0) return;
     uint32_t nf = h->n_false;
     uint32_t stride = gridDim.x * blockDim.x;
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < R; i += stride) {
+    uint32_t rounds = (R + stride - 1) / stride;
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    for (uint32_t it = 0; it < rounds; ++it, i += stride) {
+        bool live = i < R;
+        int label = 0;
+        uint32_t len = 0;
+        if (live) {
         uint32_t lin = runstart[i];
         uint32_t r = lin / (uint32_t)D.Z;
         uint32_t v = bit_at(bits, D, r, (int)(lin - r * (uint32_t)D.Z));
         unsigned long long e = rootrank[parent[i]];
-        int label = v ? (int)((uint32_t)(e & 0xffffffffu) + 1u) : -(int)((uint32_t)(e >> 32) + 1u);
+        label = v ? (int)((uint32_t)(e & 0xffffffffu) + 1u) : -(int)((uint32_t)(e >> 32) + 1u);
         lab[i] = label;
-        unsigned long long len = runstart[i + 1] - lin;
+        len = runstart[i + 1] - lin;
+        }
+        // one shared-memory update per distinct label of the warp
+        unsigned peers = __match_any_sync(MDVC_FULL, label);
+        uint32_t sum = __reduce_add_sync(peers, len);
+        if (!live || (threadIdx.x & 31) != (__ffs(peers) - 1)) continue;
         // shared table: key 0 = empty (labels are never 0)
         uint32_t slot = ((uint32_t)label * 2654435761u) >> 24;
         bool done = false;
         for (int probe = 0; probe < 8 && !done; ++probe) {
             int cur = s_key[slot];
             if (cur == 0) cur = atomicCAS(&s_key[slot], 0, label);
-            if (cur == 0 || cur == label) { atomicAdd(&s_val[slot], len); done = true; }
+            if (cur == 0 || cur == label) { atomicAdd(&s_val[slot], (unsigned long long)sum); done = true; }
             slot = (slot + 1) & (VOL_SLOTS - 1);
         }
-        if (!done) atomicAdd(&vol[(long long)label + nf], len);
+        if (!done) atomicAdd(&vol[(long long)label + nf], (unsigned long long)sum);
     }
     __syncthreads();
     for (int k = threadIdx.x; k < VOL_SLOTS; k += blockDim.x)
@@ -765,9 +797,15 @@ struct PairSink {
     uint32_t n_slots;
     uint32_t *flags;
     uint32_t overflow_bit;
-    unsigned long long last;
+    unsigned long long last, last2;       // the two most recent keys of this thread
+    // fast path inline, slow path (block cache + global set) out of line: the pair kernels call this from
+    // ~20 sites and inlining the probing loops there blew the kernel up to 44k instructions
     __device__ __forceinline__ void put(unsigned long long key) {
-        if (key == last) return;
+        if (key == last || key == last2) return;
+        put_slow(key);
+    }
+    __device__ __noinline__ void put_slow(unsigned long long key) {
+        last2 = last;
         last = key;
         if (!cache->add(key)) return;
         if (!mdvc_set_insert(slots, n_slots, key)) atomicOr(flags, overflow_bit);
@@ -789,61 +827,188 @@ __device__ __forceinline__ void emit_bridge(PairSink &s, int la, int lb, int sx,
     }
 }
 
-// One thread per run A = [a,b] of row r.  Row relations are visited once each: the four raster-order
-// predecessor offsets for x/y neighbours (in-box -> contacts, through a face -> bridges with shift
-// (sx,sy,0)), and all nine (dx,dy) for the step through the z-max face (shift (sx,sy,+1)) taken by the
-// last run of the row.  The reverse steps give the same normalised rows (emit_bridge).
-__global__ void __launch_bounds__(256)
-k_run_pairs(const uint32_t *__restrict__ bits, Dims D, Hdr *h, const uint32_t *__restrict__ rowoff,
-            const uint32_t *__restrict__ runstart, const int32_t *__restrict__ lab,
-            unsigned long long *cset, uint32_t c_slots, unsigned long long *bset, uint32_t b_slots, int periodic) {
+// Global-memory version of the pair detection for one run A = [a,b] of row r (fallback for tiles that
+// do not fit shared memory).  Row relations are visited once each: the four raster-order predecessor
+// offsets for x/y neighbours (in-box -> contacts, through a face -> bridges with shift (sx,sy,0)), and
+// all nine (dx,dy) for the step through the z-max face (shift (sx,sy,+1)) taken by the last run of the
+// row.  The reverse steps give the same normalised rows (emit_bridge).
+__device__ __noinline__ void pairs_one_run_global(const uint32_t *__restrict__ bits, const Dims &D, const uint32_t *__restrict__ rowoff,
+                                     const uint32_t *__restrict__ runstart, const int32_t *__restrict__ lab,
+                                     PairSink &cs, PairSink &bs, int periodic, uint32_t i) {
+    uint32_t lin = runstart[i];
+    uint32_t r = lin / (uint32_t)D.Z;
+    int a = (int)(lin - r * (uint32_t)D.Z);
+    int b = (int)(runstart[i + 1] - r * (uint32_t)D.Z) - 1;
+    int y = (int)(r % (uint32_t)D.Y), x = (int)(r / (uint32_t)D.Y);
+    uint32_t v = bit_at(bits, D, r, a);
+    int la = lab[i];
+    if (a > 0) emit_contact(cs, lab[i - 1], la);              // previous run of the same row
+    int lo = a > 0 ? a - 1 : 0, hi = b + 1 < D.Z ? b + 1 : D.Z - 1;
+    for (int k = 0; k < 4; ++k) {
+        int nx = x + (k < 3 ? -1 : 0), ny = y + (k < 3 ? k - 1 : -1), sx = 0, sy = 0;
+        if (nx < 0) { nx = D.X - 1; sx = -1; }
+        if (ny < 0) { ny = D.Y - 1; sy = -1; } else if (ny >= D.Y) { ny = 0; sy = 1; }
+        bool wraps = (sx | sy) != 0;
+        if (wraps && !periodic) continue;
+        uint32_t r2 = (uint32_t)nx * D.Y + ny;
+        uint32_t j = run_at(runstart, rowoff, D, r2, lo);
+        uint32_t end = rowoff[r2 + 1], limit = r2 * (uint32_t)D.Z + (uint32_t)hi;
+        if (!wraps) {                                          // contacts: runs of the other value
+            if (bit_at(bits, D, r2, lo) == v) ++j;
+            for (; j < end && runstart[j] <= limit; j += 2) emit_contact(cs, la, lab[j]);
+        } else {                                               // bridges: every run in reach
+            for (; j < end && runstart[j] <= limit; ++j) emit_bridge(bs, la, lab[j], sx, sy, 0);
+        }
+    }
+    if (periodic && b == D.Z - 1) {                            // steps through the z-max face
+        for (int dx = -1; dx <= 1; ++dx) {
+            int nx = x + dx, sx = 0;
+            if (nx < 0) { nx = D.X - 1; sx = -1; } else if (nx >= D.X) { nx = 0; sx = 1; }
+            for (int dy = -1; dy <= 1; ++dy) {
+                int ny = y + dy, sy = 0;
+                if (ny < 0) { ny = D.Y - 1; sy = -1; } else if (ny >= D.Y) { ny = 0; sy = 1; }
+                emit_bridge(bs, la, lab[rowoff[(uint32_t)nx * D.Y + ny]], sx, sy, 1);
+            }
+        }
+    }
+    if (periodic && a == 0) {
+        // -z steps into the last runs of plane x-1: neighbouring tiles on the shared-memory path rely
+        // on this direction for their dx = +1 relations (see k_tile_pairs)
+        int nx = x - 1, sx = 0;
+        if (nx < 0) { nx = D.X - 1; sx = -1; }
+        for (int dy = -1; dy <= 1; ++dy) {
+            int ny = y + dy, sy = 0;
+            if (ny < 0) { ny = D.Y - 1; sy = -1; } else if (ny >= D.Y) { ny = 0; sy = 1; }
+            emit_bridge(bs, la, lab[rowoff[(uint32_t)nx * D.Y + ny + 1] - 1], sx, sy, -1);
+        }
+    }
+}
+
+// Pair detection on tiles: PT_TY rows of plane x plus their halo rows (y0-1, y0+ny) and the rows
+// y0-1 .. y0+ny of plane x-1 (periodic wrap included) are loaded -- run z-starts and labels -- into
+// shared memory; every lookup of the walk then stays on chip.  Slot = plane * (PT_TY+2) + (yl+1).
+// z-face bridges use both directions so that only planes x and x-1 are needed: the last run of a row
+// steps +z into the first runs of the 6 rows with dx in {0,-1}; the first run steps -z into the last
+// runs of the 3 rows with dx = -1 (the reverse of the dx = +1, +z steps).
+#define PT_TY 64
+#define PT_ROWS (PT_TY + 2)
+#define PT_SLOTS (2 * PT_ROWS)
+#define PT_CAP 2048
+__global__ void __launch_bounds__(TILE_THREADS, 8)
+k_tile_pairs(const uint32_t *__restrict__ bits, Dims D, Hdr *h, const uint32_t *__restrict__ rowoff,
+             const uint32_t *__restrict__ runstart, const int32_t *__restrict__ lab,
+             unsigned long long *cset, uint32_t c_slots, unsigned long long *bset, uint32_t b_slots, int periodic) {
+    __shared__ uint32_t srow[PT_SLOTS], sgb[PT_SLOTS], scnt[PT_SLOTS], soff[PT_SLOTS + 1], spol[PT_SLOTS];
+    __shared__ int ssy[PT_SLOTS];
+    __shared__ uint32_t tz[PT_CAP];
+    __shared__ int32_t tv[PT_CAP];
     __shared__ BlockSet c_cache, b_cache;
     c_cache.clear(); b_cache.clear();
     __syncthreads();
     if (h->n_labels == 0) return;
-    uint32_t R = h->run_eff;
-    PairSink cs{&c_cache, cset, c_slots, &h->flags, MDVC_OVERFLOW_CONTACTS, MDVC_KEY_EMPTY};
-    PairSink bs{&b_cache, bset, b_slots, &h->flags, MDVC_OVERFLOW_BRIDGES, MDVC_KEY_EMPTY};
-    uint32_t stride = gridDim.x * blockDim.x;
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < R; i += stride) {
-        uint32_t lin = runstart[i];
-        uint32_t r = lin / (uint32_t)D.Z;
-        int a = (int)(lin - r * (uint32_t)D.Z);
-        uint32_t next = runstart[i + 1];
-        int b = (int)(next - r * (uint32_t)D.Z) - 1;
-        int y = (int)(r % (uint32_t)D.Y), x = (int)(r / (uint32_t)D.Y);
-        uint32_t v = bit_at(bits, D, r, a);
-        int la = lab[i];
-        if (a > 0) emit_contact(cs, lab[i - 1], la);              // previous run of the same row
-        bool last_in_row = b == D.Z - 1;
-        int lo = a > 0 ? a - 1 : 0, hi = b + 1 < D.Z ? b + 1 : D.Z - 1;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            int nx = x + (k < 3 ? -1 : 0), ny = y + (k < 3 ? k - 1 : -1), sx = 0, sy = 0;
-            if (nx < 0) { nx = D.X - 1; sx = -1; }
-            if (ny < 0) { ny = D.Y - 1; sy = -1; } else if (ny >= D.Y) { ny = 0; sy = 1; }
-            bool wraps = (sx | sy) != 0;
-            if (wraps && !periodic) continue;
-            uint32_t r2 = (uint32_t)nx * D.Y + ny;
-            uint32_t j = run_at(runstart, rowoff, D, r2, lo);
-            uint32_t end = rowoff[r2 + 1], limit = r2 * (uint32_t)D.Z + (uint32_t)hi;
-            if (!wraps) {                                          // contacts: runs of the other value
-                if (bit_at(bits, D, r2, lo) == v) ++j;
-                for (; j < end && runstart[j] <= limit; j += 2) emit_contact(cs, la, lab[j]);
-            } else {                                               // bridges: every run in reach
-                for (; j < end && runstart[j] <= limit; ++j) emit_bridge(bs, la, lab[j], sx, sy, 0);
-            }
+    PairSink cs{&c_cache, cset, c_slots, &h->flags, MDVC_OVERFLOW_CONTACTS, MDVC_KEY_EMPTY, MDVC_KEY_EMPTY};
+    PairSink bs{&b_cache, bset, b_slots, &h->flags, MDVC_OVERFLOW_BRIDGES, MDVC_KEY_EMPTY, MDVC_KEY_EMPTY};
+    const int spp = (D.Y + PT_TY - 1) / PT_TY;
+    const long long n_tiles = (long long)D.X * spp;
+    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int x = (int)(tile / spp), y0 = (int)(tile % spp) * PT_TY;
+        const int ny = min(PT_TY, D.Y - y0);
+        const int sx_other = x == 0 ? -1 : 0;
+        __syncthreads();
+        for (int t = threadIdx.x; t < PT_SLOTS; t += blockDim.x) {
+            int p = t / PT_ROWS, j = t - p * PT_ROWS;
+            int yy = y0 + j - 1, sy = 0;
+            if (yy < 0) { yy = D.Y - 1; sy = -1; } else if (yy >= D.Y) { yy = 0; sy = 1; }
+            int xx = p == 0 ? x : (x == 0 ? D.X - 1 : x - 1);
+            bool wrapped = sy != 0 || (p == 1 && x == 0);
+            bool valid = j <= ny + 1 && (periodic || !wrapped);
+            uint32_t rg = (uint32_t)xx * D.Y + yy;
+            uint32_t g0 = valid ? rowoff[rg] : 0u, g1 = valid ? rowoff[rg + 1] : 0u;
+            srow[t] = rg; sgb[t] = g0; scnt[t] = g1 - g0; ssy[t] = sy;
+            spol[t] = valid ? (bits[(size_t)rg * D.pitch] & 1u) : 0u;
         }
-        if (periodic && last_in_row) {                             // steps through the z-max face
-            for (int dx = -1; dx <= 1; ++dx) {
-                int nx = x + dx, sx = 0;
-                if (nx < 0) { nx = D.X - 1; sx = -1; } else if (nx >= D.X) { nx = 0; sx = 1; }
-                for (int dy = -1; dy <= 1; ++dy) {
-                    int ny = y + dy, sy = 0;
-                    if (ny < 0) { ny = D.Y - 1; sy = -1; } else if (ny >= D.Y) { ny = 0; sy = 1; }
-                    emit_bridge(bs, la, lab[rowoff[(uint32_t)nx * D.Y + ny]], sx, sy, 1);
+        __syncthreads();
+        if (threadIdx.x < 32) {                              // exclusive scan of the slot counts by one warp
+            constexpr int PER = (PT_SLOTS + 31) / 32;
+            uint32_t local[PER], sum = 0;
+#pragma unroll
+            for (int q = 0; q < PER; ++q) {
+                int t = threadIdx.x * PER + q;
+                local[q] = t < PT_SLOTS ? scnt[t] : 0u;
+                sum += local[q];
+            }
+            uint32_t inc = sum;
+            for (int o = 1; o < 32; o <<= 1) {
+                uint32_t up = __shfl_up_sync(MDVC_FULL, inc, o);
+                if ((int)threadIdx.x >= o) inc += up;
+            }
+            uint32_t run = inc - sum;
+#pragma unroll
+            for (int q = 0; q < PER; ++q) {
+                int t = threadIdx.x * PER + q;
+                if (t < PT_SLOTS) soff[t] = run;
+                run += local[q];
+            }
+            if (threadIdx.x == 31) soff[PT_SLOTS] = inc;
+        }
+        __syncthreads();
+        const uint32_t total = soff[PT_SLOTS];
+        const uint32_t own0 = soff[1], own1 = soff[ny + 1];          // own rows yl = 0..ny-1 are slots 1..ny
+        if (total <= PT_CAP) {
+            for (uint32_t k = threadIdx.x; k < total; k += blockDim.x) {
+                uint32_t lo = 0, hi = PT_SLOTS;                      // slot with soff[slot] <= k < soff[slot+1]
+                while (hi - lo > 1) { uint32_t mid = (lo + hi) >> 1; if (soff[mid] <= k) lo = mid; else hi = mid; }
+                uint32_t g = sgb[lo] + (k - soff[lo]);
+                tz[k] = runstart[g] - srow[lo] * (uint32_t)D.Z;
+                tv[k] = lab[g];
+            }
+            __syncthreads();
+            for (uint32_t k = own0 + threadIdx.x; k < own1; k += blockDim.x) {
+                uint32_t lo_s = 1, hi_s = ny + 1;
+                while (hi_s - lo_s > 1) { uint32_t mid = (lo_s + hi_s) >> 1; if (soff[mid] <= k) lo_s = mid; else hi_s = mid; }
+                const int slot = (int)lo_s;
+                const uint32_t rb0 = soff[slot], re0 = soff[slot + 1];
+                const int a = (int)tz[k];
+                const int b = (k + 1 < re0) ? (int)tz[k + 1] - 1 : D.Z - 1;
+                const uint32_t pol = spol[slot] ^ ((k - rb0) & 1u);
+                const int la = tv[k];
+                if (a > 0) emit_contact(cs, tv[k - 1], la);
+                const uint32_t lo = a > 0 ? a - 1 : 0, hi = b + 1 < D.Z ? b + 1 : D.Z - 1;
+                for (int q = 0; q < 4; ++q) {
+                    // q = 0: (0,-1) in the own plane; q = 1..3: (-1, dy = q-2) in the other plane
+                    const int ns = q == 0 ? slot - 1 : PT_ROWS + slot + (q - 2);
+                    const uint32_t n0 = soff[ns], n1 = soff[ns + 1];
+                    if (n0 == n1) continue;
+                    const int sx = q == 0 ? 0 : sx_other, sy = ssy[ns];
+                    uint32_t j = tile_run_at(tz, n0, n1, lo);          // tz holds plain z here (high bits zero)
+                    if (!(sx | sy)) {
+                        if ((spol[ns] ^ ((j - n0) & 1u)) == pol) ++j;
+                        for (; j < n1 && tz[j] <= hi; j += 2) emit_contact(cs, la, tv[j]);
+                    } else {
+                        for (; j < n1 && tz[j] <= hi; ++j) emit_bridge(bs, la, tv[j], sx, sy, 0);
+                    }
+                }
+                if (periodic) {
+                    if (b == D.Z - 1) {
+                        for (int q = 0; q < 6; ++q) {
+                            const int ns = (q < 3 ? 0 : PT_ROWS) + slot + (q % 3) - 1;
+                            if (soff[ns] == soff[ns + 1]) continue;
+                            emit_bridge(bs, la, tv[soff[ns]], q < 3 ? 0 : sx_other, ssy[ns], 1);
+                        }
+                    }
+                    if (a == 0) {
+                        for (int q = 0; q < 3; ++q) {
+                            const int ns = PT_ROWS + slot + q - 1;
+                            if (soff[ns] == soff[ns + 1]) continue;
+                            emit_bridge(bs, la, tv[soff[ns + 1] - 1], sx_other, ssy[ns], -1);
+                        }
+                    }
                 }
             }
+        } else {
+            const uint32_t g0 = sgb[1], g1 = sgb[ny] + scnt[ny];       // own rows are contiguous in run ids
+            for (uint32_t i = g0 + threadIdx.x; i < g1; i += blockDim.x)
+                pairs_one_run_global(bits, D, rowoff, runstart, lab, cs, bs, periodic, i);
         }
     }
 }
@@ -1103,21 +1268,21 @@ extern "C" int mdvc_frame_label(const uint32_t *bits, int X, int Y, int Z, int p
     {
         int spp = (D.Y + STRIP_TY - 1) / STRIP_TY;
         long long n_strips = (long long)D.X * spp;
-        unsigned sgrid = (unsigned)(n_strips < (long long)mdvc_num_sms() * 16 ? n_strips : (long long)mdvc_num_sms() * 16);
+        unsigned sgrid = (unsigned)(n_strips < (long long)mdvc_num_sms() * 32 ? n_strips : (long long)mdvc_num_sms() * 32);
         unsigned lgrid = mdvc_grid(caps->max_runs, 256, 4);
-        k_strip_link<<<sgrid, 256, 0, st>>>(bits, D, h, rowoff, runstart, parent, rootlist);
+        k_strip_link<<<sgrid, TILE_THREADS, 0, st>>>(bits, D, h, rowoff, runstart, parent, rootlist);
         MDVC_LAUNCH_CHECK();
         if (D.Y > STRIP_TY) {
             long long items = (long long)D.X * ((D.Y - 1) / STRIP_TY);
-            k_link_round<<<mdvc_grid(items, 256, 8), 256, 0, st>>>(bits, D, h, rowoff, runstart, parent, 0, STRIP_TY, 1 << 30);
+            k_link_round<<<mdvc_grid(items * 8, 256, 8), 256, 0, st>>>(bits, D, h, rowoff, runstart, parent, 0, STRIP_TY, 1 << 30, 8);
             MDVC_LAUNCH_CHECK();
             k_flatten_list<<<lgrid, 256, 0, st>>>(h, rootlist, parent);
             MDVC_LAUNCH_CHECK();
         }
         for (long long s = 1; s < D.X; s *= LINK_RADIX) {
             long long tiles = (long long)((D.X - 1) / s) * spp;
-            unsigned tgrid = (unsigned)(tiles < (long long)mdvc_num_sms() * 16 ? tiles : (long long)mdvc_num_sms() * 16);
-            k_tile_link_x<<<tgrid, 256, 0, st>>>(bits, D, h, rowoff, runstart, parent, (int)s, LINK_RADIX);
+            unsigned tgrid = (unsigned)(tiles < (long long)mdvc_num_sms() * 32 ? tiles : (long long)mdvc_num_sms() * 32);
+            k_tile_link_x<<<tgrid, TILE_THREADS, 0, st>>>(bits, D, h, rowoff, runstart, parent, (int)s, LINK_RADIX);
             MDVC_LAUNCH_CHECK();
             k_flatten_list<<<lgrid, 256, 0, st>>>(h, rootlist, parent);
             MDVC_LAUNCH_CHECK();
@@ -1148,11 +1313,14 @@ extern "C" int mdvc_frame_pairs(const uint32_t *bits, int X, int Y, int Z, int p
     MDVC_CUDA_CHECK(cudaMemsetAsync(cset, 0xff, (size_t)caps->contact_slots * 8, st));
     MDVC_CUDA_CHECK(cudaMemsetAsync(bset, 0xff, (size_t)caps->bridge_slots * 8, st));
     MDVC_CUDA_CHECK(cudaMemsetAsync(&h->n_contacts, 0, 2 * sizeof(uint32_t), st));
-    unsigned run_grid = mdvc_grid(caps->max_runs, 256, 8);
-    k_run_pairs<<<run_grid, 256, 0, st>>>(bits, D, h, at<uint32_t>(ws, L.rowoff), at<uint32_t>(ws, L.runstart),
-                                          at<int32_t>(ws, L.lab), cset, caps->contact_slots, bset,
-                                          caps->bridge_slots, periodic);
-    MDVC_LAUNCH_CHECK();
+    {
+        long long tiles = (long long)D.X * ((D.Y + PT_TY - 1) / PT_TY);
+        unsigned tgrid = (unsigned)(tiles < (long long)mdvc_num_sms() * 32 ? tiles : (long long)mdvc_num_sms() * 32);
+        k_tile_pairs<<<tgrid, TILE_THREADS, 0, st>>>(bits, D, h, at<uint32_t>(ws, L.rowoff), at<uint32_t>(ws, L.runstart),
+                                            at<int32_t>(ws, L.lab), cset, caps->contact_slots, bset,
+                                            caps->bridge_slots, periodic);
+        MDVC_LAUNCH_CHECK();
+    }
     k_compact_set<<<mdvc_grid(caps->contact_slots, 256, 4), 256, 0, st>>>(cset, caps->contact_slots, ckeys, &h->n_contacts);
     MDVC_LAUNCH_CHECK();
     k_sort_keys<<<1, 1024, 0, st>>>(ckeys, &h->n_contacts, caps->contact_slots);

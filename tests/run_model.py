@@ -1,8 +1,9 @@
 """Host model of the run-based algorithm implemented in csrc/frame.cu (test infrastructure).
 
 It mirrors, step by step and in plain Python, what the kernels do on runs -- start masks, raster
-numbering, the "inspect s-1, s, s+1 from each run start" adjacency rule of k_link_runs and
-k_run_pairs, the min-root union-find numbering and the periodic-component numbering of
+numbering, the "walk the runs of each raster-predecessor row that intersect [a-1, b+1]" adjacency
+rule of the link and pair kernels, the two-directional z-face enumeration of k_tile_pairs, the
+min-root union-find numbering and the periodic-component numbering of
 k_label_lut -- so the *rules* can be validated against the oracle on the CPU box, where no
 kernel can run.  It is not a fallback: the product never imports it.
 """
@@ -135,16 +136,24 @@ def pairs(grid, runstart, rowoff, lab, periodic=True):
             else:
                 while j < rowoff[r2 + 1] and runstart[j] <= r2 * Z + hi:
                     emit_b(la, int(lab[j]), (sx, sy, 0)); j += 1
-        if periodic and b == Z - 1:
-            for dx in (-1, 0, 1):
+        # z faces, both directions, so that only planes x and x-1 are consulted (k_tile_pairs)
+        if periodic and b == Z - 1:                       # +z step from the last run into first runs, dx in {0,-1}
+            for dx in (0, -1):
                 nx, sx = x + dx, 0
                 if nx < 0: nx, sx = X - 1, -1
-                elif nx >= X: nx, sx = 0, 1
                 for dy in (-1, 0, 1):
                     ny, sy = y + dy, 0
                     if ny < 0: ny, sy = Y - 1, -1
                     elif ny >= Y: ny, sy = 0, 1
                     emit_b(la, int(lab[rowoff[nx * Y + ny]]), (sx, sy, 1))
+        if periodic and a == 0:                           # -z step from the first run into last runs, dx = -1
+            nx, sx = x - 1, 0
+            if nx < 0: nx, sx = X - 1, -1
+            for dy in (-1, 0, 1):
+                ny, sy = y + dy, 0
+                if ny < 0: ny, sy = Y - 1, -1
+                elif ny >= Y: ny, sy = 0, 1
+                emit_b(la, int(lab[rowoff[nx * Y + ny + 1] - 1]), (sx, sy, -1))
     c = np.array(sorted(contacts), dtype=np.int32).reshape(-1, 2)
     b = np.array(sorted(bridges), dtype=np.int32)
     return c, b

@@ -235,6 +235,18 @@ def test_noise_grid_vs_oracle(dev):
     assert np.array_equal(vol[vals + h.n_false], cnt)
 
 
+def test_dense_noise_takes_the_global_memory_fallback(dev):
+    """More runs per 64-row strip than the shared-memory tiles hold (random voxels, long rows)."""
+    rng = np.random.default_rng(21)
+    for shape, p in [((6, 70, 256), 0.5), ((3, 130, 320), 0.4), ((40, 3, 700), 0.5)]:
+        g = rng.random(shape) < p
+        bits, plan, h, labels = run_frame(dev, g)
+        want = vo.label_3d_grid(g).astype(np.int32)
+        assert np.array_equal(labels.cpu().numpy(), want), shape
+        assert np.array_equal(plan.contacts(), vo.find_label_contacts_c(want)), shape
+        assert np.array_equal(plan.bridges(), vo.find_bridges_c(want)), shape
+
+
 # ------------------------------------------------------------------------------------------ seam-level grid functions
 @pytest.mark.parametrize("name", [n for n in sorted(CASES) if CASES[n]["has_arrays"]])
 def test_grid_contacts_bridges_match_golden(dev, name):
