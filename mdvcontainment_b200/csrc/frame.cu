@@ -890,11 +890,11 @@ __device__ __noinline__ void pairs_one_run_global(const uint32_t *__restrict__ b
 // z-face bridges use both directions so that only planes x and x-1 are needed: the last run of a row
 // steps +z into the first runs of the 6 rows with dx in {0,-1}; the first run steps -z into the last
 // runs of the 3 rows with dx = -1 (the reverse of the dx = +1, +z steps).
-#define PT_TY 64
+#define PT_TY 128
 #define PT_ROWS (PT_TY + 2)
 #define PT_SLOTS (2 * PT_ROWS)
-#define PT_CAP 2048
-__global__ void __launch_bounds__(TILE_THREADS, 8)
+#define PT_CAP 3072
+__global__ void __launch_bounds__(TILE_THREADS, 5)
 k_tile_pairs(const uint32_t *__restrict__ bits, Dims D, Hdr *h, const uint32_t *__restrict__ rowoff,
              const uint32_t *__restrict__ runstart, const int32_t *__restrict__ lab,
              unsigned long long *cset, uint32_t c_slots, unsigned long long *bset, uint32_t b_slots, int periodic) {
@@ -953,7 +953,6 @@ k_tile_pairs(const uint32_t *__restrict__ bits, Dims D, Hdr *h, const uint32_t *
         }
         __syncthreads();
         const uint32_t total = soff[PT_SLOTS];
-        const uint32_t own0 = soff[1], own1 = soff[ny + 1];          // own rows yl = 0..ny-1 are slots 1..ny
         if (total <= PT_CAP) {
             for (uint32_t k = threadIdx.x; k < total; k += blockDim.x) {
                 uint32_t lo = 0, hi = PT_SLOTS;                      // slot with soff[slot] <= k < soff[slot+1]
@@ -963,45 +962,52 @@ k_tile_pairs(const uint32_t *__restrict__ bits, Dims D, Hdr *h, const uint32_t *
                 tv[k] = lab[g];
             }
             __syncthreads();
-            for (uint32_t k = own0 + threadIdx.x; k < own1; k += blockDim.x) {
-                uint32_t lo_s = 1, hi_s = ny + 1;
-                while (hi_s - lo_s > 1) { uint32_t mid = (lo_s + hi_s) >> 1; if (soff[mid] <= k) lo_s = mid; else hi_s = mid; }
-                const int slot = (int)lo_s;
+            // one thread per own row: its runs are visited in z order, so the position in each of the four
+            // neighbour rows only moves forward (merge walk, no searches); z-face steps once per row
+            for (int slot = 1 + (int)threadIdx.x; slot <= ny; slot += blockDim.x) {
                 const uint32_t rb0 = soff[slot], re0 = soff[slot + 1];
-                const int a = (int)tz[k];
-                const int b = (k + 1 < re0) ? (int)tz[k + 1] - 1 : D.Z - 1;
-                const uint32_t pol = spol[slot] ^ ((k - rb0) & 1u);
-                const int la = tv[k];
-                if (a > 0) emit_contact(cs, tv[k - 1], la);
-                const uint32_t lo = a > 0 ? a - 1 : 0, hi = b + 1 < D.Z ? b + 1 : D.Z - 1;
+                int nsl[4]; uint32_t pj[4], pe[4];
+#pragma unroll
                 for (int q = 0; q < 4; ++q) {
                     // q = 0: (0,-1) in the own plane; q = 1..3: (-1, dy = q-2) in the other plane
-                    const int ns = q == 0 ? slot - 1 : PT_ROWS + slot + (q - 2);
-                    const uint32_t n0 = soff[ns], n1 = soff[ns + 1];
-                    if (n0 == n1) continue;
-                    const int sx = q == 0 ? 0 : sx_other, sy = ssy[ns];
-                    uint32_t j = tile_run_at(tz, n0, n1, lo);          // tz holds plain z here (high bits zero)
-                    if (!(sx | sy)) {
-                        if ((spol[ns] ^ ((j - n0) & 1u)) == pol) ++j;
-                        for (; j < n1 && tz[j] <= hi; j += 2) emit_contact(cs, la, tv[j]);
-                    } else {
-                        for (; j < n1 && tz[j] <= hi; ++j) emit_bridge(bs, la, tv[j], sx, sy, 0);
+                    nsl[q] = q == 0 ? slot - 1 : PT_ROWS + slot + (q - 2);
+                    pj[q] = soff[nsl[q]]; pe[q] = soff[nsl[q] + 1];
+                }
+                const uint32_t pol0 = spol[slot];
+                for (uint32_t k = rb0; k < re0; ++k) {
+                    const int a = (int)tz[k];
+                    const int b = (k + 1 < re0) ? (int)tz[k + 1] - 1 : D.Z - 1;
+                    const uint32_t pol = pol0 ^ ((k - rb0) & 1u);
+                    const int la = tv[k];
+                    if (k > rb0) emit_contact(cs, tv[k - 1], la);
+                    const uint32_t lo = a > 0 ? a - 1 : 0, hi = b + 1 < D.Z ? b + 1 : D.Z - 1;
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        if (pj[q] == pe[q]) continue;
+                        uint32_t j = pj[q];
+                        while (j + 1 < pe[q] && tz[j + 1] <= lo) ++j;      // run containing lo
+                        pj[q] = j;
+                        const int ns = nsl[q];
+                        const int sx = q == 0 ? 0 : sx_other, sy = ssy[ns];
+                        if (!(sx | sy)) {
+                            if ((spol[ns] ^ ((j - soff[ns]) & 1u)) == pol) ++j;
+                            for (; j < pe[q] && tz[j] <= hi; j += 2) emit_contact(cs, la, tv[j]);
+                        } else {
+                            for (; j < pe[q] && tz[j] <= hi; ++j) emit_bridge(bs, la, tv[j], sx, sy, 0);
+                        }
                     }
                 }
                 if (periodic) {
-                    if (b == D.Z - 1) {
-                        for (int q = 0; q < 6; ++q) {
-                            const int ns = (q < 3 ? 0 : PT_ROWS) + slot + (q % 3) - 1;
-                            if (soff[ns] == soff[ns + 1]) continue;
-                            emit_bridge(bs, la, tv[soff[ns]], q < 3 ? 0 : sx_other, ssy[ns], 1);
-                        }
+                    const int la_first = tv[rb0], la_last = tv[re0 - 1];
+                    for (int q = 0; q < 6; ++q) {                          // +z from the last run
+                        const int ns = (q < 3 ? 0 : PT_ROWS) + slot + (q % 3) - 1;
+                        if (soff[ns] == soff[ns + 1]) continue;
+                        emit_bridge(bs, la_last, tv[soff[ns]], q < 3 ? 0 : sx_other, ssy[ns], 1);
                     }
-                    if (a == 0) {
-                        for (int q = 0; q < 3; ++q) {
-                            const int ns = PT_ROWS + slot + q - 1;
-                            if (soff[ns] == soff[ns + 1]) continue;
-                            emit_bridge(bs, la, tv[soff[ns + 1] - 1], sx_other, ssy[ns], -1);
-                        }
+                    for (int q = 0; q < 3; ++q) {                          // -z from the first run
+                        const int ns = PT_ROWS + slot + q - 1;
+                        if (soff[ns] == soff[ns + 1]) continue;
+                        emit_bridge(bs, la_first, tv[soff[ns + 1] - 1], sx_other, ssy[ns], -1);
                     }
                 }
             }

@@ -125,3 +125,26 @@ def test_seam_functions_are_numpy_in_numpy_out():
     assert grid.dtype == np.bool_ and np.array_equal(grid, VOX["complex3D_roll11"]["grid"])
     assert set(mapping.keys()) == {"atom_voxels", "voxel_to_atoms", "atom_indices"}
     assert sum(len(v) for v in mapping["voxel_to_atoms"].values()) == len(sel)
+
+
+def test_frame_pipeline_and_trajectory_driver_match_containment():
+    """The reusable per-shape pipeline (bench / trajectory path) gives the same DAG as Containment."""
+    import torch
+    from mdvcontainment_b200 import Containment, synth
+    from mdvcontainment_b200.pipeline import FramePipeline
+    from mdvcontainment_b200.trajectory import run_trajectory
+    from mdvcontainment_b200.universe import Universe
+    frames = [synth.trajectory_frame(f, box_nm=24.0) for f in range(3)]
+    dims = frames[0][1]
+    pipe = FramePipeline(dims, 0.5, closing=True)
+    res = run_trajectory([p for p, _ in frames], dims, 0.5, closing=True)
+    for f, (pos, _) in enumerate(frames):
+        u = Universe(pos.copy(), dims)
+        c, _ = quiet(Containment, u.atoms, 0.5, closing=True, no_mapping=True, betafactors=False)
+        vc = c.voxel_containment
+        out = pipe.run(torch.from_numpy(pos).cuda())
+        assert str(out) == str(vc)
+        assert np.array_equal(out.components_dev.cpu().numpy(), vc.components_grid)
+        assert np.array_equal(out.labels_dev.cpu().numpy(), vc.nonp_labeled_grid_device.cpu().numpy())
+        assert res[f]["str"] == str(vc)
+        assert res[f]["counts"] == {int(k): int(v) for k, v in vc.voxel_counts.items()}
