@@ -185,12 +185,15 @@ def run_ours(args):
     size = args.size
     pos, dims = synth.vesicle_scene(box_nm=size / 2.0, seed=7 + rank)      # every rank its own frame
     n_atoms = len(pos)
-    pipe = FramePipeline(dims, 0.5, closing=True, max_atoms=n_atoms)
+    n_flight = max(1, args.in_flight)
+    pipes = [FramePipeline(dims, 0.5, closing=True, max_atoms=n_atoms) for _ in range(n_flight)]
+    pipe = pipes[0]
     assert pipe.shape == (size, size, size), pipe.shape
     N = size ** 3
     pos_pinned = torch.from_numpy(pos).pin_memory()
     pos_dev = torch.from_numpy(pos).cuda()
     lib = _lib.load()
+    torch.cuda.synchronize()
 
     def barrier():
         torch.cuda.synchronize()
@@ -198,16 +201,36 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, steps):
-        """EXACTLY `steps` calls between barriers; device time by CUDA events, max over ranks."""
+    out = None
+
+    def run_frames(steps, host):
+        """`steps` frames with up to n_flight frames in flight: frame i's device stages are enqueued before frame
+        i-1's host graph stage runs, so the GPU is never idle waiting for the host."""
+        nonlocal out
+        pending = []
+        for i in range(steps):
+            p = pipes[i % n_flight]
+            if len(pending) == n_flight:
+                out = pending.pop(0).finish()
+            if host:
+                p.begin(None, host_positions=pos_pinned)
+            else:
+                p.begin(pos_dev)
+            pending.append(p)
+        while pending:
+            out = pending.pop(0).finish()
+
+    def timed(steps, host):
+        """EXACTLY `steps` frames between barriers; device time by CUDA events, max over ranks."""
+        for p in pipes:
+            p.expand_elapsed_ms()
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         l0 = lib.mdvc_launch_count()
-        expand_ms = 0.0
         e0.record()
-        for _ in range(steps):
-            fn()
-            expand_ms += pipe.expand_elapsed_ms()
+        run_frames(steps, host)
+        for p in pipes:                                   # the default-stream end event must follow all pipelines
+            torch.cuda.current_stream().wait_stream(p.stream)
         e1.record()
         barrier()
         ms = e0.elapsed_time(e1)
@@ -215,28 +238,18 @@ def run_ours(args):
             t = torch.tensor([ms], device="cuda")
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms = float(t.item())
-        return ms, lib.mdvc_launch_count() - l0, expand_ms / steps
+        em = [p.expand_elapsed_ms() for p in pipes]
+        em = [v for v in em if v > 0]
+        return ms, lib.mdvc_launch_count() - l0, sum(em) / max(1, len(em))
 
-    out = None
-
-    def frame_device():
-        nonlocal out
-        out = pipe.run(pos_dev)
-
-    def frame_host():
-        nonlocal out
-        out = pipe.run_host(pos_pinned)
-
-    for _ in range(args.warmup):
-        frame_device()
+    run_frames(args.warmup, False)
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    ms_dev, launches, expand_ms = timed(frame_device, args.steps)
+    ms_dev, launches, expand_ms = timed(args.steps, False)
     clocks = sampler.stop() if rank == 0 else None
-    for _ in range(max(1, args.warmup // 2)):
-        frame_host()
-    ms_e2e, _, _ = timed(frame_host, args.steps)
+    run_frames(max(1, args.warmup // 2), True)
+    ms_e2e, _, _ = timed(args.steps, True)
 
     if rank != 0:
         if world > 1:
@@ -258,6 +271,7 @@ def run_ours(args):
                                "closing=True, periodic, labels+components grids written, one frame per step per GPU",
                    "grid": [size] * 3, "atoms": n_atoms, "frames_per_gpu_per_step": 1,
                    "l2": f"no flush: each step streams {frame_bytes / 1e9:.2f} GB (> 126 MB L2)",
+                   "frames_in_flight_per_gpu": n_flight,
                    "parallelism": f"frames sharded over {world} GPU(s), no collective on the data path"},
         "gvoxel_per_s": value * N / 1e9,
         "frame_algorithmic_gbs": frame_bytes * value / world / 1e9,
@@ -267,7 +281,7 @@ def run_ours(args):
                      "algorithmic_bytes_per_launch": expand_bytes, "avg_launch_ms": expand_ms},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(n_atoms * 12),
                 "d2h_bytes_per_step": int(small_d2h), "ms_per_step": ms_e2e / args.steps,
-                "call": "FramePipeline.run_host(pinned positions) -> containment DAG, ranks, counts on the host"},
+                "call": "FramePipeline.begin(host_positions=pinned) / finish() -> containment DAG, ranks, counts on the host"},
         "gpu_launches": int(launches),
         "clocks": clocks,
         "result": {"components": len(out.voxel_counts), "n_true": out.n_true, "n_false": out.n_false,
@@ -308,6 +322,7 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=256, help="grid side of the bounded CPU sample")
     ap.add_argument("--cpu-procs", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--in-flight", type=int, default=2, help="frames in flight per GPU (pipelines on separate streams)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

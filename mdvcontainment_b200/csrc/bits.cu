@@ -106,7 +106,15 @@ struct BinParams {
     long long nbox[9];
 };
 
+// Python floor division a // b for b > 0.  Atoms are almost always inside the box or one image away, so
+// the 64-bit division (hundreds of instructions on the GPU) is kept for the rare far-away atom only.
 __device__ __forceinline__ long long floordiv_ll(long long a, long long b) {
+    if (a >= 0) {
+        if (a < b) return 0;
+        if (a < 2 * b) return 1;
+    } else if (a >= -b) {
+        return -1;
+    }
     long long q = a / b, r = a % b;
     return (r != 0 && ((r < 0) != (b < 0))) ? q - 1 : q;
 }
@@ -125,7 +133,7 @@ k_bin_atoms(const float *__restrict__ pos, long long n, BinParams P, uint32_t *_
         long long v[3] = {0, 0, 0};
         double f[3];
         if (live) {
-            double p0 = (double)pos[3 * i], p1 = (double)pos[3 * i + 1], p2 = (double)pos[3 * i + 2];
+            double p0 = (double)__ldcs(pos + 3 * i), p1 = (double)__ldcs(pos + 3 * i + 1), p2 = (double)__ldcs(pos + 3 * i + 2);
 #pragma unroll
             for (int j = 0; j < 3; ++j) {
                 double fj = __fma_rn(p2, P.T[6 + j], __fma_rn(p1, P.T[3 + j], __dmul_rn(p0, P.T[j])));

@@ -123,9 +123,19 @@ struct RowWalker {
         if (w == 0) S |= 1u;
         return S & mdvc_valid_mask(w, Z);
     }
-    // exclusive count of starts before this lane's word (whole row so far); advances the carry
+    // exclusive count of starts before this lane's word (whole row so far); advances the carry.
+    // Smooth grids have at most one start per word: then two ballots replace the shuffle scan.
     __device__ __forceinline__ uint32_t exclusive(uint32_t S, int gl) {
-        uint32_t cnt = __popc(S), inc = cnt;
+        uint32_t cnt = __popc(S);
+        const int gshift = ((threadIdx.x & 31) / G) * G;
+        const uint32_t gmask = G == 32 ? 0xffffffffu : ((1u << G) - 1u);
+        if (__ballot_sync(MDVC_FULL, cnt > 1) == 0) {
+            uint32_t has = (__ballot_sync(MDVC_FULL, cnt != 0) >> gshift) & gmask;
+            uint32_t ex = run_carry + __popc(has & ((1u << gl) - 1u));
+            run_carry += __popc(has);
+            return ex;
+        }
+        uint32_t inc = cnt;
 #pragma unroll
         for (int o = 1; o < G; o <<= 1) {
             uint32_t t = __shfl_up_sync(MDVC_FULL, inc, o, G);
@@ -134,6 +144,23 @@ struct RowWalker {
         uint32_t ex = run_carry + inc - cnt;
         run_carry += __shfl_sync(MDVC_FULL, inc, G - 1, G);
         return ex;
+    }
+    // number of starts in the whole row (single-chunk rows)
+    __device__ __forceinline__ uint32_t row_total(uint32_t S) {
+        uint32_t cnt = __popc(S);
+        if (G == 32) return __reduce_add_sync(MDVC_FULL, cnt);
+        uint32_t total = cnt;
+#pragma unroll
+        for (int o = G / 2; o > 0; o >>= 1) total += __shfl_xor_sync(MDVC_FULL, total, o, G);
+        return total;
+    }
+    // start mask of a row that fits one chunk (no carry between chunks)
+    __device__ __forceinline__ uint32_t starts_single(uint32_t B, int w, int Z, int gl) {
+        uint32_t prev = __shfl_up_sync(MDVC_FULL, B, 1, G) >> 31;
+        if (gl == 0) prev = 0;
+        uint32_t S = B ^ ((B << 1) | prev);
+        if (w == 0) S |= 1u;
+        return S & mdvc_valid_mask(w, Z);
     }
 };
 
@@ -177,9 +204,7 @@ k_count_runs(const uint32_t *__restrict__ bits, Dims D, uint32_t *__restrict__ r
             for (int u = 0; u < U; ++u) {
                 long long row = rb + u * GPW + gi;
                 RowWalker<G> rw; rw.begin();
-                uint32_t total = __popc(rw.starts(B[u], gl, D.Z, gl));
-#pragma unroll
-                for (int o = G / 2; o > 0; o >>= 1) total += __shfl_down_sync(MDVC_FULL, total, o, G);
+                uint32_t total = rw.row_total(rw.starts_single(B[u], gl, D.Z, gl));
                 if (row < D.rows && gl == 0) runcount[row] = total;
             }
         }
@@ -239,7 +264,7 @@ k_fill_runs(const uint32_t *__restrict__ bits, Dims D, const Hdr *__restrict__ h
             for (int u = 0; u < U; ++u) {
                 long long row = rb + u * GPW + gi;
                 RowWalker<G> rw; rw.begin();
-                uint32_t S = rw.starts(B[u], gl, D.Z, gl);
+                uint32_t S = rw.starts_single(B[u], gl, D.Z, gl);
                 uint32_t id = base[u] + rw.exclusive(S, gl);
                 uint32_t lin0 = (uint32_t)(row * D.Z) + (uint32_t)(gl << 5);
                 if (row >= D.rows) S = 0;
@@ -954,12 +979,17 @@ k_tile_pairs(const uint32_t *__restrict__ bits, Dims D, Hdr *h, const uint32_t *
         __syncthreads();
         const uint32_t total = soff[PT_SLOTS];
         if (total <= PT_CAP) {
-            for (uint32_t k = threadIdx.x; k < total; k += blockDim.x) {
-                uint32_t lo = 0, hi = PT_SLOTS;                      // slot with soff[slot] <= k < soff[slot+1]
-                while (hi - lo > 1) { uint32_t mid = (lo + hi) >> 1; if (soff[mid] <= k) lo = mid; else hi = mid; }
-                uint32_t g = sgb[lo] + (k - soff[lo]);
-                tz[k] = runstart[g] - srow[lo] * (uint32_t)D.Z;
-                tv[k] = lab[g];
+            for (int t = threadIdx.x; t < PT_SLOTS; t += blockDim.x) {    // one thread copies one row (few runs each)
+                const uint32_t cnt = scnt[t], g0 = sgb[t], o = soff[t], zb = srow[t] * (uint32_t)D.Z;
+                for (uint32_t k = 0; k < cnt; k += 4) {
+                    uint32_t v[4]; int32_t l[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u)
+                        if (k + u < cnt) { v[u] = runstart[g0 + k + u]; l[u] = lab[g0 + k + u]; }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u)
+                        if (k + u < cnt) { tz[o + k + u] = v[u] - zb; tv[o + k + u] = l[u]; }
+                }
             }
             __syncthreads();
             // one thread per own row: its runs are visited in z order, so the position in each of the four

@@ -55,7 +55,10 @@ class FramePipeline:
         self.lut_dev = None
         self.lib = _lib.load()
         self._alloc_host()
-        self.ev = {k: torch.cuda.Event(enable_timing=True) for k in ("e0", "e1")}
+        self.stream = torch.cuda.Stream(device=self.device)      # every launch of this pipeline goes here
+        self.ev_stage1 = torch.cuda.Event()
+        self.expand_events = []                                   # (start, end) of every dense write
+        self._bits = None
 
     # ---------------------------------------------------------------------------------------
     def _alloc_host(self):
@@ -94,24 +97,55 @@ class FramePipeline:
         _lib.check(rc, "mdvc_morph")
         return self.bits_b
 
+    def _enqueue_stage1(self, bits: dev.BitGrid):
+        self.plan.label(bits)
+        self.plan.pairs(bits, self.periodic)
+        # small results: four async copies into pinned memory, waited for in finish()
+        self.h_header.copy_(self.d_header, non_blocking=True)
+        self.h_contacts.copy_(self.d_contacts, non_blocking=True)
+        self.h_bridges.copy_(self.d_bridges, non_blocking=True)
+        self.h_volumes.copy_(self.d_volumes, non_blocking=True)
+        self.ev_stage1.record()
+
+    def begin(self, positions_dev: torch.Tensor, host_positions: torch.Tensor | None = None):
+        """Enqueue bin -> morph -> label -> pairs and the small read-backs on this pipeline's stream; returns
+        immediately so the caller can finish() another pipeline's frame meanwhile."""
+        self._t0 = time.perf_counter()
+        with torch.cuda.stream(self.stream):
+            if host_positions is not None:
+                n = host_positions.shape[0]
+                if self.pos_dev is None or self.pos_dev.shape[0] < n:
+                    self.pos_dev = torch.empty((n, 3), dtype=torch.float32, device=self.device)
+                self.pos_dev[:n].copy_(host_positions, non_blocking=True)
+                positions_dev = self.pos_dev[:n]
+            self._bits = self.voxelize(positions_dev)
+            self._enqueue_stage1(self._bits)
+
+    def finish(self) -> FrameOutput:
+        """Wait for the small results, run the host graph stage, upload the LUT, enqueue the dense write."""
+        bits = self._bits
+        with torch.cuda.stream(self.stream):
+            out = self._finish(bits)
+        torch.cuda.current_stream().wait_stream(self.stream)     # the caller's stream sees the finished grids
+        return out
+
     def analyse(self, bits: dev.BitGrid) -> FrameOutput:
-        """label -> pairs -> (one sync) host graph -> LUT -> dense write."""
-        t0 = time.perf_counter()
+        """label -> pairs -> (one sync) host graph -> LUT -> dense write, on the current stream."""
+        self._t0 = time.perf_counter()
+        self._enqueue_stage1(bits)
+        return self._finish(bits)
+
+    def _finish(self, bits: dev.BitGrid) -> FrameOutput:
+        t0 = self._t0
         while True:
-            self.plan.label(bits)
-            self.plan.pairs(bits, self.periodic)
-            # small results: four async copies into pinned memory, one synchronisation
-            self.h_header.copy_(self.d_header, non_blocking=True)
-            self.h_contacts.copy_(self.d_contacts, non_blocking=True)
-            self.h_bridges.copy_(self.d_bridges, non_blocking=True)
-            self.h_volumes.copy_(self.d_volumes, non_blocking=True)
-            torch.cuda.current_stream().synchronize()
+            self.ev_stage1.synchronize()
             hdr = self.h_header.numpy()
             total_runs, n_true, n_false, flags, n_c, n_b = (int(v) for v in hdr[:6].view(np.uint32))
             if flags == 0:
                 break
             h = _lib.FrameHeader(total_runs, n_true, n_false, flags, n_c, n_b, 0, 0)
             self._regrow(h)
+            self._enqueue_stage1(bits)
         t1 = time.perf_counter()
         self.plan.header = _lib.FrameHeader(total_runs, n_true, n_false, 0, n_c, n_b, 0, 0)
         contacts = self.h_contacts.numpy()[:n_c].copy() if n_c <= self.n_head_c else self.plan.contacts()
@@ -144,9 +178,11 @@ class FramePipeline:
         else:
             lut_dev = torch.from_numpy(lut).to(self.device)
         self.plan.set_lut(lut_dev)
-        self.ev["e0"].record()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
         self.plan.expand(bits, self.labels, self.components)
-        self.ev["e1"].record()
+        e1.record()
+        self.expand_events.append((e0, e1))
         t2 = time.perf_counter()
         lo = int(lut.min())
         acc = np.zeros(int(lut.max()) - lo + 1, dtype=np.int64)
@@ -160,17 +196,19 @@ class FramePipeline:
         return out
 
     def run(self, positions_dev: torch.Tensor) -> FrameOutput:
-        return self.analyse(self.voxelize(positions_dev))
+        self.begin(positions_dev)
+        return self.finish()
 
     def run_host(self, positions_pinned: torch.Tensor) -> FrameOutput:
         """Host-resident positions (pinned float32 [n,3]): H2D copy, frame, results on the host."""
-        n = positions_pinned.shape[0]
-        if self.pos_dev is None or self.pos_dev.shape[0] < n:
-            self.pos_dev = torch.empty((n, 3), dtype=torch.float32, device=self.device)
-        self.pos_dev[:n].copy_(positions_pinned, non_blocking=True)
-        return self.run(self.pos_dev[:n])
+        self.begin(None, host_positions=positions_pinned)
+        return self.finish()
 
     def expand_elapsed_ms(self) -> float:
-        """Device time of the last dense write (CUDA events on the launching stream)."""
-        self.ev["e1"].synchronize()
-        return self.ev["e0"].elapsed_time(self.ev["e1"])
+        """Mean device time of the dense writes recorded since the last call (CUDA events on the launching stream)."""
+        if not self.expand_events:
+            return 0.0
+        self.stream.synchronize()
+        ms = [a.elapsed_time(b) for a, b in self.expand_events]
+        self.expand_events = []
+        return sum(ms) / len(ms)
