@@ -121,15 +121,13 @@ __device__ __forceinline__ long long floordiv_ll(long long a, long long b) {
 
 // One thread per atom.  float64 products as the FMA chain fma(p2,T2j, fma(p1,T1j, p0*T0j)) --
 // bit-identical to the reference's NumPy/OpenBLAS dgemm; __dmul_rn/__fma_rn keep
-// the compiler from contracting differently.  Lanes of a warp that hit the same occupancy word
-// are merged with __match_any_sync so one lane issues the atomicOr.
+// the compiler from contracting differently.
 __global__ void __launch_bounds__(256)
 k_bin_atoms(const float *__restrict__ pos, long long n, BinParams P, uint32_t *__restrict__ occ, int pitch,
             int32_t *__restrict__ vox_out, float *pos_out) {
     long long stride = (long long)gridDim.x * blockDim.x;
-    long long nround = ((n + 31) / 32) * 32;             // keep warps converged for the match
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nround; i += stride) {
-        bool live = i < n;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const bool live = true;
         long long v[3] = {0, 0, 0};
         double f[3];
         if (live) {
@@ -141,11 +139,27 @@ k_bin_atoms(const float *__restrict__ pos, long long n, BinParams P, uint32_t *_
                 v[j] = (long long)fl;
                 f[j] = __dsub_rn(fj, (double)v[j]);
             }
+            const long long lim = 1ll << 28;
+            if (v[0] > -lim && v[0] < lim && v[1] > -lim && v[1] < lim && v[2] > -lim && v[2] < lim && P.nbox[0] < lim &&
+                P.nbox[4] < lim && P.nbox[8] < lim) {
+                // everything fits 32 bits (any realistic box): same arithmetic without 64-bit multiplies/divides
+                int w3[3] = {(int)v[0], (int)v[1], (int)v[2]};
 #pragma unroll
-            for (int dim = 2; dim >= 0; --dim) {
-                long long s = floordiv_ll(v[dim], P.nbox[4 * dim]);
+                for (int dim = 2; dim >= 0; --dim) {
+                    int n = (int)P.nbox[4 * dim], a = w3[dim], sh;
+                    if (a >= 0) sh = a < n ? 0 : (a < 2 * n ? 1 : a / n);
+                    else sh = a >= -n ? -1 : -((-a + n - 1) / n);
 #pragma unroll
-                for (int j = 0; j < 3; ++j) v[j] -= s * P.nbox[3 * dim + j];
+                    for (int j = 0; j < 3; ++j) w3[j] -= sh * (int)P.nbox[3 * dim + j];
+                }
+                v[0] = w3[0]; v[1] = w3[1]; v[2] = w3[2];
+            } else {
+#pragma unroll
+                for (int dim = 2; dim >= 0; --dim) {
+                    long long s = floordiv_ll(v[dim], P.nbox[4 * dim]);
+#pragma unroll
+                    for (int j = 0; j < 3; ++j) v[j] -= s * P.nbox[3 * dim + j];
+                }
             }
             if (vox_out) {
                 vox_out[3 * i] = (int32_t)v[0]; vox_out[3 * i + 1] = (int32_t)v[1]; vox_out[3 * i + 2] = (int32_t)v[2];
@@ -159,22 +173,15 @@ k_bin_atoms(const float *__restrict__ pos, long long n, BinParams P, uint32_t *_
                                                 __fma_rn(g1, P.invT[3 + j], __dmul_rn(g0, P.invT[j])));
             }
         }
-        if (occ) {
+        if (occ && live) {
             long long X = P.nbox[0], Y = P.nbox[4], Z = P.nbox[8];
-            bool inside = live && v[0] >= 0 && v[0] < X && v[1] >= 0 && v[1] < Y && v[2] >= 0 && v[2] < Z;
-            long long word = inside ? ((v[0] * Y + v[1]) * pitch + (v[2] >> 5)) : -1;
-            uint32_t bit = inside ? (1u << (v[2] & 31)) : 0u;
-            unsigned peers = __match_any_sync(MDVC_FULL, word);
-            // OR the bits of all peers into the leader
-            uint32_t merged = 0;
-            unsigned rem = peers;
-            while (rem) {
-                int src = __ffs(rem) - 1;
-                merged |= __shfl_sync(peers, bit, src);
-                rem &= rem - 1;
+            if (v[0] >= 0 && v[0] < X && v[1] >= 0 && v[1] < Y && v[2] >= 0 && v[2] < Z) {
+                // Fire-and-forget RED.OR.  A __match_any_sync aggregation of lanes hitting the same word was
+                // measured on B200 (ncu: 20 of 27 stall cycles per issue on the MIO/short-scoreboard path,
+                // 255 us for 10.2 M atoms): atom order is spatially uncorrelated with the voxel grid, so
+                // there is almost nothing to merge and the match itself was the bottleneck.
+                atomicOr(&occ[(v[0] * Y + v[1]) * pitch + (v[2] >> 5)], 1u << (v[2] & 31));
             }
-            int leader = __ffs(peers) - 1;
-            if (inside && (threadIdx.x & 31) == leader) atomicOr(&occ[word], merged);
         }
     }
 }
@@ -269,30 +276,41 @@ k_morph_sweep(const uint32_t *__restrict__ in, uint32_t *__restrict__ out, int X
         return v & vmask;
     };
     uint32_t Pm2 = 0, Pm1 = 0;
-    uint32_t v = load(xs - 1);
-    for (int s = 0, x = xs - 1; x <= xe; ++x, ++s) {
-        uint32_t vnext = (x < xe) ? load(x + 1) : 0u;      // prefetch the next plane
-        uint32_t *buf = raw[s & 1];
-        if (active) buf[t] = v;
-        __syncthreads();
-        uint32_t P = 0;
-        if (is_out) {
-            const uint32_t *r0 = buf + (j - 1) * nw, *r1 = r0 + nw, *r2 = r1 + nw;
-            uint32_t c = r0[w] | r1[w] | r2[w];
-            uint32_t pw = r0[wp] | r1[wp] | r2[wp];
-            uint32_t nx = r0[wn] | r1[wn] | r2[wn];
-            uint32_t down_in = (w > 0) ? (pw >> 31) : ((pw >> last) & 1u);
-            P = (c | (c << 1) | down_in | (c >> 1) | ((nx & 1u) << top)) & vmask;
-            if (s >= 2) {
-                uint32_t o = Pm2 | Pm1 | P;
-                if (ERODE) o = ~o & vmask;
-                size_t at = ((size_t)(x - 1) * Y + yout) * pitch;
-                out[at + w] = o;
-                if (w == nw - 1) for (int k = nw; k < pitch; ++k) out[at + k] = 0u;
+    // two planes in flight per thread (deeper prefetch measured slower: the sweep is issue-bound, not latency-bound)
+    constexpr int DEPTH = 2;
+    uint32_t q[DEPTH];
+#pragma unroll
+    for (int d = 0; d < DEPTH; ++d) q[d] = (xs - 1 + d <= xe) ? load(xs - 1 + d) : 0u;
+    int s = 0;
+    for (int x0 = xs - 1; x0 <= xe; x0 += DEPTH) {
+#pragma unroll
+        for (int d = 0; d < DEPTH; ++d) {
+            const int x = x0 + d;
+            if (x > xe) break;
+            const uint32_t v = q[d];
+            q[d] = (x + DEPTH <= xe) ? load(x + DEPTH) : 0u;
+            uint32_t *buf = raw[s & 1];
+            if (active) buf[t] = v;
+            __syncthreads();
+            uint32_t P = 0;
+            if (is_out) {
+                const uint32_t *r0 = buf + (j - 1) * nw, *r1 = r0 + nw, *r2 = r1 + nw;
+                uint32_t c = r0[w] | r1[w] | r2[w];
+                uint32_t pw = r0[wp] | r1[wp] | r2[wp];
+                uint32_t nx = r0[wn] | r1[wn] | r2[wn];
+                uint32_t down_in = (w > 0) ? (pw >> 31) : ((pw >> last) & 1u);
+                P = (c | (c << 1) | down_in | (c >> 1) | ((nx & 1u) << top)) & vmask;
+                if (s >= 2) {
+                    uint32_t o = Pm2 | Pm1 | P;
+                    if (ERODE) o = ~o & vmask;
+                    size_t at = ((size_t)(x - 1) * Y + yout) * pitch;
+                    out[at + w] = o;
+                    if (w == nw - 1) for (int k = nw; k < pitch; ++k) out[at + k] = 0u;
+                }
             }
+            Pm2 = Pm1; Pm1 = P;
+            ++s;
         }
-        Pm2 = Pm1; Pm1 = P;
-        v = vnext;
     }
 }
 
