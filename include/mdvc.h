@@ -114,7 +114,9 @@ size_t mdvc_frame_workspace_bytes(int X, int Y, int Z, const mdvc_frame_caps *ca
 int mdvc_frame_label(const uint32_t *bits, int X, int Y, int Z, int pitch,
                      void *workspace, size_t workspace_bytes, const mdvc_frame_caps *caps, void *stream);
 /* Stage 2: unique contact pairs and bridge records, sorted like the reference's rows.
- * periodic = 0 skips bridges (the reference's slab=True path, containment_main.py:67-69). */
+ * periodic = 0 skips bridges (the reference's slab=True path, containment_main.py:67-69); 1 = periodic in x, y
+ * and z; 2 = periodic in y and z only (one slab of a slab-decomposed grid: the x faces are the caller's,
+ * see mdvc_plane_pairs). */
 int mdvc_frame_pairs(const uint32_t *bits, int X, int Y, int Z, int pitch,
                      void *workspace, size_t workspace_bytes, const mdvc_frame_caps *caps,
                      int periodic, void *stream);
@@ -131,6 +133,15 @@ int mdvc_frame_set_lut(int X, int Y, int Z, void *workspace, size_t workspace_by
 int mdvc_frame_expand(const uint32_t *bits, int X, int Y, int Z, int pitch,
                       void *workspace, size_t workspace_bytes, const mdvc_frame_caps *caps,
                       int32_t *labels_out, int32_t *components_out, void *stream);
+
+/* Same for the planes [x_begin, x_end) only; outputs hold (x_end - x_begin) * Y * Z elements. */
+int mdvc_frame_expand_planes(const uint32_t *bits, int X, int Y, int Z, int pitch,
+                             void *workspace, size_t workspace_bytes, const mdvc_frame_caps *caps,
+                             int x_begin, int x_end, int32_t *labels_out, int32_t *components_out, void *stream);
+/* Slab decomposition: replace every run's label by lut[label + n_false] (local -> global numbering).  Call
+ * after mdvc_frame_set_lut (whose LUT is indexed by the local labels) and before the final expand. */
+int mdvc_frame_relabel_runs(int X, int Y, int Z, void *workspace, size_t workspace_bytes,
+                            const mdvc_frame_caps *caps, const int32_t *lut_dev, uint32_t n_entries, void *stream);
 
 /* Synchronises the stream and copies the header to the host. Returns flags as MDVC_OVERFLOW_*. */
 int mdvc_frame_read_header(const void *workspace, mdvc_frame_header *header_host, void *stream);
@@ -160,6 +171,13 @@ int mdvc_grid_contacts(const int32_t *labels, int X, int Y, int Z, unsigned long
 int mdvc_grid_bridges(const int32_t *labels, int X, int Y, int Z, unsigned long long *set_slots,
                       uint32_t n_slots, int32_t *rows_out, uint32_t rows_cap, uint32_t *n_rows_dev,
                       uint32_t *flags_dev, void *stream);
+/* Slab boundaries (no reference counterpart: the reference is single-process).  Every step from plane_a (last
+ * plane of a slab, int32 [Y][Z]) to the 9 neighbours in plane_b (first plane of the next slab), y/z periodic when
+ * periodic_yz: rows (la, lb, sx_boundary, sy, sz), sorted unique, NOT normalised (la, lb are numbered by
+ * different slabs).  sx_boundary = 0 inside the box, +1 for the step through the x-max face. */
+int mdvc_plane_pairs(const int32_t *plane_a, const int32_t *plane_b, int Y, int Z, int sx_boundary, int periodic_yz,
+                     unsigned long long *set_slots, uint32_t n_slots, int32_t *rows_out, uint32_t rows_cap,
+                     uint32_t *n_rows_dev, uint32_t *flags_dev, void *stream);
 /* create_components_grid (label.py:21-38): out = lut[label - lut_lo] (0 where outside the LUT). */
 int mdvc_grid_relabel(const int32_t *labels, long long n, const int32_t *lut, int lut_lo, int lut_n,
                       int32_t *out, void *stream);

@@ -56,6 +56,8 @@ SIGNATURES = {
     "mdvc_frame_components": (_I, [_I, _I, _I, _P, _SZ, _CAPS, _I, _P]),
     "mdvc_frame_set_lut": (_I, [_I, _I, _I, _P, _SZ, _CAPS, _P, _U32, _P]),
     "mdvc_frame_expand": (_I, [_P, _I, _I, _I, _I, _P, _SZ, _CAPS, _P, _P, _P]),
+    "mdvc_frame_expand_planes": (_I, [_P, _I, _I, _I, _I, _P, _SZ, _CAPS, _I, _I, _P, _P, _P]),
+    "mdvc_frame_relabel_runs": (_I, [_I, _I, _I, _P, _SZ, _CAPS, _P, _U32, _P]),
     "mdvc_frame_read_header": (_I, [_P, ctypes.POINTER(FrameHeader), _P]),
     "mdvc_frame_contacts_ptr": (_P, [_P, _I, _I, _I, _CAPS]),
     "mdvc_frame_bridges_ptr": (_P, [_P, _I, _I, _I, _CAPS]),
@@ -65,6 +67,7 @@ SIGNATURES = {
     "mdvc_frame_debug_ptr": (_P, [_P, _I, _I, _I, _CAPS, _I]),
     "mdvc_grid_contacts": (_I, [_P, _I, _I, _I, _P, _U32, _P, _U32, _P, _P, _P]),
     "mdvc_grid_bridges": (_I, [_P, _I, _I, _I, _P, _U32, _P, _U32, _P, _P, _P]),
+    "mdvc_plane_pairs": (_I, [_P, _P, _I, _I, _I, _I, _P, _U32, _P, _U32, _P, _P, _P]),
     "mdvc_grid_relabel": (_I, [_P, _LL, _P, _I, _I, _P, _P]),
     "mdvc_grid_count": (_I, [_P, _LL, _I, _I, _P, _P]),
     "mdvc_grid_select_scratch_words": (_SZ, [_LL]),

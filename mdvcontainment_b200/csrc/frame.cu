@@ -874,7 +874,7 @@ __device__ __noinline__ void pairs_one_run_global(const uint32_t *__restrict__ b
         if (nx < 0) { nx = D.X - 1; sx = -1; }
         if (ny < 0) { ny = D.Y - 1; sy = -1; } else if (ny >= D.Y) { ny = 0; sy = 1; }
         bool wraps = (sx | sy) != 0;
-        if (wraps && !periodic) continue;
+        if ((sy && !periodic) || (sx && periodic != 1)) continue;
         uint32_t r2 = (uint32_t)nx * D.Y + ny;
         uint32_t j = run_at(runstart, rowoff, D, r2, lo);
         uint32_t end = rowoff[r2 + 1], limit = r2 * (uint32_t)D.Z + (uint32_t)hi;
@@ -889,6 +889,7 @@ __device__ __noinline__ void pairs_one_run_global(const uint32_t *__restrict__ b
         for (int dx = -1; dx <= 1; ++dx) {
             int nx = x + dx, sx = 0;
             if (nx < 0) { nx = D.X - 1; sx = -1; } else if (nx >= D.X) { nx = 0; sx = 1; }
+            if (sx && periodic != 1) continue;
             for (int dy = -1; dy <= 1; ++dy) {
                 int ny = y + dy, sy = 0;
                 if (ny < 0) { ny = D.Y - 1; sy = -1; } else if (ny >= D.Y) { ny = 0; sy = 1; }
@@ -901,7 +902,7 @@ __device__ __noinline__ void pairs_one_run_global(const uint32_t *__restrict__ b
         // on this direction for their dx = +1 relations (see k_tile_pairs)
         int nx = x - 1, sx = 0;
         if (nx < 0) { nx = D.X - 1; sx = -1; }
-        for (int dy = -1; dy <= 1; ++dy) {
+        for (int dy = -1; dy <= 1 && !(sx && periodic != 1); ++dy) {
             int ny = y + dy, sy = 0;
             if (ny < 0) { ny = D.Y - 1; sy = -1; } else if (ny >= D.Y) { ny = 0; sy = 1; }
             emit_bridge(bs, la, lab[rowoff[(uint32_t)nx * D.Y + ny + 1] - 1], sx, sy, -1);
@@ -945,8 +946,8 @@ k_tile_pairs(const uint32_t *__restrict__ bits, Dims D, Hdr *h, const uint32_t *
             int yy = y0 + j - 1, sy = 0;
             if (yy < 0) { yy = D.Y - 1; sy = -1; } else if (yy >= D.Y) { yy = 0; sy = 1; }
             int xx = p == 0 ? x : (x == 0 ? D.X - 1 : x - 1);
-            bool wrapped = sy != 0 || (p == 1 && x == 0);
-            bool valid = j <= ny + 1 && (periodic || !wrapped);
+            // periodic: 0 none, 1 all axes, 2 y and z only (slab interior: the x faces belong to the caller)
+            bool valid = j <= ny + 1 && (sy == 0 || periodic != 0) && (!(p == 1 && x == 0) || periodic == 1);
             uint32_t rg = (uint32_t)xx * D.Y + yy;
             uint32_t g0 = valid ? rowoff[rg] : 0u, g1 = valid ? rowoff[rg + 1] : 0u;
             srow[t] = rg; sgb[t] = g0; scnt[t] = g1 - g0; ssy[t] = sy;
@@ -1188,16 +1189,16 @@ template <int G, bool VEC>
 __global__ void __launch_bounds__(256)
 k_expand(const uint32_t *__restrict__ bits, Dims D, const Hdr *__restrict__ h, const uint32_t *__restrict__ rowoff,
          const int32_t *__restrict__ lab, const int32_t *__restrict__ runcomp,
-         int32_t *__restrict__ out_lab, int32_t *__restrict__ out_comp) {
+         int32_t *__restrict__ out_lab, int32_t *__restrict__ out_comp, long long row_begin, long long row_end) {
     if (h->n_labels == 0) return;
     const int lane = threadIdx.x & 31, gl = lane & (G - 1), gi = lane / G;
     constexpr int GPW = 32 / G;
     long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
     int nchunks = (D.nw + G - 1) / G;
-    for (long long rb = warp * GPW; rb < D.rows; rb += nwarps * GPW) {
+    for (long long rb = row_begin + warp * GPW; rb < row_end; rb += nwarps * GPW) {
         long long row = rb + gi;
-        bool rv = row < D.rows;
+        bool rv = row < row_end;
         const uint32_t *rp = bits + (rv ? row : 0) * D.pitch;
         uint32_t base = rv ? rowoff[row] : 0u;
         const int32_t *lrow = lab + base;
@@ -1431,23 +1432,65 @@ extern "C" int mdvc_frame_set_lut(int X, int Y, int Z, void *ws, size_t ws_bytes
     return MDVC_OK;
 }
 
-extern "C" int mdvc_frame_expand(const uint32_t *bits, int X, int Y, int Z, int pitch, void *ws, size_t ws_bytes,
-                                 const mdvc_frame_caps *caps, int32_t *labels_out, int32_t *components_out, void *stream) {
+static int expand_rows(const uint32_t *bits, int X, int Y, int Z, int pitch, void *ws, size_t ws_bytes,
+                       const mdvc_frame_caps *caps, int32_t *labels_out, int32_t *components_out,
+                       long long row_begin, long long row_end, void *stream) {
     Dims D; Layout L;
     if (!bits || !make_dims(X, Y, Z, pitch, D)) return MDVC_ERR_BADARG;
     int rc = check_ws(ws, ws_bytes, caps, D.rows, L);
     if (rc) return rc;
-    if (!labels_out && !components_out) return MDVC_OK;
+    if (row_begin < 0 || row_end > D.rows || row_begin > row_end) return MDVC_ERR_BADARG;
+    if ((!labels_out && !components_out) || row_begin == row_end) return MDVC_OK;
     cudaStream_t st = (cudaStream_t)stream;
     int g = pick_group(D.nw);
     bool vec = (Z % 4 == 0) && ((reinterpret_cast<uintptr_t>(labels_out) & 15) == 0) &&
                ((reinterpret_cast<uintptr_t>(components_out) & 15) == 0);
-    unsigned grid = mdvc_grid(D.rows * g, 256, 8);
+    unsigned grid = mdvc_grid((row_end - row_begin) * g, 256, 8);
     const Hdr *h = at<Hdr>(ws, L.hdr);
     const uint32_t *rowoff = at<uint32_t>(ws, L.rowoff);
     const int32_t *lab = at<int32_t>(ws, L.lab), *rc_ = at<int32_t>(ws, L.runcomp);
-    if (vec) { MDVC_DISPATCH_G(g, (k_expand<G, true><<<grid, 256, 0, st>>>(bits, D, h, rowoff, lab, rc_, labels_out, components_out))); }
-    else { MDVC_DISPATCH_G(g, (k_expand<G, false><<<grid, 256, 0, st>>>(bits, D, h, rowoff, lab, rc_, labels_out, components_out))); }
+    // the kernel indexes its outputs by absolute row: shift the bases so that row_begin lands on element 0
+    int32_t *lo = labels_out ? labels_out - row_begin * Z : nullptr;
+    int32_t *co = components_out ? components_out - row_begin * Z : nullptr;
+    if (vec) { MDVC_DISPATCH_G(g, (k_expand<G, true><<<grid, 256, 0, st>>>(bits, D, h, rowoff, lab, rc_, lo, co, row_begin, row_end))); }
+    else { MDVC_DISPATCH_G(g, (k_expand<G, false><<<grid, 256, 0, st>>>(bits, D, h, rowoff, lab, rc_, lo, co, row_begin, row_end))); }
+    MDVC_LAUNCH_CHECK();
+    return MDVC_OK;
+}
+
+extern "C" int mdvc_frame_expand(const uint32_t *bits, int X, int Y, int Z, int pitch, void *ws, size_t ws_bytes,
+                                 const mdvc_frame_caps *caps, int32_t *labels_out, int32_t *components_out, void *stream) {
+    return expand_rows(bits, X, Y, Z, pitch, ws, ws_bytes, caps, labels_out, components_out, 0, (long long)X * Y, stream);
+}
+
+// planes [x_begin, x_end) only; the outputs hold (x_end - x_begin) * Y * Z elements
+extern "C" int mdvc_frame_expand_planes(const uint32_t *bits, int X, int Y, int Z, int pitch, void *ws, size_t ws_bytes,
+                                        const mdvc_frame_caps *caps, int x_begin, int x_end, int32_t *labels_out,
+                                        int32_t *components_out, void *stream) {
+    if (x_begin < 0 || x_end > X || x_begin > x_end) return MDVC_ERR_BADARG;
+    return expand_rows(bits, X, Y, Z, pitch, ws, ws_bytes, caps, labels_out, components_out, (long long)x_begin * Y,
+                       (long long)x_end * Y, stream);
+}
+
+// lab[i] = lut[lab[i] + n_false] for every run (slab decomposition: local label -> global label).  Call after
+// mdvc_frame_set_lut, which indexes its LUT by the *local* labels.
+__global__ void k_relabel_runs(const Hdr *__restrict__ h, int32_t *lab, const int32_t *__restrict__ lut, uint32_t lut_n) {
+    if (h->n_labels == 0) return;
+    uint32_t R = h->run_eff, nf = h->n_false, stride = gridDim.x * blockDim.x;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < R; i += stride) {
+        uint32_t j = (uint32_t)(lab[i] + (int)nf);
+        lab[i] = j < lut_n ? lut[j] : 0;
+    }
+}
+
+extern "C" int mdvc_frame_relabel_runs(int X, int Y, int Z, void *ws, size_t ws_bytes, const mdvc_frame_caps *caps,
+                                       const int32_t *lut_dev, uint32_t n_entries, void *stream) {
+    Dims D; Layout L;
+    if (!lut_dev || !make_dims(X, Y, Z, mdvc_words(Z), D)) return MDVC_ERR_BADARG;
+    int rc = check_ws(ws, ws_bytes, caps, D.rows, L);
+    if (rc) return rc;
+    k_relabel_runs<<<mdvc_grid(caps->max_runs, 256, 8), 256, 0, (cudaStream_t)stream>>>(at<Hdr>(ws, L.hdr), at<int32_t>(ws, L.lab),
+                                                                                         lut_dev, n_entries);
     MDVC_LAUNCH_CHECK();
     return MDVC_OK;
 }

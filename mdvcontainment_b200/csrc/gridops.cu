@@ -211,6 +211,59 @@ extern "C" int mdvc_grid_bridges(const int32_t *labels, int X, int Y, int Z, uns
     return grid_pairs(true, labels, X, Y, Z, set_slots, n_slots, rows_out, rows_cap, n_rows_dev, flags_dev, (cudaStream_t)stream);
 }
 
+// Slab boundaries: every step from a voxel of plane A (labels la, x = last plane of one slab) to its 9
+// neighbours in plane B (labels lb, x + 1 = first plane of the next slab), y and z periodic.  Rows are
+// (la, lb, sx, sy, sz) with sx = sx_boundary (0 inside the box, +1 when the step leaves through the x-max
+// face), NOT normalised: la and lb are numbered by different slabs, the caller maps them to global labels
+// first.  sorted unique, int32 [K][5].
+__global__ void __launch_bounds__(256)
+k_plane_pairs(const int32_t *__restrict__ A, const int32_t *__restrict__ B, int Y, int Z, int sx_boundary, int periodic_yz,
+              unsigned long long *slots, uint32_t n_slots, uint32_t *flags) {
+    __shared__ GBlockSet cache;
+    cache.clear();
+    __syncthreads();
+    GSink sink{&cache, slots, n_slots, flags, MDVC_OVERFLOW_BRIDGES, MDVC_KEY_EMPTY};
+    long long n = (long long)Y * Z, stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        int la = A[i];
+        if (la == 0) continue;
+        int z = (int)(i % Z), y = (int)(i / Z);
+        for (int dy = -1; dy <= 1; ++dy) {
+            int ny = y + dy, sy = 0;
+            if (ny < 0) { ny = Y - 1; sy = -1; } else if (ny >= Y) { ny = 0; sy = 1; }
+            if (sy && !periodic_yz) continue;
+            for (int dz = -1; dz <= 1; ++dz) {
+                int nz = z + dz, sz = 0;
+                if (nz < 0) { nz = Z - 1; sz = -1; } else if (nz >= Z) { nz = 0; sz = 1; }
+                if (sz && !periodic_yz) continue;
+                int lb = B[(long long)ny * Z + nz];
+                if (lb == 0) continue;
+                if (!label_key_ok(la) || !label_key_ok(lb)) { atomicOr(flags, MDVC_OVERFLOW_LABELS); continue; }
+                sink.put(mdvc_pack_key(la, lb, mdvc_shift_code(sx_boundary, sy, sz)));
+            }
+        }
+    }
+}
+
+extern "C" int mdvc_plane_pairs(const int32_t *plane_a, const int32_t *plane_b, int Y, int Z, int sx_boundary, int periodic_yz,
+                                unsigned long long *set_slots, uint32_t n_slots, int32_t *rows_out, uint32_t rows_cap,
+                                uint32_t *n_rows_dev, uint32_t *flags_dev, void *stream) {
+    if (!plane_a || !plane_b || !set_slots || !rows_out || !n_rows_dev || !flags_dev || Y <= 0 || Z <= 0) return MDVC_ERR_BADARG;
+    if (n_slots < 64 || (n_slots & (n_slots - 1)) || sx_boundary < -1 || sx_boundary > 1) return MDVC_ERR_BADARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    MDVC_CUDA_CHECK(cudaMemsetAsync(set_slots, 0xff, (size_t)n_slots * 8, st));
+    MDVC_CUDA_CHECK(cudaMemsetAsync(n_rows_dev, 0, sizeof(uint32_t), st));
+    k_plane_pairs<<<mdvc_grid((long long)Y * Z, 256, 8), 256, 0, st>>>(plane_a, plane_b, Y, Z, sx_boundary, periodic_yz, set_slots,
+                                                                      n_slots, flags_dev);
+    MDVC_LAUNCH_CHECK();
+    k_g_sort_slots<<<1, 1024, 0, st>>>(set_slots, n_slots);
+    MDVC_LAUNCH_CHECK();
+    k_g_decode<<<mdvc_grid(n_slots, 256, 4), 256, 0, st>>>(set_slots, n_slots, 1, rows_out, rows_cap, n_rows_dev, flags_dev,
+                                                           MDVC_OVERFLOW_BRIDGES);
+    MDVC_LAUNCH_CHECK();
+    return MDVC_OK;
+}
+
 // ------------------------------------------------------------------------------------------
 // relabel through a LUT, histogram
 // ------------------------------------------------------------------------------------------
