@@ -93,3 +93,30 @@ def salt_noise_grid(shape, p_true: float = 0.5, salt: float = 0.02, seed: int = 
         coarse = (coarse + np.roll(coarse, blob // 2, ax) + np.roll(coarse, -(blob // 2), ax)) / 3
     base = coarse > np.quantile(coarse, 1 - p_true)
     return base ^ (rng.random(shape) < salt)
+
+
+def gyroid_salt_planes(x0: int, x1: int, shape, salt: float = 1e-4, seed: int = 5, device="cuda", chunk: int = 8):
+    """Config 5 at scale: planes [x0, x1) of a periodic gyroid-like solid (sin-sum level set, periodic in all
+    three axes) XOR Bernoulli(salt) noise, generated on the device plane-chunk by plane-chunk and returned as a
+    bit-packed ``BitGrid`` of the slab.  Every plane depends only on its global x and the seed, so any slab
+    decomposition produces the same global grid (input generation, not part of the hot path)."""
+    import torch
+    from . import device as dev
+    X, Y, Z = (int(v) for v in shape)
+    out = dev.BitGrid((x1 - x0, Y, Z), device=device)
+    yy = torch.arange(Y, device=device, dtype=torch.float32)[None, :, None] * (2 * np.pi * 3 / Y)
+    zz = torch.arange(Z, device=device, dtype=torch.float32)[None, None, :] * (2 * np.pi * 2 / Z)
+    for c0 in range(x0, x1, chunk):
+        c1 = min(c0 + chunk, x1)
+        xx = torch.arange(c0, c1, device=device, dtype=torch.float32)[:, None, None] * (2 * np.pi * 2 / X)
+        solid = (torch.sin(xx) * torch.cos(yy) + torch.sin(yy) * torch.cos(zz) + torch.sin(zz) * torch.cos(xx)) > 0.3
+        if salt > 0:
+            noise = torch.empty((c1 - c0, Y, Z), device=device, dtype=torch.float32)
+            for k, x in enumerate(range(c0, c1)):
+                gen = torch.Generator(device=device)
+                gen.manual_seed(seed * 1_000_003 + x)
+                noise[k].uniform_(generator=gen)
+            solid ^= noise < salt
+        part = dev.BitGrid.from_bool(solid)
+        out.words[c0 - x0:c1 - x0].copy_(part.words)
+    return out
