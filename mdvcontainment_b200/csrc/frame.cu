@@ -1185,7 +1185,14 @@ __global__ void k_run_components(const Hdr *__restrict__ h, const int32_t *__res
 // run ordinals by popcount, looks the per-run value up (L1-resident: consecutive voxels share runs)
 // and streams the row out with 16-byte stores.
 // ------------------------------------------------------------------------------------------
-template <int G, bool VEC>
+// 256-bit streaming store (sm_100: STG.E.EF.256)
+__device__ __forceinline__ void st_v8_cs(int32_t *p, int a, int b, int c, int d, int e, int f, int g, int h) {
+    asm volatile("st.global.cs.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(a), "r"(b), "r"(c), "r"(d), "r"(e), "r"(f),
+                 "r"(g), "r"(h)
+                 : "memory");
+}
+
+template <int G, int VEC>
 __global__ void __launch_bounds__(256)
 k_expand(const uint32_t *__restrict__ bits, Dims D, const Hdr *__restrict__ h, const uint32_t *__restrict__ rowoff,
          const int32_t *__restrict__ lab, const int32_t *__restrict__ runcomp,
@@ -1210,7 +1217,48 @@ k_expand(const uint32_t *__restrict__ bits, Dims D, const Hdr *__restrict__ h, c
             uint32_t B = (rv && w < D.nw) ? (rp[w] & mdvc_valid_mask(w, D.Z)) : 0u;
             uint32_t S = rw.starts(B, w, D.Z, gl);
             uint32_t ex = rw.exclusive(S, gl);
-            if (VEC) {
+            if (VEC == 8) {
+                // eight voxels (a quarter word) per lane and iteration, written with one 256-bit streaming store
+                // (STG.E.EF.256: a warp store covers 1 KiB of full sectors).  Most quarter words contain no run
+                // start, so all eight voxels take one looked-up value.  Needs Z % 8 == 0 and 32-byte aligned outputs.
+#pragma unroll
+                for (int it = 0; it < 4; ++it) {
+                    const int q = it * G + gl;                 // quarter-word index inside the chunk
+                    const int src = q >> 2;
+                    const uint32_t Sw = __shfl_sync(MDVC_FULL, S, src, G);
+                    const uint32_t Ew = __shfl_sync(MDVC_FULL, ex, src, G);
+                    const int k0 = (q & 3) << 3;
+                    const int z0 = ((c * G + src) << 5) + k0;
+                    if (rv && z0 < D.Z) {
+                        const uint32_t o0 = Ew + __popc(Sw & ((2u << k0) - 1u)) - 1u;
+                        const uint32_t byte = (Sw >> k0) & 0xffu;
+                        const size_t at = obase + z0;
+                        if ((byte >> 1) == 0) {
+                            if (out_lab) {
+                                const int v = __ldg(lrow + o0);
+                                st_v8_cs(out_lab + at, v, v, v, v, v, v, v, v);
+                            }
+                            if (out_comp) {
+                                const int v = __ldg(crow + o0);
+                                st_v8_cs(out_comp + at, v, v, v, v, v, v, v, v);
+                            }
+                        } else {
+                            uint32_t o[8];
+                            o[0] = o0;
+#pragma unroll
+                            for (int j = 1; j < 8; ++j) o[j] = o[j - 1] + ((byte >> j) & 1u);
+                            if (out_lab) {
+                                st_v8_cs(out_lab + at, __ldg(lrow + o[0]), __ldg(lrow + o[1]), __ldg(lrow + o[2]), __ldg(lrow + o[3]),
+                                         __ldg(lrow + o[4]), __ldg(lrow + o[5]), __ldg(lrow + o[6]), __ldg(lrow + o[7]));
+                            }
+                            if (out_comp) {
+                                st_v8_cs(out_comp + at, __ldg(crow + o[0]), __ldg(crow + o[1]), __ldg(crow + o[2]), __ldg(crow + o[3]),
+                                         __ldg(crow + o[4]), __ldg(crow + o[5]), __ldg(crow + o[6]), __ldg(crow + o[7]));
+                            }
+                        }
+                    }
+                }
+            } else if (VEC == 4) {
 #pragma unroll
                 for (int it = 0; it < 8; ++it) {
                     int q = it * G + gl;                       // quad (4 voxels) inside the chunk
@@ -1443,8 +1491,8 @@ static int expand_rows(const uint32_t *bits, int X, int Y, int Z, int pitch, voi
     if ((!labels_out && !components_out) || row_begin == row_end) return MDVC_OK;
     cudaStream_t st = (cudaStream_t)stream;
     int g = pick_group(D.nw);
-    bool vec = (Z % 4 == 0) && ((reinterpret_cast<uintptr_t>(labels_out) & 15) == 0) &&
-               ((reinterpret_cast<uintptr_t>(components_out) & 15) == 0);
+    uintptr_t both = reinterpret_cast<uintptr_t>(labels_out) | reinterpret_cast<uintptr_t>(components_out);
+    int vec = (Z % 8 == 0 && (both & 31) == 0) ? 8 : ((Z % 4 == 0 && (both & 15) == 0) ? 4 : 0);
     unsigned grid = mdvc_grid((row_end - row_begin) * g, 256, 8);
     const Hdr *h = at<Hdr>(ws, L.hdr);
     const uint32_t *rowoff = at<uint32_t>(ws, L.rowoff);
@@ -1452,8 +1500,9 @@ static int expand_rows(const uint32_t *bits, int X, int Y, int Z, int pitch, voi
     // the kernel indexes its outputs by absolute row: shift the bases so that row_begin lands on element 0
     int32_t *lo = labels_out ? labels_out - row_begin * Z : nullptr;
     int32_t *co = components_out ? components_out - row_begin * Z : nullptr;
-    if (vec) { MDVC_DISPATCH_G(g, (k_expand<G, true><<<grid, 256, 0, st>>>(bits, D, h, rowoff, lab, rc_, lo, co, row_begin, row_end))); }
-    else { MDVC_DISPATCH_G(g, (k_expand<G, false><<<grid, 256, 0, st>>>(bits, D, h, rowoff, lab, rc_, lo, co, row_begin, row_end))); }
+    if (vec == 8) { MDVC_DISPATCH_G(g, (k_expand<G, 8><<<grid, 256, 0, st>>>(bits, D, h, rowoff, lab, rc_, lo, co, row_begin, row_end))); }
+    else if (vec == 4) { MDVC_DISPATCH_G(g, (k_expand<G, 4><<<grid, 256, 0, st>>>(bits, D, h, rowoff, lab, rc_, lo, co, row_begin, row_end))); }
+    else { MDVC_DISPATCH_G(g, (k_expand<G, 0><<<grid, 256, 0, st>>>(bits, D, h, rowoff, lab, rc_, lo, co, row_begin, row_end))); }
     MDVC_LAUNCH_CHECK();
     return MDVC_OK;
 }
