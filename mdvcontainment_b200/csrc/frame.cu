@@ -1186,7 +1186,18 @@ __global__ void k_run_components(const Hdr *__restrict__ h, const int32_t *__res
 // and streams the row out with 16-byte stores.
 // ------------------------------------------------------------------------------------------
 // 256-bit streaming store (sm_100: STG.E.EF.256)
+__device__ int g_expand_hint = 1;
 __device__ __forceinline__ void st_v8_cs(int32_t *p, int a, int b, int c, int d, int e, int f, int g, int h) {
+    if (g_expand_hint == 0) {
+        asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(a), "r"(b), "r"(c), "r"(d), "r"(e), "r"(f),
+                     "r"(g), "r"(h) : "memory");
+        return;
+    }
+    if (g_expand_hint == 2) {
+        asm volatile("st.global.wt.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(a), "r"(b), "r"(c), "r"(d), "r"(e), "r"(f),
+                     "r"(g), "r"(h) : "memory");
+        return;
+    }
     asm volatile("st.global.cs.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(a), "r"(b), "r"(c), "r"(d), "r"(e), "r"(f),
                  "r"(g), "r"(h)
                  : "memory");
@@ -1336,7 +1347,9 @@ extern "C" int mdvc_frame_label(const uint32_t *bits, int X, int Y, int Z, int p
     MDVC_CUDA_CHECK(cudaMemsetAsync(vol, 0, (size_t)caps->max_labels * 8, st));
     int g = pick_group(D.nw);
     long long row_threads = D.rows * g;
-    unsigned row_grid = mdvc_grid(row_threads, 256, 8);
+    static int row_bps = 0;
+    if (!row_bps) { const char *e = getenv("MDVC_ROW_BPS"); row_bps = e ? atoi(e) : 8; }
+    unsigned row_grid = mdvc_grid(row_threads / 4, 256, row_bps);      // four rows per group and iteration
     MDVC_DISPATCH_G(g, (k_count_runs<G><<<row_grid, 256, 0, st>>>(bits, D, rowoff)));
     MDVC_LAUNCH_CHECK();
     rc = mdvc_exclusive_scan<uint32_t>(rowoff, rowoff, nullptr, (uint32_t)D.rows, at<uint32_t>(ws, L.tile32),
@@ -1493,7 +1506,14 @@ static int expand_rows(const uint32_t *bits, int X, int Y, int Z, int pitch, voi
     int g = pick_group(D.nw);
     uintptr_t both = reinterpret_cast<uintptr_t>(labels_out) | reinterpret_cast<uintptr_t>(components_out);
     int vec = (Z % 8 == 0 && (both & 31) == 0) ? 8 : ((Z % 4 == 0 && (both & 15) == 0) ? 4 : 0);
-    unsigned grid = mdvc_grid((row_end - row_begin) * g, 256, 8);
+    static int bps = 0, hint = -1;
+    if (!bps) {
+        const char *e;
+        bps = (e = getenv("MDVC_EXPAND_BPS")) ? atoi(e) : 256;
+        hint = (e = getenv("MDVC_EXPAND_HINT")) ? atoi(e) : 1;
+        cudaMemcpyToSymbol(g_expand_hint, &hint, sizeof(int));
+    }
+    unsigned grid = mdvc_grid((row_end - row_begin) * g, 256, bps);
     const Hdr *h = at<Hdr>(ws, L.hdr);
     const uint32_t *rowoff = at<uint32_t>(ws, L.rowoff);
     const int32_t *lab = at<int32_t>(ws, L.lab), *rc_ = at<int32_t>(ws, L.runcomp);
