@@ -314,6 +314,63 @@ k_morph_sweep(const uint32_t *__restrict__ in, uint32_t *__restrict__ out, int X
     }
 }
 
+// Same sweep for rows of 1, 2, 4, 8, 16 or 32 words (Z <= 1024, power-of-two word count): the lanes of a
+// row are neighbours in a warp segment, so the z-dilation takes its two neighbour words by shuffle (the
+// segment-relative source index wraps, which is exactly the periodic z boundary) and only the z-dilated word
+// goes through shared memory; the y-dilation then needs two LDS instead of nine.
+template <bool ERODE>
+__global__ void __launch_bounds__(MORPH_MAX_THREADS)
+k_morph_sweep_p2(const uint32_t *__restrict__ in, uint32_t *__restrict__ out, int X, int Y, int Z, int pitch, int nw,
+                 int JT, int TX) {
+    __shared__ uint32_t dzs[2][MORPH_MAX_THREADS];
+    const int t = threadIdx.x;
+    const int w = t & (nw - 1), j = t / nw;
+    const bool active = j < JT;
+    const int TY = JT - 2;
+    const int y0 = blockIdx.x * TY;
+    int yy = y0 - 1 + j;
+    yy %= Y; if (yy < 0) yy += Y;
+    const int yout = y0 + j - 1;
+    const bool is_out = active && j >= 1 && j <= TY && yout < Y;
+    const int xs = blockIdx.y * TX, xe = min(xs + TX, X);
+    const uint32_t vmask = mdvc_valid_mask(w, Z);
+    const int last = (Z - 1) & 31;
+    const int top = (w == nw - 1) ? last : 31;
+    const size_t plane = (size_t)Y * pitch;
+    const uint32_t *src = in + (size_t)yy * pitch + w;
+    uint32_t *dst = out + (size_t)yout * pitch + w;
+    uint32_t Pm2 = 0, Pm1 = 0;
+    int xw = xs - 1 < 0 ? X - 1 : xs - 1;
+    uint32_t v = active ? src[(size_t)xw * plane] : 0u;
+    int s = 0;
+    for (int x = xs - 1; x <= xe; ++x, ++s) {
+        int xn = x + 1 >= X ? x + 1 - X : x + 1;
+        uint32_t vnext = (x < xe && active) ? src[(size_t)xn * plane] : 0u;       // prefetch the next plane
+        if (ERODE) v = ~v;
+        v &= vmask;
+        const uint32_t pv = __shfl_sync(MDVC_FULL, v, w - 1, nw);
+        const uint32_t nv = __shfl_sync(MDVC_FULL, v, w + 1, nw);
+        const uint32_t down_in = (w > 0) ? (pv >> 31) : ((pv >> last) & 1u);
+        const uint32_t dz = (v | (v << 1) | down_in | (v >> 1) | ((nv & 1u) << top)) & vmask;
+        uint32_t *buf = dzs[s & 1];
+        buf[t] = dz;
+        __syncthreads();
+        uint32_t P = 0;
+        if (is_out) {
+            P = buf[t - nw] | dz | buf[t + nw];
+            if (s >= 2) {
+                uint32_t o = Pm2 | Pm1 | P;
+                if (ERODE) o = ~o & vmask;
+                uint32_t *op = dst + (size_t)(x - 1) * plane;
+                *op = o;
+                if (w == nw - 1) for (int k = 1; k < pitch - nw + 1; ++k) op[k] = 0u;
+            }
+        }
+        Pm2 = Pm1; Pm1 = P;
+        v = vnext;
+    }
+}
+
 static int launch_morph(const uint32_t *src, uint32_t *dst, int X, int Y, int Z, int pitch, bool erode, cudaStream_t st) {
     int nw = mdvc_words(Z);
     if (nw * 3 > MORPH_MAX_THREADS) {      // very long rows: the simple kernel
@@ -336,7 +393,10 @@ static int launch_morph(const uint32_t *src, uint32_t *dst, int X, int Y, int Z,
     xchunks = (X + TX - 1) / TX;
     int threads = ((JT * nw + 31) / 32) * 32;
     dim3 grid(ny, xchunks);
-    if (erode) k_morph_sweep<true><<<grid, threads, 0, st>>>(src, dst, X, Y, Z, pitch, nw, JT, TX);
+    if ((nw & (nw - 1)) == 0 && nw <= 32) {
+        if (erode) k_morph_sweep_p2<true><<<grid, threads, 0, st>>>(src, dst, X, Y, Z, pitch, nw, JT, TX);
+        else k_morph_sweep_p2<false><<<grid, threads, 0, st>>>(src, dst, X, Y, Z, pitch, nw, JT, TX);
+    } else if (erode) k_morph_sweep<true><<<grid, threads, 0, st>>>(src, dst, X, Y, Z, pitch, nw, JT, TX);
     else k_morph_sweep<false><<<grid, threads, 0, st>>>(src, dst, X, Y, Z, pitch, nw, JT, TX);
     MDVC_LAUNCH_CHECK();
     return MDVC_OK;
