@@ -18,7 +18,6 @@
 #include "common.cuh"
 #include "scan.cuh"
 
-#include <stdlib.h>
 #include <string.h>
 
 // ------------------------------------------------------------------------------------------
@@ -449,20 +448,6 @@ k_link_round(const uint32_t *__restrict__ bits, Dims D, const Hdr *__restrict__ 
                 }
             }
         }
-    }
-}
-
-// depth -> 1.  Read-only climb; parent[i] is written by thread i alone (see k_flatten_flags).
-__global__ void __launch_bounds__(256)
-k_flatten(const Hdr *__restrict__ h, uint32_t *parent) {
-    uint32_t R = h->run_eff;
-    uint32_t stride = gridDim.x * blockDim.x;
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < R; i += stride) {
-        uint32_t p = __ldcg(&parent[i]);
-        if (p == i) continue;
-        uint32_t root = p, up;
-        while ((up = __ldcg(&parent[root])) != root) root = up;
-        if (root != p) parent[i] = root;
     }
 }
 
@@ -1186,18 +1171,7 @@ __global__ void k_run_components(const Hdr *__restrict__ h, const int32_t *__res
 // and streams the row out with 16-byte stores.
 // ------------------------------------------------------------------------------------------
 // 256-bit streaming store (sm_100: STG.E.EF.256)
-__device__ int g_expand_hint = 1;
 __device__ __forceinline__ void st_v8_cs(int32_t *p, int a, int b, int c, int d, int e, int f, int g, int h) {
-    if (g_expand_hint == 0) {
-        asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(a), "r"(b), "r"(c), "r"(d), "r"(e), "r"(f),
-                     "r"(g), "r"(h) : "memory");
-        return;
-    }
-    if (g_expand_hint == 2) {
-        asm volatile("st.global.wt.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(a), "r"(b), "r"(c), "r"(d), "r"(e), "r"(f),
-                     "r"(g), "r"(h) : "memory");
-        return;
-    }
     asm volatile("st.global.cs.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(a), "r"(b), "r"(c), "r"(d), "r"(e), "r"(f),
                  "r"(g), "r"(h)
                  : "memory");
@@ -1347,9 +1321,7 @@ extern "C" int mdvc_frame_label(const uint32_t *bits, int X, int Y, int Z, int p
     MDVC_CUDA_CHECK(cudaMemsetAsync(vol, 0, (size_t)caps->max_labels * 8, st));
     int g = pick_group(D.nw);
     long long row_threads = D.rows * g;
-    static int row_bps = 0;
-    if (!row_bps) { const char *e = getenv("MDVC_ROW_BPS"); row_bps = e ? atoi(e) : 8; }
-    unsigned row_grid = mdvc_grid(row_threads / 4, 256, row_bps);      // four rows per group and iteration
+    unsigned row_grid = mdvc_grid(row_threads / 4, 256, 8);             // four rows per group and iteration
     MDVC_DISPATCH_G(g, (k_count_runs<G><<<row_grid, 256, 0, st>>>(bits, D, rowoff)));
     MDVC_LAUNCH_CHECK();
     rc = mdvc_exclusive_scan<uint32_t>(rowoff, rowoff, nullptr, (uint32_t)D.rows, at<uint32_t>(ws, L.tile32),
@@ -1506,14 +1478,10 @@ static int expand_rows(const uint32_t *bits, int X, int Y, int Z, int pitch, voi
     int g = pick_group(D.nw);
     uintptr_t both = reinterpret_cast<uintptr_t>(labels_out) | reinterpret_cast<uintptr_t>(components_out);
     int vec = (Z % 8 == 0 && (both & 31) == 0) ? 8 : ((Z % 4 == 0 && (both & 15) == 0) ? 4 : 0);
-    static int bps = 0, hint = -1;
-    if (!bps) {
-        const char *e;
-        bps = (e = getenv("MDVC_EXPAND_BPS")) ? atoi(e) : 256;
-        hint = (e = getenv("MDVC_EXPAND_HINT")) ? atoi(e) : 1;
-        cudaMemcpyToSymbol(g_expand_hint, &hint, sizeof(int));
-    }
-    unsigned grid = mdvc_grid((row_end - row_begin) * g, 256, bps);
+    // Not a persistent grid: one short-lived CTA per 8 row groups keeps the concurrently written rows close
+    // together in memory (measured on B200 at 1024^3, labels + components: 1.45 ms with 8 CTAs/SM grid-stride,
+    // 1.27 ms = 6.77 TB/s with up to 256 CTAs/SM).
+    unsigned grid = mdvc_grid((row_end - row_begin) * g, 256, 256);
     const Hdr *h = at<Hdr>(ws, L.hdr);
     const uint32_t *rowoff = at<uint32_t>(ws, L.rowoff);
     const int32_t *lab = at<int32_t>(ws, L.lab), *rc_ = at<int32_t>(ws, L.runcomp);

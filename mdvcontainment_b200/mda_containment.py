@@ -169,6 +169,14 @@ def _tempfactors_attr(values):
 class Containment(ContainmentBase):
     """Voxelise an AtomGroup and build its containment hierarchy (mda_containment.py:268-400)."""
 
+    @property
+    def _negative_atomgroup(self):
+        # the reference computes this set difference eagerly in the constructor (mda_containment.py:361);
+        # same value, evaluated lazily because it costs an np.isin over the whole universe
+        if self._negative_cache is None:
+            self._negative_cache = self._universe.atoms - self._atomgroup
+        return self._negative_cache
+
     def __init__(self, atomgroup, resolution, closing=False, slab=False, morph="", max_offset=0.05,
                  verbose=False, write_structures=False, no_mapping=False, return_counts=True,
                  betafactors=True):
@@ -204,7 +212,7 @@ class Containment(ContainmentBase):
         self._return_counts = return_counts
         self._betafactors = betafactors
         self._universe = atomgroup.universe
-        self._negative_atomgroup = self._universe.atoms - self._atomgroup
+        self._negative_cache = None          # universe.atoms - atomgroup, built on first access
 
         self._bits, self._voxel2atom = self._voxelize_atomgroup()
         self._grid_shape = self._bits.shape

@@ -35,6 +35,10 @@ class AtomGroup:
     def __init__(self, universe: "Universe", ix):
         self._u = universe
         self._ix = np.asarray(ix, dtype=np.int64).reshape(-1)
+        n = len(self._ix)
+        # contiguous index ranges (e.g. universe.atoms) read and write positions as slices, not gathers
+        self._range = (int(self._ix[0]), int(self._ix[0]) + n) if n and int(self._ix[-1]) - int(self._ix[0]) == n - 1 \
+            and bool(np.all(self._ix[1:] - self._ix[:-1] == 1)) else None
 
     # --- identity -------------------------------------------------------
     @property
@@ -63,12 +67,17 @@ class AtomGroup:
     # --- coordinates ----------------------------------------------------
     @property
     def positions(self):
+        if self._range is not None:
+            return self._u._positions[self._range[0]:self._range[1]].copy()
         return self._u._positions[self._ix]
 
     @positions.setter
     def positions(self, value):
         # MDAnalysis stores coordinates as float32; assignment casts.
-        self._u._positions[self._ix] = np.asarray(value).astype(np.float32)
+        if self._range is not None:
+            self._u._positions[self._range[0]:self._range[1]] = value
+        else:
+            self._u._positions[self._ix] = np.asarray(value).astype(np.float32)
 
     @property
     def dimensions(self):
