@@ -125,55 +125,69 @@ __device__ __forceinline__ long long floordiv_ll(long long a, long long b) {
 __global__ void __launch_bounds__(256)
 k_bin_atoms(const float *__restrict__ pos, long long n, BinParams P, uint32_t *__restrict__ occ, int pitch,
             int32_t *__restrict__ vox_out, float *pos_out) {
-    long long stride = (long long)gridDim.x * blockDim.x;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-        const bool live = true;
-        long long v[3] = {0, 0, 0};
+    // positions are AoS (x,y,z per atom = 12 B): a tile of 256 atoms is fetched as 192 coalesced float4 loads
+    // into shared memory and read back with stride 3 (conflict-free), instead of three strided 4-byte loads
+    // per atom that each touch every sector of the tile (ncu: 2.5x the compulsory DRAM reads)
+    __shared__ float sp[256 * 3];
+    const bool vec_ok = (reinterpret_cast<uintptr_t>(pos) & 15) == 0;
+    const long long n_tiles = (n + 255) / 256;
+    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const long long base = tile * 256;
+        const int cnt = (int)min(256ll, n - base);
+        __syncthreads();
+        if (vec_ok && cnt == 256) {
+            if (threadIdx.x < 192)
+                reinterpret_cast<float4 *>(sp)[threadIdx.x] = __ldcs(reinterpret_cast<const float4 *>(pos + 3 * base) + threadIdx.x);
+        } else {
+            for (int k = threadIdx.x; k < 3 * cnt; k += 256) sp[k] = pos[3 * base + k];
+        }
+        __syncthreads();
+        if ((int)threadIdx.x >= cnt) continue;
+        const long long i = base + threadIdx.x;
+        long long v[3];
         double f[3];
-        if (live) {
-            double p0 = (double)__ldcs(pos + 3 * i), p1 = (double)__ldcs(pos + 3 * i + 1), p2 = (double)__ldcs(pos + 3 * i + 2);
+        const double p0 = (double)sp[3 * threadIdx.x], p1 = (double)sp[3 * threadIdx.x + 1], p2 = (double)sp[3 * threadIdx.x + 2];
 #pragma unroll
-            for (int j = 0; j < 3; ++j) {
-                double fj = __fma_rn(p2, P.T[6 + j], __fma_rn(p1, P.T[3 + j], __dmul_rn(p0, P.T[j])));
-                double fl = floor(fj);
-                v[j] = (long long)fl;
-                f[j] = __dsub_rn(fj, (double)v[j]);
+        for (int j = 0; j < 3; ++j) {
+            double fj = __fma_rn(p2, P.T[6 + j], __fma_rn(p1, P.T[3 + j], __dmul_rn(p0, P.T[j])));
+            double fl = floor(fj);
+            v[j] = (long long)fl;
+            f[j] = __dsub_rn(fj, (double)v[j]);
+        }
+        const long long lim = 1ll << 28;
+        if (v[0] > -lim && v[0] < lim && v[1] > -lim && v[1] < lim && v[2] > -lim && v[2] < lim && P.nbox[0] < lim &&
+            P.nbox[4] < lim && P.nbox[8] < lim) {
+            // everything fits 32 bits (any realistic box): same arithmetic without 64-bit multiplies/divides
+            int w3[3] = {(int)v[0], (int)v[1], (int)v[2]};
+#pragma unroll
+            for (int dim = 2; dim >= 0; --dim) {
+                int nn = (int)P.nbox[4 * dim], a = w3[dim], sh;
+                if (a >= 0) sh = a < nn ? 0 : (a < 2 * nn ? 1 : a / nn);
+                else sh = a >= -nn ? -1 : -((-a + nn - 1) / nn);
+#pragma unroll
+                for (int j = 0; j < 3; ++j) w3[j] -= sh * (int)P.nbox[3 * dim + j];
             }
-            const long long lim = 1ll << 28;
-            if (v[0] > -lim && v[0] < lim && v[1] > -lim && v[1] < lim && v[2] > -lim && v[2] < lim && P.nbox[0] < lim &&
-                P.nbox[4] < lim && P.nbox[8] < lim) {
-                // everything fits 32 bits (any realistic box): same arithmetic without 64-bit multiplies/divides
-                int w3[3] = {(int)v[0], (int)v[1], (int)v[2]};
+            v[0] = w3[0]; v[1] = w3[1]; v[2] = w3[2];
+        } else {
 #pragma unroll
-                for (int dim = 2; dim >= 0; --dim) {
-                    int n = (int)P.nbox[4 * dim], a = w3[dim], sh;
-                    if (a >= 0) sh = a < n ? 0 : (a < 2 * n ? 1 : a / n);
-                    else sh = a >= -n ? -1 : -((-a + n - 1) / n);
+            for (int dim = 2; dim >= 0; --dim) {
+                long long s = floordiv_ll(v[dim], P.nbox[4 * dim]);
 #pragma unroll
-                    for (int j = 0; j < 3; ++j) w3[j] -= sh * (int)P.nbox[3 * dim + j];
-                }
-                v[0] = w3[0]; v[1] = w3[1]; v[2] = w3[2];
-            } else {
-#pragma unroll
-                for (int dim = 2; dim >= 0; --dim) {
-                    long long s = floordiv_ll(v[dim], P.nbox[4 * dim]);
-#pragma unroll
-                    for (int j = 0; j < 3; ++j) v[j] -= s * P.nbox[3 * dim + j];
-                }
-            }
-            if (vox_out) {
-                vox_out[3 * i] = (int32_t)v[0]; vox_out[3 * i + 1] = (int32_t)v[1]; vox_out[3 * i + 2] = (int32_t)v[2];
-            }
-            if (pos_out) {
-                double g0 = __dadd_rn((double)v[0], f[0]), g1 = __dadd_rn((double)v[1], f[1]),
-                       g2 = __dadd_rn((double)v[2], f[2]);
-#pragma unroll
-                for (int j = 0; j < 3; ++j)
-                    pos_out[3 * i + j] = (float)__fma_rn(g2, P.invT[6 + j],
-                                                __fma_rn(g1, P.invT[3 + j], __dmul_rn(g0, P.invT[j])));
+                for (int j = 0; j < 3; ++j) v[j] -= s * P.nbox[3 * dim + j];
             }
         }
-        if (occ && live) {
+        if (vox_out) {
+            vox_out[3 * i] = (int32_t)v[0]; vox_out[3 * i + 1] = (int32_t)v[1]; vox_out[3 * i + 2] = (int32_t)v[2];
+        }
+        if (pos_out) {
+            double g0 = __dadd_rn((double)v[0], f[0]), g1 = __dadd_rn((double)v[1], f[1]),
+                   g2 = __dadd_rn((double)v[2], f[2]);
+#pragma unroll
+            for (int j = 0; j < 3; ++j)
+                pos_out[3 * i + j] = (float)__fma_rn(g2, P.invT[6 + j],
+                                            __fma_rn(g1, P.invT[3 + j], __dmul_rn(g0, P.invT[j])));
+        }
+        if (occ) {
             long long X = P.nbox[0], Y = P.nbox[4], Z = P.nbox[8];
             if (v[0] >= 0 && v[0] < X && v[1] >= 0 && v[1] < Y && v[2] >= 0 && v[2] < Z) {
                 // Fire-and-forget RED.OR.  A __match_any_sync aggregation of lanes hitting the same word was
@@ -197,7 +211,7 @@ extern "C" int mdvc_bin_atoms(const float *pos, long long n, const double *T_hos
     memcpy(P.T, T_host, sizeof(P.T));
     memcpy(P.invT, invT_host, sizeof(P.invT));
     memcpy(P.nbox, nbox_host, sizeof(P.nbox));
-    k_bin_atoms<<<mdvc_grid(n, 256), 256, 0, (cudaStream_t)stream>>>(pos, n, P, occ_bits, pitch, vox_out, pos_out);
+    k_bin_atoms<<<mdvc_grid(n, 256, 64), 256, 0, (cudaStream_t)stream>>>(pos, n, P, occ_bits, pitch, vox_out, pos_out);
     MDVC_LAUNCH_CHECK();
     return MDVC_OK;
 }
