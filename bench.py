@@ -231,6 +231,7 @@ def run_ours(args):
         run_frames(steps, host)
         for p in pipes:                                   # the default-stream end event must follow all pipelines
             torch.cuda.current_stream().wait_stream(p.stream)
+            torch.cuda.current_stream().wait_stream(p.stream_x)
         e1.record()
         barrier()
         ms = e0.elapsed_time(e1)

@@ -55,7 +55,11 @@ class FramePipeline:
         self.lut_dev = None
         self.lib = _lib.load()
         self._alloc_host()
-        self.stream = torch.cuda.Stream(device=self.device)      # every launch of this pipeline goes here
+        # stage 1 (bin .. pairs: latency/issue-bound, small) on a high-priority stream, the dense write (HBM-bound,
+        # tens of thousands of short CTAs) on a low-priority one: with several pipelines in flight the block
+        # scheduler then slots the next frame's stage-1 CTAs in between the current frame's write CTAs
+        self.stream = torch.cuda.Stream(device=self.device, priority=-1)
+        self.stream_x = torch.cuda.Stream(device=self.device, priority=0)
         self.ev_stage1 = torch.cuda.Event()
         self.expand_events = []                                   # (start, end) of every dense write
         self._bits = None
@@ -111,6 +115,7 @@ class FramePipeline:
         """Enqueue bin -> morph -> label -> pairs and the small read-backs on this pipeline's stream; returns
         immediately so the caller can finish() another pipeline's frame meanwhile."""
         self._t0 = time.perf_counter()
+        self.stream.wait_stream(self.stream_x)               # the previous frame's dense write still reads our buffers
         with torch.cuda.stream(self.stream):
             if host_positions is not None:
                 n = host_positions.shape[0]
@@ -126,7 +131,7 @@ class FramePipeline:
         bits = self._bits
         with torch.cuda.stream(self.stream):
             out = self._finish(bits)
-        torch.cuda.current_stream().wait_stream(self.stream)     # the caller's stream sees the finished grids
+        torch.cuda.current_stream().wait_stream(self.stream_x)   # the caller's stream sees the finished grids
         return out
 
     def analyse(self, bits: dev.BitGrid) -> FrameOutput:
@@ -177,11 +182,14 @@ class FramePipeline:
             lut_dev = self.lut_dev[:nl]
         else:
             lut_dev = torch.from_numpy(lut).to(self.device)
-        self.plan.set_lut(lut_dev)
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        self.plan.expand(bits, self.labels, self.components)
-        e1.record()
+        wr = self.stream_x if torch.cuda.current_stream() == self.stream else torch.cuda.current_stream()
+        wr.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(wr):
+            self.plan.set_lut(lut_dev)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            self.plan.expand(bits, self.labels, self.components)
+            e1.record()
         self.expand_events.append((e0, e1))
         t2 = time.perf_counter()
         lo = int(lut.min())
@@ -208,7 +216,8 @@ class FramePipeline:
         """Mean device time of the dense writes recorded since the last call (CUDA events on the launching stream)."""
         if not self.expand_events:
             return 0.0
-        self.stream.synchronize()
+        self.stream_x.synchronize()
+        torch.cuda.current_stream().synchronize()
         ms = [a.elapsed_time(b) for a, b in self.expand_events]
         self.expand_events = []
         return sum(ms) / len(ms)
