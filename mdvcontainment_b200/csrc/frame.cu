@@ -990,6 +990,24 @@ k_tile_pairs(const uint32_t *__restrict__ bits, Dims D, Hdr *h, const uint32_t *
                     pj[q] = soff[nsl[q]]; pe[q] = soff[nsl[q] + 1];
                 }
                 const uint32_t pol0 = spol[slot];
+                // Shortcut for in-box neighbour rows that mirror this row: same number of runs, same first
+                // value, same label per run, and starts that interleave (every run starts before the next run
+                // of the other row: s'_m < s_{m+1} and s_m < s'_{m+1}).  Then run k only reaches runs k-1, k,
+                // k+1 of the neighbour, whose labels are this row's own neighbours' labels, so every cross-row
+                // contact is already among the in-row contacts emitted below.  True for most row pairs of
+                // smooth structures; anything else takes the walk.
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int ns = nsl[q];
+                    if (pj[q] == pe[q] || ((q == 0 ? 0 : sx_other) | ssy[ns])) continue;
+                    const uint32_t n = re0 - rb0, pb = pj[q];
+                    bool mirror = (pe[q] - pb) == n && spol[ns] == pol0;
+                    for (uint32_t k = 0; mirror && k < n; ++k) {
+                        mirror = tv[pb + k] == tv[rb0 + k] &&
+                                 (k + 1 >= n || (tz[pb + k] < tz[rb0 + k + 1] && tz[rb0 + k] < tz[pb + k + 1]));
+                    }
+                    if (mirror) pj[q] = pe[q];
+                }
                 for (uint32_t k = rb0; k < re0; ++k) {
                     const int a = (int)tz[k];
                     const int b = (k + 1 < re0) ? (int)tz[k + 1] - 1 : D.Z - 1;

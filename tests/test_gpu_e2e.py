@@ -148,3 +148,25 @@ def test_frame_pipeline_and_trajectory_driver_match_containment():
         assert np.array_equal(out.labels_dev.cpu().numpy(), vc.nonp_labeled_grid_device.cpu().numpy())
         assert res[f]["str"] == str(vc)
         assert res[f]["counts"] == {int(k): int(v) for k, v in vc.voxel_counts.items()}
+
+
+def test_translation_invariance_of_the_containment_hierarchy():
+    """README.md:12 of the reference: rolling the periodic grid must not change the hierarchy (up to renumbering)."""
+    import networkx as nx
+    from mdvcontainment_b200 import VoxelContainment
+    rng = np.random.default_rng(5)
+    base = VOX["perlin_48x32x16_s2_closed"]["grid"]
+
+    def signature(vc):
+        g = vc.containment_graph
+        lab = {n: (int(vc.voxel_counts[n]), int(vc.component_ranks[n]), int(n) > 0) for n in g.nodes}
+        return lab, g
+
+    ref_lab, ref_g = signature(VoxelContainment(base))
+    for _ in range(4):
+        shift = tuple(int(rng.integers(0, s)) for s in base.shape)
+        vc = VoxelContainment(np.roll(base, shift, axis=(0, 1, 2)))
+        lab, g = signature(vc)
+        assert sorted(lab.values()) == sorted(ref_lab.values())
+        nx.set_node_attributes(g, lab, "sig"); nx.set_node_attributes(ref_g, ref_lab, "sig")
+        assert nx.is_isomorphic(nx.DiGraph(g), nx.DiGraph(ref_g), node_match=lambda a, b: a["sig"] == b["sig"])
