@@ -216,6 +216,15 @@ int mdvc_atom_select(const uint32_t *order, const unsigned long long *keys, long
                      const long long *atom_ix, uint32_t *scratch, long long *out,
                      unsigned long long *n_out_dev, void *stream);
 
+/* voxels2atomgroup_cy (atoms_voxels_mapping.pyx:59-91) for an explicit voxel list query[m][3] (int32): the atoms of
+ * each query voxel, query order then atom order, mapped through atom_ix (int64, optional).  order/keys are the CSR
+ * arrays of mdvc_atom_sort_by_voxel.  Call with out = NULL to obtain the count in *n_out_dev, then with a buffer of
+ * that capacity.  scratch: mdvc_atom_gather_scratch_words(m) uint32. */
+size_t mdvc_atom_gather_scratch_words(long long m);
+int mdvc_atom_gather_voxels(const int32_t *query, long long m, int X, int Y, int Z, const uint32_t *order,
+                            const unsigned long long *keys, long long n, const long long *atom_ix, uint32_t *scratch,
+                            long long *out, unsigned long long out_cap, unsigned long long *n_out_dev, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -75,6 +75,8 @@ SIGNATURES = {
     "mdvc_atom_components": (_I, [_P, _LL, _P, _I, _I, _I, _P, _P]),
     "mdvc_atom_sort_scratch_bytes": (_SZ, [_LL]),
     "mdvc_atom_sort_by_voxel": (_I, [_P, _LL, _I, _I, _I, _P, _P, _P, _P]),
+    "mdvc_atom_gather_scratch_words": (_SZ, [_LL]),
+    "mdvc_atom_gather_voxels": (_I, [_P, _LL, _I, _I, _I, _P, _P, _LL, _P, _P, _P, _U64, _P, _P]),
     "mdvc_atom_select": (_I, [_P, _P, _LL, _P, _P, _I, _I, _P, _P, _P, _P, _P]),
 }
 

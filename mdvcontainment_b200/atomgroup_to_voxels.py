@@ -172,7 +172,10 @@ def voxels2atomgroup(voxels, mapping, atomgroup):
     q = np.asarray(voxels, dtype=np.int32).reshape(-1, 3)
     if len(q) == 0:
         return atomgroup.universe.atoms[[]]
-    m = mapping._as_dict() if isinstance(mapping, DeviceMapping) else mapping
+    if isinstance(mapping, DeviceMapping):             # device gather over the voxel-sorted atom list
+        idx = mapping.csr.gather_voxels(q, mapping.atom_ix_dev)
+        return atomgroup.universe.atoms[idx] if len(idx) else atomgroup.universe.atoms[[]]
+    m = mapping
     v2a, atom_indices = m['voxel_to_atoms'], m['atom_indices']
     hits = [v2a[k] for k in map(tuple, q.tolist()) if k in v2a]
     if not hits:

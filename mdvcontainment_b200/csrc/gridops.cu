@@ -595,3 +595,68 @@ extern "C" int mdvc_atom_select(const uint32_t *order, const unsigned long long 
     MDVC_LAUNCH_CHECK();
     return MDVC_OK;
 }
+
+// gather for an explicit voxel list (voxels2atomgroup_cy, atoms_voxels_mapping.pyx:59-91): for every query voxel,
+// in the given order, the atoms of that voxel in atom order.  Voxels without atoms (or outside the grid) add nothing.
+__global__ void __launch_bounds__(256)
+k_vox_ranges(const int32_t *__restrict__ q, long long m, int X, int Y, int Z, const unsigned long long *__restrict__ keys,
+             long long n, uint32_t *__restrict__ start, uint32_t *__restrict__ cnt) {
+    long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < m; i += stride) {
+        int x = q[3 * i], y = q[3 * i + 1], z = q[3 * i + 2];
+        uint32_t lo = 0, c = 0;
+        if (x >= 0 && x < X && y >= 0 && y < Y && z >= 0 && z < Z) {
+            unsigned long long key = (unsigned long long)(((long long)x * Y + y) * Z + z);
+            long long a = 0, b = n;                       // lower bound
+            while (a < b) { long long mid = (a + b) >> 1; if (keys[mid] < key) a = mid + 1; else b = mid; }
+            long long first = a;
+            b = n;                                        // upper bound
+            while (a < b) { long long mid = (a + b) >> 1; if (keys[mid] <= key) a = mid + 1; else b = mid; }
+            lo = (uint32_t)first; c = (uint32_t)(a - first);
+        }
+        start[i] = lo; cnt[i] = c;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+k_vox_gather(long long m, const uint32_t *__restrict__ start, const uint32_t *__restrict__ cnt_raw,
+             const uint32_t *__restrict__ off, const uint32_t *__restrict__ order, const long long *__restrict__ atom_ix,
+             long long *__restrict__ out, unsigned long long out_cap) {
+    long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < m; i += stride) {
+        uint32_t s0 = start[i], c = cnt_raw[i];
+        unsigned long long o = off[i];
+        for (uint32_t k = 0; k < c && o + k < out_cap; ++k) {
+            uint32_t a = order[s0 + k];
+            out[o + k] = atom_ix ? atom_ix[a] : (long long)a;
+        }
+    }
+}
+
+extern "C" size_t mdvc_atom_gather_scratch_words(long long m) {
+    return (size_t)m * 3 + mdvc_scan_scratch_elems((uint32_t)(m > 0 ? m : 1)) + 8;
+}
+
+extern "C" int mdvc_atom_gather_voxels(const int32_t *query, long long m, int X, int Y, int Z, const uint32_t *order,
+                                       const unsigned long long *keys, long long n, const long long *atom_ix,
+                                       uint32_t *scratch, long long *out, unsigned long long out_cap,
+                                       unsigned long long *n_out_dev, void *stream) {
+    if (m < 0 || n < 0 || m >= (1ll << 31) || n >= (1ll << 31) || !scratch || !n_out_dev || X <= 0 || Y <= 0 || Z <= 0 ||
+        (m > 0 && !query) || (n > 0 && (!order || !keys)))
+        return MDVC_ERR_BADARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (m == 0) { MDVC_CUDA_CHECK(cudaMemsetAsync(n_out_dev, 0, 8, st)); return MDVC_OK; }
+    uint32_t *start = scratch, *cnt = scratch + m, *off = scratch + 2 * m, *tile_scratch = scratch + 3 * m;
+    uint32_t *total = tile_scratch + mdvc_scan_scratch_elems((uint32_t)m);
+    k_vox_ranges<<<mdvc_grid(m, 256, 8), 256, 0, st>>>(query, m, X, Y, Z, keys, n, start, cnt);
+    MDVC_LAUNCH_CHECK();
+    int rc = mdvc_exclusive_scan<uint32_t>(cnt, off, nullptr, (uint32_t)m, tile_scratch, total, nullptr, st);
+    if (rc) return rc;
+    k_widen_count<<<1, 1, 0, st>>>(total, n_out_dev);
+    MDVC_LAUNCH_CHECK();
+    if (out && out_cap) {
+        k_vox_gather<<<mdvc_grid(m, 256, 8), 256, 0, st>>>(m, start, cnt, off, order, atom_ix, out, out_cap);
+        MDVC_LAUNCH_CHECK();
+    }
+    return MDVC_OK;
+}

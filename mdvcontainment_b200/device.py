@@ -355,3 +355,24 @@ class AtomCSR:
         check(lib.mdvc_atom_select(_ptr(self.order), _ptr(self.keys), n, _ptr(grid), _ptr(member), int(lo), int(n_values),
                                    _ptr(atom_ix), _ptr(scratch), _ptr(out), _ptr(n_out), _stream()), "mdvc_atom_select")
         return out[: int(n_out.item())].cpu().numpy()
+
+    def gather_voxels(self, query_voxels, atom_ix: torch.Tensor | None) -> np.ndarray:
+        """Atoms of an explicit voxel list (query order, then atom order) -> int64 atom indices."""
+        q = np.ascontiguousarray(np.asarray(query_voxels, dtype=np.int32).reshape(-1, 3))
+        m, n = len(q), int(self.order.shape[0])
+        if m == 0 or n == 0:
+            return np.array([], dtype=np.int64)
+        lib = _lib.load()
+        dev_ = self.order.device
+        qd = torch.from_numpy(q).to(dev_)
+        scratch = torch.empty(lib.mdvc_atom_gather_scratch_words(m), dtype=torch.int32, device=dev_)
+        n_out = torch.zeros(1, dtype=torch.int64, device=dev_)
+        X, Y, Z = self.shape
+        args = (_ptr(qd), m, X, Y, Z, _ptr(self.order), _ptr(self.keys), n, _ptr(atom_ix), _ptr(scratch))
+        check(lib.mdvc_atom_gather_voxels(*args, None, 0, _ptr(n_out), _stream()), "mdvc_atom_gather_voxels")
+        total = int(n_out.item())
+        if total == 0:
+            return np.array([], dtype=np.int64)
+        out = torch.empty(total, dtype=torch.int64, device=dev_)
+        check(lib.mdvc_atom_gather_voxels(*args, _ptr(out), total, _ptr(n_out), _stream()), "mdvc_atom_gather_voxels")
+        return out.cpu().numpy()

@@ -87,9 +87,28 @@ def _view_order(all_nodes, subset_array):
     over the Python ``set`` built from the subset, whose order depends on CPython's hashing of the
     np.int32 scalars.  Rather than emulating either, ask the installed networkx itself on a
     node-only graph (no edges needed for the order)."""
+    # the order depends only on the two node sets; label sets are contiguous ranges (-nF..-1, 1..nT) on the
+    # frame path, so trajectories hit this cache on nearly every frame
+    n_all, n_sub = len(all_nodes), len(subset_array)
+    key = None
+    if 0 < n_sub and n_all <= 4096:
+        lo, hi = all_nodes[0], all_nodes[-1]
+        s0, s1 = int(subset_array[0]), int(subset_array[-1])
+        canonical = all_nodes == [v for v in range(lo, hi + 1) if v != 0]
+        if canonical and subset_array.tolist() == [v for v in range(s0, s1 + 1) if v != 0]:
+            key = (lo, hi, s0, s1, subset_array.dtype.str)
+        hit = _VIEW_ORDER_CACHE.get(key)
+        if hit is not None:
+            return hit
     g = nx.MultiDiGraph()
     g.add_nodes_from(all_nodes)
-    return list(g.subgraph(subset_array))
+    order = list(g.subgraph(subset_array))
+    if key is not None and len(_VIEW_ORDER_CACHE) < 256:
+        _VIEW_ORDER_CACHE[key] = order
+    return order
+
+
+_VIEW_ORDER_CACHE = {}
 
 
 def periodic_components(lg: LabelGraph):

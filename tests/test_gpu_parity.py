@@ -312,3 +312,8 @@ def test_atom_components_and_csr(dev):
         want = vo.voxels2atoms(q, mapping)
         got = csr.select(cd, nodes, -3, 7, torch.from_numpy(ix).cuda())
         assert got.dtype == np.int64 and np.array_equal(got, want)
+        # explicit voxel lists: C-order, shuffled, with repeats, empty voxels and out-of-grid entries
+        for qq in (q, rng.permutation(q)[:500], np.concatenate([q[:50], q[:50], [[-1, 0, 0], [99, 0, 0]]]) if len(q) else q):
+            qq = np.asarray(qq).reshape(-1, 3)
+            inside = (qq >= 0).all(1) & (qq < np.array(shape)).all(1)
+            assert np.array_equal(csr.gather_voxels(qq, torch.from_numpy(ix).cuda()), vo.voxels2atoms(qq[inside], mapping))
