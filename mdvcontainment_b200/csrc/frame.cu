@@ -18,6 +18,7 @@
 #include "common.cuh"
 #include "scan.cuh"
 
+#include <limits.h>
 #include <string.h>
 
 // ------------------------------------------------------------------------------------------
@@ -921,6 +922,9 @@ k_tile_pairs(const uint32_t *__restrict__ bits, Dims D, Hdr *h, const uint32_t *
     PairSink bs{&b_cache, bset, b_slots, &h->flags, MDVC_OVERFLOW_BRIDGES, MDVC_KEY_EMPTY, MDVC_KEY_EMPTY};
     const int spp = (D.Y + PT_TY - 1) / PT_TY;
     const long long n_tiles = (long long)D.X * spp;
+    int zc[9], zc_first = 0, zc_last = 0, zc_flags = -1;        // last emitted z-face signature of this thread
+#pragma unroll
+    for (int q = 0; q < 9; ++q) zc[q] = 0;
     for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const int x = (int)(tile / spp), y0 = (int)(tile % spp) * PT_TY;
         const int ny = min(PT_TY, D.Y - y0);
@@ -1032,16 +1036,38 @@ k_tile_pairs(const uint32_t *__restrict__ bits, Dims D, Hdr *h, const uint32_t *
                     }
                 }
                 if (periodic) {
+                    // z-face steps: nine records per row whose labels and wrap flags almost always repeat from
+                    // the previous row this thread handled.  The nine keys cycle through the 2-key cache, so
+                    // each would take the out-of-line set insertion; instead the row's z-face signature (the
+                    // labels involved + wrap flags) is compared with the last one emitted and skipped if equal.
                     const int la_first = tv[rb0], la_last = tv[re0 - 1];
-                    for (int q = 0; q < 6; ++q) {                          // +z from the last run
+                    int zl[9], flags = sx_other + 1;
+#pragma unroll
+                    for (int q = 0; q < 6; ++q) {
                         const int ns = (q < 3 ? 0 : PT_ROWS) + slot + (q % 3) - 1;
-                        if (soff[ns] == soff[ns + 1]) continue;
-                        emit_bridge(bs, la_last, tv[soff[ns]], q < 3 ? 0 : sx_other, ssy[ns], 1);
+                        zl[q] = soff[ns] == soff[ns + 1] ? INT_MIN : tv[soff[ns]];
+                        flags = flags * 4 + (ssy[ns] + 1);
                     }
-                    for (int q = 0; q < 3; ++q) {                          // -z from the first run
+#pragma unroll
+                    for (int q = 0; q < 3; ++q) {
                         const int ns = PT_ROWS + slot + q - 1;
-                        if (soff[ns] == soff[ns + 1]) continue;
-                        emit_bridge(bs, la_first, tv[soff[ns + 1] - 1], sx_other, ssy[ns], -1);
+                        zl[6 + q] = soff[ns] == soff[ns + 1] ? INT_MIN : tv[soff[ns + 1] - 1];
+                    }
+                    bool same = la_first == zc_first && la_last == zc_last && flags == zc_flags;
+#pragma unroll
+                    for (int q = 0; q < 9; ++q) same = same && zl[q] == zc[q];
+                    if (!same) {
+                        zc_first = la_first; zc_last = la_last; zc_flags = flags;
+#pragma unroll
+                        for (int q = 0; q < 9; ++q) zc[q] = zl[q];
+                        for (int q = 0; q < 6; ++q) {                      // +z from the last run
+                            const int ns = (q < 3 ? 0 : PT_ROWS) + slot + (q % 3) - 1;
+                            if (zl[q] != INT_MIN) emit_bridge(bs, la_last, zl[q], q < 3 ? 0 : sx_other, ssy[ns], 1);
+                        }
+                        for (int q = 0; q < 3; ++q) {                      // -z from the first run
+                            const int ns = PT_ROWS + slot + q - 1;
+                            if (zl[6 + q] != INT_MIN) emit_bridge(bs, la_first, zl[6 + q], sx_other, ssy[ns], -1);
+                        }
                     }
                 }
             }
