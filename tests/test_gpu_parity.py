@@ -58,6 +58,34 @@ def test_morph_golden_closings(dev):
             assert sha(got, np.uint8) == c["sha_grid"]
 
 
+FUSED_CLOSE_SHAPES = [
+    (20, 70, 1024), (9, 33, 1000), (3, 29, 600), (1, 5, 160), (2, 1, 33), (17, 300, 128), (40, 9, 31), (5, 2, 64),
+    (33, 61, 96), (12, 130, 257), (64, 64, 64), (1, 1, 1), (4, 3, 1024),
+]
+
+
+@pytest.mark.parametrize("shape", FUSED_CLOSE_SHAPES)
+@pytest.mark.parametrize("ops", ["de", "dde", "ded", "edde"])
+def test_fused_closing_tiles(dev, shape, ops):
+    """'d' directly followed by 'e' runs as one TMA-staged launch; shapes chosen to cross y tiles, x chunks,
+    the periodic wrap inside a tile, partial last words and non-power-of-two row lengths."""
+    rng = np.random.default_rng(hash(shape) % 1000)
+    for p in (0.02, 0.3, 0.8):
+        g = rng.random(shape) < p
+        got = dev.morph(dev.BitGrid.from_bool(g), ops).to_bool().cpu().numpy()
+        assert np.array_equal(got, vo.morph(g, ops)), (shape, ops, p)
+
+
+def test_fused_closing_equals_two_steps(dev, monkeypatch):
+    from mdvcontainment_b200 import synth
+    g = synth.salt_noise_grid((192, 200, 224), salt=0.03)
+    fused = dev.morph(dev.BitGrid.from_bool(g), "de")
+    monkeypatch.setenv("MDVC_NO_FUSED_CLOSE", "1")
+    two = dev.morph(dev.BitGrid.from_bool(g), "de")
+    assert torch.equal(fused.words, two.words)
+    assert np.array_equal(two.to_bool().cpu().numpy(), vo.morph(g, "de"))
+
+
 def test_morph_rejects_unknown_op(dev):
     from mdvcontainment_b200._lib import MdvcError
     with pytest.raises(MdvcError):
