@@ -73,3 +73,24 @@ APPENDIX_D = {
     "perlin_64x64x64_s3": ("d9c9a46b5e4dd7f5", "f2fb41db4bf616f5", "d7e1354389f6c39d", "8d1024a80812ffc8", "4df70f7b642c218b"),
     "perlin_64x64x64_s3_closed": ("53733b6e0502629b", "dc73bb700857a868", "3b3791a372368f57", "afbbc468374ccc01", "843bf302879b27bd"),
 }
+
+
+def tensor_digest(t, chunk=1 << 26):
+    """Order-dependent 64-bit checksum (wrapping int64 arithmetic, so the summation order does not matter) of an
+    integer / bool torch tensor, computed on the tensor's own device: sum(value[i] * (i mod 1000003 + 1))."""
+    import torch
+    flat = t.reshape(-1)
+    acc = torch.zeros((), dtype=torch.int64, device=flat.device)
+    for s in range(0, flat.numel(), chunk):
+        part = flat[s:s + chunk].to(torch.int64)
+        w = torch.arange(s, s + part.numel(), device=flat.device, dtype=torch.int64) % 1000003 + 1
+        acc += (part * w).sum()
+    return int(acc.item())
+
+
+def fullsize_golden(name="fullsize_vesicle_1024.json"):
+    path = os.path.join(GOLD, name)
+    if not os.path.exists(path):
+        return None
+    with open(path) as fh:
+        return json.load(fh)
