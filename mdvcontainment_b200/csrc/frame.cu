@@ -305,6 +305,128 @@ k_fill_runs(const uint32_t *__restrict__ bits, Dims D, const Hdr *__restrict__ h
 }
 
 // ------------------------------------------------------------------------------------------
+// stage 1a/1b for rows of at most 128 words (Z <= 4096): LQ lanes per row, four words (one 16-byte load) per
+// lane.  Run starts inside the quad come from funnel shifts, only the quad's first word needs a neighbour lane;
+// about a third of the instructions per word of the word-per-lane kernels above.
+// ------------------------------------------------------------------------------------------
+struct QuadStarts { uint32_t s0, s1, s2, s3; };
+
+template <int LQ>
+__device__ __forceinline__ QuadStarts quad_starts(uint4 B, uint4 vm, int ql) {
+    uint32_t prev = __shfl_up_sync(MDVC_FULL, B.w, 1, LQ) >> 31;
+    if (ql == 0) prev = 0;
+    QuadStarts q;
+    q.s0 = B.x ^ ((B.x << 1) | prev);
+    if (ql == 0) q.s0 |= 1u;
+    q.s0 &= vm.x;
+    q.s1 = (B.y ^ __funnelshift_l(B.x, B.y, 1)) & vm.y;
+    q.s2 = (B.z ^ __funnelshift_l(B.y, B.z, 1)) & vm.z;
+    q.s3 = (B.w ^ __funnelshift_l(B.z, B.w, 1)) & vm.w;
+    return q;
+}
+
+__device__ __forceinline__ uint4 quad_valid_mask(int ql, int nq, int Z) {
+    if (ql >= nq) return make_uint4(0u, 0u, 0u, 0u);
+    return make_uint4(mdvc_valid_mask(4 * ql, Z), mdvc_valid_mask(4 * ql + 1, Z), mdvc_valid_mask(4 * ql + 2, Z),
+                      mdvc_valid_mask(4 * ql + 3, Z));
+}
+
+template <int LQ>
+__global__ void __launch_bounds__(256)
+k_count_runs_q(const uint32_t *__restrict__ bits, Dims D, uint32_t *__restrict__ runcount) {
+    constexpr int RPW = 32 / LQ, U = 4;
+    const int lane = threadIdx.x & 31, ql = lane & (LQ - 1), gi = lane / LQ;
+    const int nq = D.pitch >> 2;
+    const uint4 vm = quad_valid_mask(ql, nq, D.Z);
+    const uint4 *b4 = reinterpret_cast<const uint4 *>(bits);
+    long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    for (long long rb = warp * (RPW * U); rb < D.rows; rb += nwarps * (RPW * U)) {
+        uint4 B[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            long long row = rb + u * RPW + gi;
+            B[u] = (row < D.rows && ql < nq) ? __ldg(b4 + row * nq + ql) : make_uint4(0u, 0u, 0u, 0u);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            long long row = rb + u * RPW + gi;
+            QuadStarts q = quad_starts<LQ>(B[u], vm, ql);
+            uint32_t total = __popc(q.s0) + __popc(q.s1) + __popc(q.s2) + __popc(q.s3);
+#pragma unroll
+            for (int o = LQ / 2; o > 0; o >>= 1) total += __shfl_xor_sync(MDVC_FULL, total, o, LQ);
+            if (row < D.rows && ql == 0) runcount[row] = total;
+        }
+    }
+}
+
+__device__ __forceinline__ uint32_t emit_starts(uint32_t S, uint32_t id, uint32_t lin0, uint32_t *__restrict__ runstart,
+                                                uint32_t *__restrict__ parent) {
+    while (S) {
+        int k = __ffs(S) - 1;
+        S &= S - 1;
+        runstart[id] = lin0 + k;
+        parent[id] = id;
+        ++id;
+    }
+    return id;
+}
+
+template <int LQ>
+__global__ void __launch_bounds__(256)
+k_fill_runs_q(const uint32_t *__restrict__ bits, Dims D, const Hdr *__restrict__ h, const uint32_t *__restrict__ rowoff,
+              uint32_t *__restrict__ runstart, uint32_t *__restrict__ parent) {
+    if (h->run_eff == 0) return;
+    constexpr int RPW = 32 / LQ, U = 4;
+    const int lane = threadIdx.x & 31, ql = lane & (LQ - 1), gi = lane / LQ;
+    const int nq = D.pitch >> 2;
+    const uint4 vm = quad_valid_mask(ql, nq, D.Z);
+    const uint4 *b4 = reinterpret_cast<const uint4 *>(bits);
+    long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    for (long long rb = warp * (RPW * U); rb < D.rows; rb += nwarps * (RPW * U)) {
+        uint4 B[U];
+        uint32_t base[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            long long row = rb + u * RPW + gi;
+            bool rv = row < D.rows;
+            B[u] = (rv && ql < nq) ? __ldg(b4 + row * nq + ql) : make_uint4(0u, 0u, 0u, 0u);
+            base[u] = rv ? rowoff[row] : 0u;
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            long long row = rb + u * RPW + gi;
+            QuadStarts q = quad_starts<LQ>(B[u], vm, ql);
+            const uint32_t cnt = __popc(q.s0) + __popc(q.s1) + __popc(q.s2) + __popc(q.s3);
+            uint32_t inc = cnt;
+#pragma unroll
+            for (int o = 1; o < LQ; o <<= 1) {
+                uint32_t t = __shfl_up_sync(MDVC_FULL, inc, o, LQ);
+                if (ql >= o) inc += t;
+            }
+            if (row >= D.rows) continue;
+            uint32_t id = base[u] + inc - cnt;
+            const uint32_t lin0 = (uint32_t)(row * D.Z) + (uint32_t)(ql << 7);
+            id = emit_starts(q.s0, id, lin0, runstart, parent);
+            id = emit_starts(q.s1, id, lin0 + 32, runstart, parent);
+            id = emit_starts(q.s2, id, lin0 + 64, runstart, parent);
+            emit_starts(q.s3, id, lin0 + 96, runstart, parent);
+        }
+    }
+}
+
+#define MDVC_DISPATCH_LQ(lq, CALL)                        \
+    switch (lq) {                                         \
+        case 1: { constexpr int LQ = 1; CALL; } break;    \
+        case 2: { constexpr int LQ = 2; CALL; } break;    \
+        case 4: { constexpr int LQ = 4; CALL; } break;    \
+        case 8: { constexpr int LQ = 8; CALL; } break;    \
+        case 16: { constexpr int LQ = 16; CALL; } break;  \
+        default: { constexpr int LQ = 32; CALL; } break;  \
+    }
+
+// ------------------------------------------------------------------------------------------
 // run lookups
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t bit_at(const uint32_t *__restrict__ bits, const Dims &D, uint32_t row, int z) {
@@ -1366,14 +1488,28 @@ extern "C" int mdvc_frame_label(const uint32_t *bits, int X, int Y, int Z, int p
     int g = pick_group(D.nw);
     long long row_threads = D.rows * g;
     unsigned row_grid = mdvc_grid(row_threads / 4, 256, 8);             // four rows per group and iteration
-    MDVC_DISPATCH_G(g, (k_count_runs<G><<<row_grid, 256, 0, st>>>(bits, D, rowoff)));
+    // rows of at most 128 words on 16-byte aligned grids: the quad-per-lane kernels
+    int lq = 1;
+    while (lq < D.pitch / 4) lq <<= 1;
+    const bool quad = lq <= 32 && D.pitch % 4 == 0 && (reinterpret_cast<uintptr_t>(bits) & 15) == 0 &&
+                      !getenv("MDVC_NO_QUAD_RUNS");
+    if (quad) {
+        row_grid = mdvc_grid(D.rows * lq / 4, 256, 8);
+        MDVC_DISPATCH_LQ(lq, (k_count_runs_q<LQ><<<row_grid, 256, 0, st>>>(bits, D, rowoff)));
+    } else {
+        MDVC_DISPATCH_G(g, (k_count_runs<G><<<row_grid, 256, 0, st>>>(bits, D, rowoff)));
+    }
     MDVC_LAUNCH_CHECK();
     rc = mdvc_exclusive_scan<uint32_t>(rowoff, rowoff, nullptr, (uint32_t)D.rows, at<uint32_t>(ws, L.tile32),
                                        rowoff + D.rows, nullptr, st);
     if (rc) return rc;
     k_after_row_scan<<<1, 1, 0, st>>>(h, rowoff, D.rows, caps->max_runs, runstart, D.N);
     MDVC_LAUNCH_CHECK();
-    MDVC_DISPATCH_G(g, (k_fill_runs<G><<<row_grid, 256, 0, st>>>(bits, D, h, rowoff, runstart, parent)));
+    if (quad) {
+        MDVC_DISPATCH_LQ(lq, (k_fill_runs_q<LQ><<<row_grid, 256, 0, st>>>(bits, D, h, rowoff, runstart, parent)));
+    } else {
+        MDVC_DISPATCH_G(g, (k_fill_runs<G><<<row_grid, 256, 0, st>>>(bits, D, h, rowoff, runstart, parent)));
+    }
     MDVC_LAUNCH_CHECK();
     unsigned run_grid = mdvc_grid(caps->max_runs, 256, 8);
     // linking: strips in shared memory -> strip borders -> plane borders in radix-LINK_RADIX rounds;
