@@ -835,37 +835,90 @@ k_tile_link_x(const uint32_t *__restrict__ bits, Dims D, const Hdr *__restrict__
     }
 }
 
-// stage 1d: flatten + root flags (lo32: True root, hi32: False root)
+// stage 1d: flatten + root numbering.  Labels follow scipy's order: the k-th True (False) root in run order is
+// label k+1 (-(k+1)).  One CTA per tile of ROOT_TILE consecutive runs, eight consecutive runs per thread:
+//   - read-only climb to the root and flatten (parent[i] = root);
+//   - rank of every root inside its tile (block scan of packed 16+16-bit counts) -> localrank[root]
+//     (lo16: True roots before it, hi16: False roots before it);
+//   - roots of the tile -> tile_sums[tile] (lo32 True, hi32 False).
+// k_root_tile_offsets turns the tile sums into exclusive offsets, and k_assign_labels adds the two: no dense
+// scan of one flag per run (was three more launches over 8 B per run).
+#define ROOT_TILE 2048
+#define ROOT_ITEMS 8
 __global__ void __launch_bounds__(256)
 k_flatten_flags(const uint32_t *__restrict__ bits, Dims D, const Hdr *__restrict__ h,
-                const uint32_t *__restrict__ runstart, uint32_t *parent, unsigned long long *__restrict__ flags) {
-    uint32_t R = h->run_eff;
-    uint32_t stride = gridDim.x * blockDim.x;
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < R; i += stride) {
-        // read-only climb: in this kernel parent[i] is written by thread i alone, so after the kernel
-        // every entry holds a root (a pointer-jumping find here could overwrite a neighbour's
-        // finished entry with a non-root ancestor)
-        uint32_t root = i, up;
-        while ((up = __ldcg(&parent[root])) != root) root = up;
-        unsigned long long f = 0;
-        if (root == i) {
-            uint32_t lin = runstart[i];
-            uint32_t r = lin / (uint32_t)D.Z;
-            f = bit_at(bits, D, r, (int)(lin - r * (uint32_t)D.Z)) ? 1ull : (1ull << 32);
-        } else {
-            parent[i] = root;
+                const uint32_t *__restrict__ runstart, uint32_t *parent, uint32_t *__restrict__ localrank,
+                unsigned long long *__restrict__ tile_sums) {
+    __shared__ uint32_t sm[33];
+    const uint32_t R = h->run_eff;
+    const uint32_t base = blockIdx.x * ROOT_TILE;
+    if (base >= R) return;
+    const uint32_t i0 = base + threadIdx.x * ROOT_ITEMS;
+    uint32_t f[ROOT_ITEMS];
+    uint32_t mine = 0;
+#pragma unroll
+    for (int k = 0; k < ROOT_ITEMS; ++k) {
+        const uint32_t i = i0 + k;
+        f[k] = 0;
+        if (i < R) {
+            // read-only climb: in this kernel parent[i] is written by thread i alone, so after the kernel
+            // every entry holds a root (a pointer-jumping find here could overwrite a neighbour's
+            // finished entry with a non-root ancestor)
+            uint32_t root = i, up;
+            while ((up = __ldcg(&parent[root])) != root) root = up;
+            if (root == i) {
+                uint32_t lin = runstart[i];
+                uint32_t r = lin / (uint32_t)D.Z;
+                f[k] = bit_at(bits, D, r, (int)(lin - r * (uint32_t)D.Z)) ? 1u : (1u << 16);
+            } else {
+                parent[i] = root;
+            }
         }
-        flags[i] = f;
+        mine += f[k];
     }
+    uint32_t total;
+    uint32_t off = mdvc_block_exscan<uint32_t>(mine, sm, &total);
+#pragma unroll
+    for (int k = 0; k < ROOT_ITEMS; ++k) {
+        if (f[k]) localrank[i0 + k] = off;
+        off += f[k];
+    }
+    if (threadIdx.x == 0) tile_sums[blockIdx.x] = (unsigned long long)(total & 0xffffu) | ((unsigned long long)(total >> 16) << 32);
 }
 
-__global__ void k_after_root_scan(Hdr *h, uint32_t max_labels) {
-    if (h->run_eff == 0) { h->n_labels = 0; return; }
+// single block: exclusive scan of the root tile sums of the runs in use; total -> h->tot_roots
+__global__ void __launch_bounds__(1024)
+k_root_tile_offsets(Hdr *h, unsigned long long *tile_sums) {
+    __shared__ unsigned long long sm[33];
+    const uint32_t n_tiles = (h->run_eff + ROOT_TILE - 1) / ROOT_TILE;
+    const uint32_t per = (n_tiles + blockDim.x - 1) / blockDim.x;
+    const uint32_t lo = min(threadIdx.x * per, n_tiles), hi = min(lo + per, n_tiles);
+    unsigned long long acc = 0;
+    for (uint32_t i = lo; i < hi; ++i) acc += tile_sums[i];
+    unsigned long long total;
+    unsigned long long off = mdvc_block_exscan<unsigned long long>(acc, sm, &total);
+    for (uint32_t i = lo; i < hi; ++i) { unsigned long long v = tile_sums[i]; tile_sums[i] = off; off += v; }
+    if (threadIdx.x == 0) h->tot_roots = total;
+}
+
+// publishes the label totals and zeroes the volume table of exactly the labels in use (instead of a memset of
+// the whole max_labels table, 50 MB at 1024^3, every frame)
+__global__ void __launch_bounds__(256)
+k_after_root_scan(Hdr *h, uint32_t max_labels, unsigned long long *__restrict__ vol) {
+    const bool leader = blockIdx.x == 0 && threadIdx.x == 0;
+    if (h->run_eff == 0) { if (leader) h->n_labels = 0; return; }
     uint32_t nt = (uint32_t)(h->tot_roots & 0xffffffffu), nf = (uint32_t)(h->tot_roots >> 32);
-    h->n_true = nt; h->n_false = nf;
     unsigned long long nl = (unsigned long long)nt + nf + 1;
-    if (nl > max_labels || nt >= MDVC_LABEL_BIAS || nf >= MDVC_LABEL_BIAS) { h->flags |= MDVC_OVERFLOW_LABELS; h->n_labels = 0; }
-    else h->n_labels = (uint32_t)nl;
+    const bool bad = nl > max_labels || nt >= MDVC_LABEL_BIAS || nf >= MDVC_LABEL_BIAS;
+    if (leader) {
+        h->n_true = nt; h->n_false = nf;
+        if (bad) { h->flags |= MDVC_OVERFLOW_LABELS; h->n_labels = 0; }
+        else h->n_labels = (uint32_t)nl;
+    }
+    if (bad) return;
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < nl;
+         i += (unsigned long long)gridDim.x * blockDim.x)
+        vol[i] = 0ull;
 }
 
 // stage 1e: canonical label per run + label volumes
@@ -876,8 +929,8 @@ __global__ void k_after_root_scan(Hdr *h, uint32_t max_labels) {
 __global__ void __launch_bounds__(256)
 k_assign_labels(const uint32_t *__restrict__ bits, Dims D, const Hdr *__restrict__ h,
                 const uint32_t *__restrict__ runstart, const uint32_t *__restrict__ parent,
-                const unsigned long long *__restrict__ rootrank, int32_t *__restrict__ lab,
-                unsigned long long *vol) {
+                const uint32_t *__restrict__ localrank, const unsigned long long *__restrict__ tile_off,
+                int32_t *__restrict__ lab, unsigned long long *vol) {
     __shared__ int s_key[VOL_SLOTS];
     __shared__ unsigned long long s_val[VOL_SLOTS];
     for (int k = threadIdx.x; k < VOL_SLOTS; k += blockDim.x) { s_key[k] = 0; s_val[k] = 0; }
@@ -896,8 +949,10 @@ k_assign_labels(const uint32_t *__restrict__ bits, Dims D, const Hdr *__restrict
         uint32_t lin = runstart[i];
         uint32_t r = lin / (uint32_t)D.Z;
         uint32_t v = bit_at(bits, D, r, (int)(lin - r * (uint32_t)D.Z));
-        unsigned long long e = rootrank[parent[i]];
-        label = v ? (int)((uint32_t)(e & 0xffffffffu) + 1u) : -(int)((uint32_t)(e >> 32) + 1u);
+        const uint32_t root = parent[i];
+        const unsigned long long e = tile_off[root / ROOT_TILE];
+        const uint32_t lr = localrank[root];
+        label = v ? (int)((uint32_t)(e & 0xffffffffu) + (lr & 0xffffu) + 1u) : -(int)((uint32_t)(e >> 32) + (lr >> 16) + 1u);
         lab[i] = label;
         len = runstart[i + 1] - lin;
         }
@@ -1484,7 +1539,6 @@ extern "C" int mdvc_frame_label(const uint32_t *bits, int X, int Y, int Z, int p
     unsigned long long *vol = at<unsigned long long>(ws, L.vol);
 
     MDVC_CUDA_CHECK(cudaMemsetAsync(h, 0, sizeof(Hdr), st));
-    MDVC_CUDA_CHECK(cudaMemsetAsync(vol, 0, (size_t)caps->max_labels * 8, st));
     int g = pick_group(D.nw);
     long long row_threads = D.rows * g;
     unsigned row_grid = mdvc_grid(row_threads / 4, 256, 8);             // four rows per group and iteration
@@ -1538,14 +1592,15 @@ extern "C" int mdvc_frame_label(const uint32_t *bits, int X, int Y, int Z, int p
             MDVC_LAUNCH_CHECK();
         }
     }
-    k_flatten_flags<<<run_grid, 256, 0, st>>>(bits, D, h, runstart, parent, scan64);
+    uint32_t *localrank = reinterpret_cast<uint32_t *>(scan64);
+    unsigned long long *root_tiles = at<unsigned long long>(ws, L.tile64);
+    k_flatten_flags<<<(caps->max_runs + ROOT_TILE - 1) / ROOT_TILE, 256, 0, st>>>(bits, D, h, runstart, parent, localrank, root_tiles);
     MDVC_LAUNCH_CHECK();
-    rc = mdvc_exclusive_scan<unsigned long long>(scan64, scan64, &h->run_eff, caps->max_runs,
-                                                 at<unsigned long long>(ws, L.tile64), &h->tot_roots, nullptr, st);
-    if (rc) return rc;
-    k_after_root_scan<<<1, 1, 0, st>>>(h, caps->max_labels);
+    k_root_tile_offsets<<<1, 1024, 0, st>>>(h, root_tiles);
     MDVC_LAUNCH_CHECK();
-    k_assign_labels<<<run_grid, 256, 0, st>>>(bits, D, h, runstart, parent, scan64, lab, vol);
+    k_after_root_scan<<<mdvc_num_sms(), 256, 0, st>>>(h, caps->max_labels, vol);
+    MDVC_LAUNCH_CHECK();
+    k_assign_labels<<<run_grid, 256, 0, st>>>(bits, D, h, runstart, parent, localrank, root_tiles, lab, vol);
     MDVC_LAUNCH_CHECK();
     return MDVC_OK;
 }
@@ -1661,7 +1716,9 @@ static int expand_rows(const uint32_t *bits, int X, int Y, int Z, int pitch, voi
     // Not a persistent grid: one short-lived CTA per 8 row groups keeps the concurrently written rows close
     // together in memory (measured on B200 at 1024^3, labels + components: 1.45 ms with 8 CTAs/SM grid-stride,
     // 1.27 ms = 6.77 TB/s with up to 256 CTAs/SM).
-    unsigned grid = mdvc_grid((row_end - row_begin) * g, 256, 256);
+    static int expand_cap = 0;
+    if (!expand_cap) expand_cap = getenv("MDVC_EXPAND_CTAS_PER_SM") ? atoi(getenv("MDVC_EXPAND_CTAS_PER_SM")) : 256;
+    unsigned grid = mdvc_grid((row_end - row_begin) * g, 256, expand_cap);
     const Hdr *h = at<Hdr>(ws, L.hdr);
     const uint32_t *rowoff = at<uint32_t>(ws, L.rowoff);
     const int32_t *lab = at<int32_t>(ws, L.lab), *rc_ = at<int32_t>(ws, L.runcomp);
