@@ -257,6 +257,12 @@ def run_ours(args):
         pipe.run(pos_dev)
         iso.append(pipe.expand_elapsed_ms())
     expand_iso_ms = min(iso)
+    # informational: the same frames when only the components grid -- the one dense array the reference's API keeps
+    # (containment_main.py:91,134; the non-periodic label grid is a local there) -- is materialised
+    for p in pipes:
+        p.labels, p.write_labels = None, False
+    run_frames(max(1, args.warmup // 2), False)
+    ms_conly, _, _ = timed(args.steps, False)
 
     if rank != 0:
         if world > 1:
@@ -293,6 +299,9 @@ def run_ours(args):
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(n_atoms * 12),
                 "d2h_bytes_per_step": int(small_d2h), "ms_per_step": ms_e2e / args.steps,
                 "call": "FramePipeline.begin(host_positions=pinned) / finish() -> containment DAG, ranks, counts on the host"},
+        "components_only": {"value": world * args.steps / (ms_conly / 1e3), "unit": UNIT, "ms_per_step": ms_conly / args.steps,
+                            "note": "informational, not the headline: labels grid not materialised (4 B/voxel written instead "
+                                    "of 8); every other stage identical"},
         "gpu_launches": int(launches),
         "clocks": clocks,
         "result": {"components": len(out.voxel_counts), "n_true": out.n_true, "n_false": out.n_false,

@@ -1716,9 +1716,7 @@ static int expand_rows(const uint32_t *bits, int X, int Y, int Z, int pitch, voi
     // Not a persistent grid: one short-lived CTA per 8 row groups keeps the concurrently written rows close
     // together in memory (measured on B200 at 1024^3, labels + components: 1.45 ms with 8 CTAs/SM grid-stride,
     // 1.27 ms = 6.77 TB/s with up to 256 CTAs/SM).
-    static int expand_cap = 0;
-    if (!expand_cap) expand_cap = getenv("MDVC_EXPAND_CTAS_PER_SM") ? atoi(getenv("MDVC_EXPAND_CTAS_PER_SM")) : 256;
-    unsigned grid = mdvc_grid((row_end - row_begin) * g, 256, expand_cap);
+    unsigned grid = mdvc_grid((row_end - row_begin) * g, 256, 256);
     const Hdr *h = at<Hdr>(ws, L.hdr);
     const uint32_t *rowoff = at<uint32_t>(ws, L.rowoff);
     const int32_t *lab = at<int32_t>(ws, L.lab), *rc_ = at<int32_t>(ws, L.runcomp);

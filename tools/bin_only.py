@@ -16,6 +16,16 @@ def main():
     n = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
     reps = int(sys.argv[2]) if len(sys.argv) > 2 else 20
     pos, dims = synth.vesicle_scene(box_nm=n / 2.0)
+    order = os.environ.get("BIN_ORDER", "none")          # locality experiment: none | slabs<k> | full
+    if order != "none":
+        import numpy as np
+        vx = np.floor(pos[:, 0] / 5.0).astype(np.int64) % n
+        if order == "full":
+            vy = np.floor(pos[:, 1] / 5.0).astype(np.int64) % n
+            key = vx * n + vy
+        else:
+            key = vx // (n // int(order[5:]))
+        pos = pos[np.argsort(key, kind="stable")]
     _, nbox, T, invT = voxel_transform(dims, 0.5)
     bits0 = dev.BitGrid((n, n, n))
     p = torch.from_numpy(pos).cuda()
