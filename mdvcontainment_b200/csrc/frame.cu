@@ -1172,11 +1172,12 @@ k_tile_pairs(const uint32_t *__restrict__ bits, Dims D, Hdr *h, const uint32_t *
                 }
                 const uint32_t pol0 = spol[slot];
                 // Shortcut for in-box neighbour rows that mirror this row: same number of runs, same first
-                // value, same label per run, and starts that interleave (every run starts before the next run
-                // of the other row: s'_m < s_{m+1} and s_m < s'_{m+1}).  Then run k only reaches runs k-1, k,
-                // k+1 of the neighbour, whose labels are this row's own neighbours' labels, so every cross-row
-                // contact is already among the in-row contacts emitted below.  True for most row pairs of
-                // smooth structures; anything else takes the walk.
+                // value, and starts that interleave (every run starts before the next run of the other row:
+                // s'_m < s_{m+1} and s_m < s'_{m+1}).  Then run k overlaps run k of the neighbour voxel on voxel
+                // (same value, adjacent rows: one 26-connected set, hence the same label) and otherwise only
+                // reaches its runs k-1 and k+1, whose labels are this row's own neighbours' labels, so every
+                // cross-row contact is already among the in-row contacts emitted below.  True for most row
+                // pairs of smooth structures; anything else takes the walk.
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
                     const int ns = nsl[q];
@@ -1184,8 +1185,7 @@ k_tile_pairs(const uint32_t *__restrict__ bits, Dims D, Hdr *h, const uint32_t *
                     const uint32_t n = re0 - rb0, pb = pj[q];
                     bool mirror = (pe[q] - pb) == n && spol[ns] == pol0;
                     for (uint32_t k = 0; mirror && k < n; ++k) {
-                        mirror = tv[pb + k] == tv[rb0 + k] &&
-                                 (k + 1 >= n || (tz[pb + k] < tz[rb0 + k + 1] && tz[rb0 + k] < tz[pb + k + 1]));
+                        mirror = k + 1 >= n || (tz[pb + k] < tz[rb0 + k + 1] && tz[rb0 + k] < tz[pb + k + 1]);
                     }
                     if (mirror) pj[q] = pe[q];
                 }
@@ -1195,18 +1195,24 @@ k_tile_pairs(const uint32_t *__restrict__ bits, Dims D, Hdr *h, const uint32_t *
                     const uint32_t pol = pol0 ^ ((k - rb0) & 1u);
                     const int la = tv[k];
                     if (k > rb0) emit_contact(cs, tv[k - 1], la);
+                    // Bridges take every run of the neighbour row within one voxel of [a, b].  Contacts only need the
+                    // runs of the other value that overlap [a, b] itself: a run that merely touches diagonally sits
+                    // next to a run of this run's value that overlaps it (same label as this run), so that pair is
+                    // one of the neighbour row's own in-row contacts.
                     const uint32_t lo = a > 0 ? a - 1 : 0, hi = b + 1 < D.Z ? b + 1 : D.Z - 1;
 #pragma unroll
                     for (int q = 0; q < 4; ++q) {
                         if (pj[q] == pe[q]) continue;
-                        uint32_t j = pj[q];
-                        while (j + 1 < pe[q] && tz[j + 1] <= lo) ++j;      // run containing lo
-                        pj[q] = j;
                         const int ns = nsl[q];
                         const int sx = q == 0 ? 0 : sx_other, sy = ssy[ns];
-                        if (!(sx | sy)) {
+                        const bool wrapped = (sx | sy) != 0;
+                        const uint32_t from = wrapped ? lo : (uint32_t)a;
+                        uint32_t j = pj[q];
+                        while (j + 1 < pe[q] && tz[j + 1] <= from) ++j;    // run containing `from`
+                        pj[q] = j;
+                        if (!wrapped) {
                             if ((spol[ns] ^ ((j - soff[ns]) & 1u)) == pol) ++j;
-                            for (; j < pe[q] && tz[j] <= hi; j += 2) emit_contact(cs, la, tv[j]);
+                            for (; j < pe[q] && tz[j] <= (uint32_t)b; j += 2) emit_contact(cs, la, tv[j]);
                         } else {
                             for (; j < pe[q] && tz[j] <= hi; ++j) emit_bridge(bs, la, tv[j], sx, sy, 0);
                         }
