@@ -685,7 +685,18 @@ k_strip_link(const uint32_t *__restrict__ bits, Dims D, Hdr *h, const uint32_t *
             }
             __syncthreads();
             if (threadIdx.x == 0) s_nroots = 0;
-            __syncthreads();
+            // Every union hung a run under one of the previous row, so the trees are chains as deep as the strip
+            // has rows (ncu: the plain climb below was 47 % of this kernel's instructions).  Pointer jumping
+            // halves the depth per round; entries only ever move to an ancestor, so the rounds need no
+            // double buffering.
+            for (int round = 0; round < 7; ++round) {
+                bool moved = false;
+                for (uint32_t k = threadIdx.x; k < nloc; k += blockDim.x) {
+                    const uint32_t p = spar[k], gp = spar[p];
+                    if (gp != p) { spar[k] = gp; moved = true; }
+                }
+                if (!__syncthreads_or(moved)) break;
+            }
             for (uint32_t k = threadIdx.x; k < nloc; k += blockDim.x) {
                 uint32_t root = k, up;
                 while ((up = spar[root]) != root) root = up;
