@@ -639,11 +639,22 @@ __device__ __forceinline__ void link_run_vs_row(const uint32_t *__restrict__ bit
     }
 }
 
+// runs [a0, a1) of one row against runs [b0, b1) of a neighbour row (packed entries, z in the low 24 bits):
+// same count, same first value, and every run starts before the next run of the other row
+__device__ __forceinline__ bool rows_mirror(const uint32_t *tz, uint32_t a0, uint32_t a1, uint32_t b0, uint32_t b1, bool same_first) {
+    const uint32_t n = a1 - a0;
+    bool mirror = same_first && (b1 - b0) == n;
+    for (uint32_t m = 0; mirror && m + 1 < n; ++m)
+        mirror = (tz[b0 + m] & ZMASK) < (tz[a0 + m + 1] & ZMASK) && (tz[a0 + m] & ZMASK) < (tz[b0 + m + 1] & ZMASK);
+    return mirror;
+}
+
 __global__ void __launch_bounds__(TILE_THREADS, 8)
 k_strip_link(const uint32_t *__restrict__ bits, Dims D, Hdr *h, const uint32_t *__restrict__ rowoff,
              const uint32_t *__restrict__ runstart, uint32_t *parent, uint32_t *rootlist) {
     __shared__ uint32_t srow[STRIP_TY + 1];
     __shared__ uint32_t spol[STRIP_TY];
+    __shared__ uint8_t smir[STRIP_TY];
     __shared__ uint32_t sz[STRIP_CAP];
     __shared__ uint32_t spar[STRIP_CAP];
     __shared__ uint32_t s_nroots, s_base;
@@ -670,14 +681,21 @@ k_strip_link(const uint32_t *__restrict__ bits, Dims D, Hdr *h, const uint32_t *
                 spar[k] = k;
             }
             __syncthreads();
+            // rows that mirror the previous row (same run count, same first value, interleaving starts): run m
+            // touches run m of that row and no other run of its value, so the link needs no search
+            for (int t = threadIdx.x; t < ny; t += blockDim.x)
+                smir[t] = t > 0 && rows_mirror(sz, srow[t] - gbase, srow[t + 1] - gbase, srow[t - 1] - gbase,
+                                               srow[t] - gbase, spol[t] == spol[t - 1]);
+            __syncthreads();
             for (uint32_t k = threadIdx.x; k < nloc; k += blockDim.x) {
                 uint32_t e = sz[k], lr = e >> 24;
                 if (lr == 0) continue;
                 uint32_t rb0 = srow[lr] - gbase, re0 = srow[lr + 1] - gbase;      // own row [rb0, re0)
+                uint32_t n0 = srow[lr - 1] - gbase, n1 = rb0;                     // previous row [n0, n1)
+                if (smir[lr]) { smem_union(spar, k, n0 + (k - rb0)); continue; }
                 int a = (int)(e & ZMASK);
                 int b = (k + 1 < re0) ? (int)(sz[k + 1] & ZMASK) - 1 : D.Z - 1;
                 uint32_t pol = spol[lr] ^ ((k - rb0) & 1u);
-                uint32_t n0 = srow[lr - 1] - gbase, n1 = rb0;                     // previous row [n0, n1)
                 uint32_t lo = a > 0 ? a - 1 : 0, hi = b + 1 < D.Z ? b + 1 : D.Z - 1;
                 uint32_t j = tile_run_at(sz, n0, n1, lo);
                 if ((spol[lr - 1] ^ ((j - n0) & 1u)) != pol) ++j;
@@ -752,6 +770,7 @@ k_tile_link_x(const uint32_t *__restrict__ bits, Dims D, const Hdr *__restrict__
     __shared__ uint32_t orow[STRIP_TY + 1], brow[STRIP_TY + 3];
     __shared__ uint32_t opol[STRIP_TY], bpol[STRIP_TY + 2];
     __shared__ uint32_t tz[STRIP_CAP], troot[STRIP_CAP];       // own runs first, then the other plane's
+    __shared__ uint8_t smir[3 * STRIP_TY];
     __shared__ BlockSet seen;
     if (h->run_eff == 0) return;
     const int spp = (D.Y + STRIP_TY - 1) / STRIP_TY;
@@ -800,6 +819,18 @@ k_tile_link_x(const uint32_t *__restrict__ bits, Dims D, const Hdr *__restrict__
                 }
             }
             __syncthreads();
+            // (own row, dy) pairs whose rows mirror each other: the link partner of run m is run m, no search
+            for (int t = threadIdx.x; t < 3 * ny; t += blockDim.x) {
+                const int lr = t / 3, dy = t - 3 * lr - 1, yy = y0 + lr + dy;
+                bool mir = false;
+                if (yy >= 0 && yy < D.Y) {
+                    const int bl = yy - yA;
+                    mir = rows_mirror(tz, orow[lr] - go, orow[lr + 1] - go, no + (brow[bl] - gb), no + (brow[bl + 1] - gb),
+                                      opol[lr] == bpol[bl]);
+                }
+                smir[t] = mir;
+            }
+            __syncthreads();
             for (uint32_t k = threadIdx.x; k < no; k += blockDim.x) {
                 uint32_t e = tz[k], lr = e >> 24;
                 uint32_t rb0 = orow[lr] - go, re0 = orow[lr + 1] - go;
@@ -813,9 +844,14 @@ k_tile_link_x(const uint32_t *__restrict__ bits, Dims D, const Hdr *__restrict__
                     if (yy < 0 || yy >= D.Y) continue;
                     int bl = yy - yA;                                          // row slot in the other plane
                     uint32_t n0 = no + (brow[bl] - gb), n1 = no + (brow[bl + 1] - gb);
-                    uint32_t j = tile_run_at(tz, n0, n1, lo);
-                    if ((bpol[bl] ^ ((j - n0) & 1u)) != pol) ++j;
-                    for (; j < n1 && (tz[j] & ZMASK) <= hi; j += 2) {
+                    uint32_t j, jend;
+                    if (smir[3 * lr + dy + 1]) { j = n0 + (k - rb0); jend = j + 1; }
+                    else {
+                        j = tile_run_at(tz, n0, n1, lo);
+                        if ((bpol[bl] ^ ((j - n0) & 1u)) != pol) ++j;
+                        jend = n1;
+                    }
+                    for (; j < jend && (tz[j] & ZMASK) <= hi; j += 2) {
                         uint32_t rb = troot[j];
                         if (ra == rb) continue;
                         unsigned long long key = ra < rb ? ((unsigned long long)ra << 32) | rb : ((unsigned long long)rb << 32) | ra;
