@@ -886,10 +886,17 @@ k_tile_link_x(const uint32_t *__restrict__ bits, Dims D, const Hdr *__restrict__
 // label k+1 (-(k+1)).  One CTA per tile of ROOT_TILE consecutive runs, eight consecutive runs per thread:
 //   - read-only climb to the root and flatten (parent[i] = root);
 //   - rank of every root inside its tile (block scan of packed 16+16-bit counts) -> localrank[root]
-//     (lo16: True roots before it, hi16: False roots before it);
+//     (bits 0-11: True roots before it, bits 16-27: False roots before it, bit 15: the root's own value, which
+//     is the value of every run of its tree -- k_assign_labels needs no look-up in the bit grid);
 //   - roots of the tile -> tile_sums[tile] (lo32 True, hi32 False).
 // k_root_tile_offsets turns the tile sums into exclusive offsets, and k_assign_labels adds the two: no dense
 // scan of one flag per run (was three more launches over 8 B per run).
+__device__ __forceinline__ uint32_t ld_ca_u32(const uint32_t *p) {
+    uint32_t v;
+    asm volatile("ld.global.ca.u32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
+
 #define ROOT_TILE 2048
 #define ROOT_ITEMS 8
 __global__ void __launch_bounds__(256)
@@ -901,24 +908,39 @@ k_flatten_flags(const uint32_t *__restrict__ bits, Dims D, const Hdr *__restrict
     const uint32_t base = blockIdx.x * ROOT_TILE;
     if (base >= R) return;
     const uint32_t i0 = base + threadIdx.x * ROOT_ITEMS;
-    uint32_t f[ROOT_ITEMS];
+    // read-only climb: in this kernel parent[i] is written by thread i alone, so after the kernel every entry
+    // holds a root (a pointer-jumping find here could overwrite a neighbour's finished entry with a non-root
+    // ancestor).  The eight climbs advance in lockstep, one round of eight independent loads at a time.
+    // The loads may hit L1 (unlike in the union kernels): the only stores of this kernel replace an entry by its
+    // root and roots do not change here, so a stale line still holds an ancestor and the climb still ends at the
+    // root.  All runs of a component converge on a handful of root entries; served from L2 alone those few
+    // sectors serialise the whole grid.
+    uint32_t cur[ROOT_ITEMS], f[ROOT_ITEMS];
+#pragma unroll
+    for (int k = 0; k < ROOT_ITEMS; ++k) cur[k] = min(i0 + k, R - 1);
+    uint32_t live = (1u << ROOT_ITEMS) - 1u;
+    do {
+        uint32_t up[ROOT_ITEMS];
+#pragma unroll
+        for (int k = 0; k < ROOT_ITEMS; ++k) up[k] = (live >> k) & 1u ? ld_ca_u32(parent + cur[k]) : cur[k];
+#pragma unroll
+        for (int k = 0; k < ROOT_ITEMS; ++k) {
+            if (up[k] == cur[k]) live &= ~(1u << k);
+            cur[k] = up[k];
+        }
+    } while (live);
     uint32_t mine = 0;
 #pragma unroll
     for (int k = 0; k < ROOT_ITEMS; ++k) {
         const uint32_t i = i0 + k;
         f[k] = 0;
         if (i < R) {
-            // read-only climb: in this kernel parent[i] is written by thread i alone, so after the kernel
-            // every entry holds a root (a pointer-jumping find here could overwrite a neighbour's
-            // finished entry with a non-root ancestor)
-            uint32_t root = i, up;
-            while ((up = __ldcg(&parent[root])) != root) root = up;
-            if (root == i) {
+            if (cur[k] == i) {
                 uint32_t lin = runstart[i];
                 uint32_t r = lin / (uint32_t)D.Z;
                 f[k] = bit_at(bits, D, r, (int)(lin - r * (uint32_t)D.Z)) ? 1u : (1u << 16);
             } else {
-                parent[i] = root;
+                parent[i] = cur[k];
             }
         }
         mine += f[k];
@@ -927,7 +949,7 @@ k_flatten_flags(const uint32_t *__restrict__ bits, Dims D, const Hdr *__restrict
     uint32_t off = mdvc_block_exscan<uint32_t>(mine, sm, &total);
 #pragma unroll
     for (int k = 0; k < ROOT_ITEMS; ++k) {
-        if (f[k]) localrank[i0 + k] = off;
+        if (f[k]) localrank[i0 + k] = off | ((f[k] & 1u) << 15);      // bit 15: the tree is a True component
         off += f[k];
     }
     if (threadIdx.x == 0) tile_sums[blockIdx.x] = (unsigned long long)(total & 0xffffu) | ((unsigned long long)(total >> 16) << 32);
@@ -993,13 +1015,12 @@ k_assign_labels(const uint32_t *__restrict__ bits, Dims D, const Hdr *__restrict
         int label = 0;
         uint32_t len = 0;
         if (live) {
-        uint32_t lin = runstart[i];
-        uint32_t r = lin / (uint32_t)D.Z;
-        uint32_t v = bit_at(bits, D, r, (int)(lin - r * (uint32_t)D.Z));
+        const uint32_t lin = runstart[i];
         const uint32_t root = parent[i];
         const unsigned long long e = tile_off[root / ROOT_TILE];
         const uint32_t lr = localrank[root];
-        label = v ? (int)((uint32_t)(e & 0xffffffffu) + (lr & 0xffffu) + 1u) : -(int)((uint32_t)(e >> 32) + (lr >> 16) + 1u);
+        label = (lr & 0x8000u) ? (int)((uint32_t)(e & 0xffffffffu) + (lr & 0xfffu) + 1u)
+                               : -(int)((uint32_t)(e >> 32) + ((lr >> 16) & 0xfffu) + 1u);
         lab[i] = label;
         len = runstart[i + 1] - lin;
         }
