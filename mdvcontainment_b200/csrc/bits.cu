@@ -105,6 +105,8 @@ struct BinParams {
     double T[9];
     double invT[9];
     long long nbox[9];
+    int nbox32[9];       // the same matrix when every entry fits (fits32), for the all-32-bit fast path
+    int fits32;
 };
 
 // Python floor division a // b for b > 0.  Atoms are almost always inside the box or one image away, so
@@ -120,15 +122,75 @@ __device__ __forceinline__ long long floordiv_ll(long long a, long long b) {
     return (r != 0 && ((r < 0) != (b < 0))) ? q - 1 : q;
 }
 
-// One thread per atom.  float64 products as the FMA chain fma(p2,T2j, fma(p1,T1j, p0*T0j)) --
-// bit-identical to the reference's NumPy/OpenBLAS dgemm; __dmul_rn/__fma_rn keep
-// the compiler from contracting differently.
+// One atom: fractional voxel coordinates as the FMA chain fma(p2,T2j, fma(p1,T1j, p0*T0j)) in float64 --
+// bit-identical to the reference's NumPy/OpenBLAS dgemm; __dmul_rn/__fma_rn keep the compiler
+// from contracting differently -- floor, triclinic wrap (z, y, x; Python floor division), optional outputs.
+// Fast path: when the floors and the box matrix fit 28 bits (any realistic box) everything after the floor is
+// 32-bit integer work; the general path keeps 64-bit integers like the reference's int64 arrays.
+// Returns true and the wrapped voxel when it lies inside the grid.
+__device__ __forceinline__ bool bin_one_atom(const float *sp3, long long i, const BinParams &P,
+                                             int32_t *__restrict__ vox_out, float *pos_out, int &ox, int &oy, int &oz) {
+    const double p0 = (double)sp3[0], p1 = (double)sp3[1], p2 = (double)sp3[2];
+    double fj[3], fl[3];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+        fj[j] = __fma_rn(p2, P.T[6 + j], __fma_rn(p1, P.T[3 + j], __dmul_rn(p0, P.T[j])));
+        fl[j] = floor(fj[j]);
+    }
+    const double lim = 268435456.0;                      // 2^28
+    if (P.fits32 && fabs(fl[0]) < lim && fabs(fl[1]) < lim && fabs(fl[2]) < lim) {
+        const int u0 = __double2int_rz(fl[0]), u1 = __double2int_rz(fl[1]), u2 = __double2int_rz(fl[2]);
+        int w3[3] = {u0, u1, u2};
+#pragma unroll
+        for (int dim = 2; dim >= 0; --dim) {
+            const int nn = P.nbox32[4 * dim], a = w3[dim];
+            int sh;
+            if (a >= 0) sh = a < nn ? 0 : (a < 2 * nn ? 1 : a / nn);
+            else sh = a >= -nn ? -1 : -((-a + nn - 1) / nn);
+#pragma unroll
+            for (int j = 0; j < 3; ++j) w3[j] -= sh * P.nbox32[3 * dim + j];
+        }
+        if (vox_out) { vox_out[3 * i] = w3[0]; vox_out[3 * i + 1] = w3[1]; vox_out[3 * i + 2] = w3[2]; }
+        if (pos_out) {
+            // (voxel + fractional part) back through inv(T): atomgroup_to_voxels.py:142
+            const double g0 = __dadd_rn((double)w3[0], __dsub_rn(fj[0], (double)u0)),
+                         g1 = __dadd_rn((double)w3[1], __dsub_rn(fj[1], (double)u1)),
+                         g2 = __dadd_rn((double)w3[2], __dsub_rn(fj[2], (double)u2));
+#pragma unroll
+            for (int j = 0; j < 3; ++j)
+                pos_out[3 * i + j] = (float)__fma_rn(g2, P.invT[6 + j], __fma_rn(g1, P.invT[3 + j], __dmul_rn(g0, P.invT[j])));
+        }
+        ox = w3[0]; oy = w3[1]; oz = w3[2];
+        return (unsigned)w3[0] < (unsigned)P.nbox32[0] && (unsigned)w3[1] < (unsigned)P.nbox32[4] &&
+               (unsigned)w3[2] < (unsigned)P.nbox32[8];
+    }
+    long long v[3];
+    double f[3];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) { v[j] = (long long)fl[j]; f[j] = __dsub_rn(fj[j], (double)v[j]); }
+#pragma unroll
+    for (int dim = 2; dim >= 0; --dim) {
+        long long sft = floordiv_ll(v[dim], P.nbox[4 * dim]);
+#pragma unroll
+        for (int j = 0; j < 3; ++j) v[j] -= sft * P.nbox[3 * dim + j];
+    }
+    if (vox_out) { vox_out[3 * i] = (int32_t)v[0]; vox_out[3 * i + 1] = (int32_t)v[1]; vox_out[3 * i + 2] = (int32_t)v[2]; }
+    if (pos_out) {
+        const double g0 = __dadd_rn((double)v[0], f[0]), g1 = __dadd_rn((double)v[1], f[1]), g2 = __dadd_rn((double)v[2], f[2]);
+#pragma unroll
+        for (int j = 0; j < 3; ++j)
+            pos_out[3 * i + j] = (float)__fma_rn(g2, P.invT[6 + j], __fma_rn(g1, P.invT[3 + j], __dmul_rn(g0, P.invT[j])));
+    }
+    ox = (int)v[0]; oy = (int)v[1]; oz = (int)v[2];
+    return v[0] >= 0 && v[0] < P.nbox[0] && v[1] >= 0 && v[1] < P.nbox[4] && v[2] >= 0 && v[2] < P.nbox[8];
+}
+
+// One thread per atom.  Positions are AoS (x,y,z per atom = 12 B): a tile of 256 atoms is fetched as 192 coalesced
+// float4 loads into shared memory and read back with stride 3 (conflict-free), instead of three strided 4-byte
+// loads per atom that each touch every sector of the tile (ncu: 2.5x the compulsory DRAM reads).
 __global__ void __launch_bounds__(256)
 k_bin_atoms(const float *__restrict__ pos, long long n, BinParams P, uint32_t *__restrict__ occ, int pitch,
             int32_t *__restrict__ vox_out, float *pos_out) {
-    // positions are AoS (x,y,z per atom = 12 B): a tile of 256 atoms is fetched as 192 coalesced float4 loads
-    // into shared memory and read back with stride 3 (conflict-free), instead of three strided 4-byte loads
-    // per atom that each touch every sector of the tile (ncu: 2.5x the compulsory DRAM reads)
     __shared__ float sp[256 * 3];
     const bool vec_ok = (reinterpret_cast<uintptr_t>(pos) & 15) == 0;
     const long long n_tiles = (n + 255) / 256;
@@ -144,59 +206,16 @@ k_bin_atoms(const float *__restrict__ pos, long long n, BinParams P, uint32_t *_
         }
         __syncthreads();
         if ((int)threadIdx.x >= cnt) continue;
-        const long long i = base + threadIdx.x;
-        long long v[3];
-        double f[3];
-        const double p0 = (double)sp[3 * threadIdx.x], p1 = (double)sp[3 * threadIdx.x + 1], p2 = (double)sp[3 * threadIdx.x + 2];
-#pragma unroll
-        for (int j = 0; j < 3; ++j) {
-            double fj = __fma_rn(p2, P.T[6 + j], __fma_rn(p1, P.T[3 + j], __dmul_rn(p0, P.T[j])));
-            double fl = floor(fj);
-            v[j] = (long long)fl;
-            f[j] = __dsub_rn(fj, (double)v[j]);
-        }
-        const long long lim = 1ll << 28;
-        if (v[0] > -lim && v[0] < lim && v[1] > -lim && v[1] < lim && v[2] > -lim && v[2] < lim && P.nbox[0] < lim &&
-            P.nbox[4] < lim && P.nbox[8] < lim) {
-            // everything fits 32 bits (any realistic box): same arithmetic without 64-bit multiplies/divides
-            int w3[3] = {(int)v[0], (int)v[1], (int)v[2]};
-#pragma unroll
-            for (int dim = 2; dim >= 0; --dim) {
-                int nn = (int)P.nbox[4 * dim], a = w3[dim], sh;
-                if (a >= 0) sh = a < nn ? 0 : (a < 2 * nn ? 1 : a / nn);
-                else sh = a >= -nn ? -1 : -((-a + nn - 1) / nn);
-#pragma unroll
-                for (int j = 0; j < 3; ++j) w3[j] -= sh * (int)P.nbox[3 * dim + j];
-            }
-            v[0] = w3[0]; v[1] = w3[1]; v[2] = w3[2];
-        } else {
-#pragma unroll
-            for (int dim = 2; dim >= 0; --dim) {
-                long long s = floordiv_ll(v[dim], P.nbox[4 * dim]);
-#pragma unroll
-                for (int j = 0; j < 3; ++j) v[j] -= s * P.nbox[3 * dim + j];
-            }
-        }
-        if (vox_out) {
-            vox_out[3 * i] = (int32_t)v[0]; vox_out[3 * i + 1] = (int32_t)v[1]; vox_out[3 * i + 2] = (int32_t)v[2];
-        }
-        if (pos_out) {
-            double g0 = __dadd_rn((double)v[0], f[0]), g1 = __dadd_rn((double)v[1], f[1]),
-                   g2 = __dadd_rn((double)v[2], f[2]);
-#pragma unroll
-            for (int j = 0; j < 3; ++j)
-                pos_out[3 * i + j] = (float)__fma_rn(g2, P.invT[6 + j],
-                                            __fma_rn(g1, P.invT[3 + j], __dmul_rn(g0, P.invT[j])));
-        }
-        if (occ) {
-            long long X = P.nbox[0], Y = P.nbox[4], Z = P.nbox[8];
-            if (v[0] >= 0 && v[0] < X && v[1] >= 0 && v[1] < Y && v[2] >= 0 && v[2] < Z) {
-                // Fire-and-forget RED.OR.  A __match_any_sync aggregation of lanes hitting the same word was
-                // measured on B200 (ncu: 20 of 27 stall cycles per issue on the MIO/short-scoreboard path,
-                // 255 us for 10.2 M atoms): atom order is spatially uncorrelated with the voxel grid, so
-                // there is almost nothing to merge and the match itself was the bottleneck.
-                atomicOr(&occ[(v[0] * Y + v[1]) * pitch + (v[2] >> 5)], 1u << (v[2] & 31));
-            }
+        int vx, vy, vz;
+        const bool inside = bin_one_atom(sp + 3 * threadIdx.x, base + threadIdx.x, P, vox_out, pos_out, vx, vy, vz);
+        if (occ && inside) {
+            // Fire-and-forget RED.OR.  A __match_any_sync aggregation of lanes hitting the same word was
+            // measured on B200 (ncu: 20 of 27 stall cycles per issue on the MIO/short-scoreboard path,
+            // 255 us for 10.2 M atoms): atom order is spatially uncorrelated with the voxel grid, so
+            // there is almost nothing to merge and the match itself was the bottleneck.
+            // inside the grid => the row index fits 32 bits (the grid holds fewer than 2^31 voxels)
+            const uint32_t row = (uint32_t)vx * (uint32_t)P.nbox[4] + (uint32_t)vy;
+            atomicOr(&occ[(size_t)row * pitch + ((uint32_t)vz >> 5)], 1u << (vz & 31));
         }
     }
 }
@@ -212,6 +231,11 @@ extern "C" int mdvc_bin_atoms(const float *pos, long long n, const double *T_hos
     memcpy(P.T, T_host, sizeof(P.T));
     memcpy(P.invT, invT_host, sizeof(P.invT));
     memcpy(P.nbox, nbox_host, sizeof(P.nbox));
+    P.fits32 = 1;
+    for (int k = 0; k < 9; ++k) {
+        if (nbox_host[k] <= -(1ll << 28) || nbox_host[k] >= (1ll << 28)) P.fits32 = 0;
+        P.nbox32[k] = (int)nbox_host[k];
+    }
     k_bin_atoms<<<mdvc_grid(n, 256, 64), 256, 0, (cudaStream_t)stream>>>(pos, n, P, occ_bits, pitch, vox_out, pos_out);
     MDVC_LAUNCH_CHECK();
     return MDVC_OK;
