@@ -272,6 +272,14 @@ def run_ours(args):
     value = world * args.steps / (ms_dev / 1e3)
     e2e_value = world * args.steps / (ms_e2e / 1e3)
     peak, peak_src = measured_peak()
+    traffic, traffic_src = None, None                    # DRAM bytes of one k_expand launch from the committed ncu capture
+    try:
+        with open(os.path.join(ROOT, "profiles", "expand_traffic.json")) as fh:
+            tr = json.load(fh)
+        if tr["grid"] == [size] * 3:
+            traffic, traffic_src = tr["dram_bytes_read"] + tr["dram_bytes_write"], tr["source"]
+    except (OSError, KeyError, ValueError):
+        pass
     expand_bytes = N * 8.0 + N / 8.0                      # labels + components written once, bit grid read once
     achieved = expand_bytes / (expand_ms / 1e3) / 1e9
     frame_bytes = B_ALG_PER_VOXEL * N + B_ALG_PER_ATOM * n_atoms
@@ -290,7 +298,8 @@ def run_ours(args):
         "frame_algorithmic_gbs": frame_bytes * value / world / 1e9,
         "frame_roofline_frac": frame_bytes * value / world / 1e9 / peak,
         "roofline": {"kernel": "k_expand (dense write of labels + components)", "bound": "hbm", "achieved": achieved,
-                     "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                     "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
+                     "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": expand_bytes, "avg_launch_ms": expand_ms,
                      "note": "avg_launch_ms is measured inside the timed region, where the dense write of one frame shares "
                              "the GPU with the run-level kernels of the next frames in flight",

@@ -654,7 +654,7 @@ k_strip_link(const uint32_t *__restrict__ bits, Dims D, Hdr *h, const uint32_t *
              const uint32_t *__restrict__ runstart, uint32_t *parent, uint32_t *rootlist) {
     __shared__ uint32_t srow[STRIP_TY + 1];
     __shared__ uint32_t spol[STRIP_TY];
-    __shared__ uint8_t smir[STRIP_TY];
+    __shared__ uint8_t smir[STRIP_TY], stop[STRIP_TY];
     __shared__ uint32_t sz[STRIP_CAP];
     __shared__ uint32_t spar[STRIP_CAP];
     __shared__ uint32_t s_nroots, s_base;
@@ -687,12 +687,19 @@ k_strip_link(const uint32_t *__restrict__ bits, Dims D, Hdr *h, const uint32_t *
                 smir[t] = t > 0 && rows_mirror(sz, srow[t] - gbase, srow[t + 1] - gbase, srow[t - 1] - gbase,
                                                srow[t] - gbase, spol[t] == spol[t - 1]);
             __syncthreads();
+            // a stack of consecutively mirrored rows links run m of every row straight to run m of the stack's top
+            // row (the correspondence m -> m is transitive), which keeps the trees one level deep
+            if (threadIdx.x == 0) {
+                uint8_t top = 0;
+                for (int t = 0; t < ny; ++t) { if (!smir[t]) top = (uint8_t)t; stop[t] = top; }
+            }
+            __syncthreads();
             for (uint32_t k = threadIdx.x; k < nloc; k += blockDim.x) {
                 uint32_t e = sz[k], lr = e >> 24;
                 if (lr == 0) continue;
                 uint32_t rb0 = srow[lr] - gbase, re0 = srow[lr + 1] - gbase;      // own row [rb0, re0)
                 uint32_t n0 = srow[lr - 1] - gbase, n1 = rb0;                     // previous row [n0, n1)
-                if (smir[lr]) { smem_union(spar, k, n0 + (k - rb0)); continue; }
+                if (smir[lr]) { smem_union(spar, k, (srow[stop[lr]] - gbase) + (k - rb0)); continue; }
                 int a = (int)(e & ZMASK);
                 int b = (k + 1 < re0) ? (int)(sz[k + 1] & ZMASK) - 1 : D.Z - 1;
                 uint32_t pol = spol[lr] ^ ((k - rb0) & 1u);
