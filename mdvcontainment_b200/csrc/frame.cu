@@ -689,9 +689,20 @@ k_strip_link(const uint32_t *__restrict__ bits, Dims D, Hdr *h, const uint32_t *
             __syncthreads();
             // a stack of consecutively mirrored rows links run m of every row straight to run m of the stack's top
             // row (the correspondence m -> m is transitive), which keeps the trees one level deep
-            if (threadIdx.x == 0) {
-                uint8_t top = 0;
-                for (int t = 0; t < ny; ++t) { if (!smir[t]) top = (uint8_t)t; stop[t] = top; }
+            if (threadIdx.x < 32) {                          // top[t] = last row <= t that is not mirrored: max-scan, 2 rows per lane
+                static_assert(STRIP_TY == 64, "two rows per lane of one warp");
+                const int t0 = 2 * threadIdx.x, t1 = t0 + 1;
+                const uint32_t a = (t0 < ny && !smir[t0]) ? t0 : 0, b = max(a, (t1 < ny && !smir[t1]) ? (uint32_t)t1 : 0u);
+                uint32_t inc = b;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const uint32_t up = __shfl_up_sync(MDVC_FULL, inc, o);
+                    if ((int)threadIdx.x >= o) inc = max(inc, up);
+                }
+                uint32_t ex = __shfl_up_sync(MDVC_FULL, inc, 1);
+                if (threadIdx.x == 0) ex = 0;
+                if (t0 < ny) stop[t0] = (uint8_t)max(ex, a);
+                if (t1 < ny) stop[t1] = (uint8_t)max(ex, b);
             }
             __syncthreads();
             for (uint32_t k = threadIdx.x; k < nloc; k += blockDim.x) {
