@@ -249,7 +249,7 @@ def run_ours(args):
         sampler.start()
     ms_dev, launches, expand_ms = timed(args.steps, False)
     clocks = sampler.stop() if rank == 0 else None
-    run_frames(max(1, args.warmup // 2), True)
+    run_frames(args.warmup, True)
     ms_e2e, _, _ = timed(args.steps, True)
     # the dominant kernel alone (one frame at a time, nothing else on the GPU), for the roofline's context
     iso = []
