@@ -37,6 +37,7 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
         return LIB
     objs = []
     flags = [f for f in NVCC_FLAGS if not f.startswith("--use_fast_math")]
+    flags += os.environ.get("MDVC_NVCC_EXTRA", "").split()          # e.g. -DSTRIP_TY=128 for tuning experiments
     for src in SOURCES:
         obj = os.path.join(CSRC, src.replace(".cu", ".o"))
         cmd = [_nvcc(), *flags, "-c", os.path.join(CSRC, src), "-o", obj]

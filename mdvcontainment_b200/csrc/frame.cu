@@ -516,7 +516,9 @@ __device__ __forceinline__ void rem_union(uint32_t *parent, uint32_t a, uint32_t
 // Most adjacent run pairs are redundant (same two trees as their neighbours): each thread climbs
 // read-only to the current roots, and a per-CTA key cache lets only the first (root,root) pair of a
 // CTA go on to the atomic union.
+#ifndef LINK_RADIX
 #define LINK_RADIX 32
+#endif
 __device__ __forceinline__ uint32_t climb_ro(const uint32_t *parent, uint32_t v) {
     uint32_t up;
     while ((up = __ldcg(&parent[v])) != v) v = up;
@@ -583,7 +585,9 @@ k_link_round(const uint32_t *__restrict__ bits, Dims D, const Hdr *__restrict__ 
 // (noise-like input) fall back to the global-memory walk.  Strip roots are appended to a list: they
 // are the only runs that can become interior tree nodes later, so flattening that short list
 // (k_flatten_list) after each merging round keeps every run within two hops of its root.
+#ifndef STRIP_TY
 #define STRIP_TY 64
+#endif
 #define STRIP_CAP 2048
 #define TILE_THREADS 128
 #define ZMASK 0xffffffu            // packed run entry: (local row << 24) | z   (Z < 2^24, STRIP_TY + 2 < 256)
@@ -689,11 +693,17 @@ k_strip_link(const uint32_t *__restrict__ bits, Dims D, Hdr *h, const uint32_t *
             __syncthreads();
             // a stack of consecutively mirrored rows links run m of every row straight to run m of the stack's top
             // row (the correspondence m -> m is transitive), which keeps the trees one level deep
-            if (threadIdx.x < 32) {                          // top[t] = last row <= t that is not mirrored: max-scan, 2 rows per lane
-                static_assert(STRIP_TY == 64, "two rows per lane of one warp");
-                const int t0 = 2 * threadIdx.x, t1 = t0 + 1;
-                const uint32_t a = (t0 < ny && !smir[t0]) ? t0 : 0, b = max(a, (t1 < ny && !smir[t1]) ? (uint32_t)t1 : 0u);
-                uint32_t inc = b;
+            if (threadIdx.x < 32) {                          // top[t] = last row <= t that is not mirrored: max-scan by one warp
+                constexpr int RPL = STRIP_TY / 32;           // consecutive rows per lane
+                static_assert(STRIP_TY % 32 == 0 && STRIP_TY <= 256, "rows per lane, uint8 row indices");
+                uint32_t loc[RPL], run = 0;
+#pragma unroll
+                for (int q = 0; q < RPL; ++q) {
+                    const int t = RPL * threadIdx.x + q;
+                    if (t < ny && !smir[t]) run = t;
+                    loc[q] = run;
+                }
+                uint32_t inc = run;
 #pragma unroll
                 for (int o = 1; o < 32; o <<= 1) {
                     const uint32_t up = __shfl_up_sync(MDVC_FULL, inc, o);
@@ -701,8 +711,11 @@ k_strip_link(const uint32_t *__restrict__ bits, Dims D, Hdr *h, const uint32_t *
                 }
                 uint32_t ex = __shfl_up_sync(MDVC_FULL, inc, 1);
                 if (threadIdx.x == 0) ex = 0;
-                if (t0 < ny) stop[t0] = (uint8_t)max(ex, a);
-                if (t1 < ny) stop[t1] = (uint8_t)max(ex, b);
+#pragma unroll
+                for (int q = 0; q < RPL; ++q) {
+                    const int t = RPL * threadIdx.x + q;
+                    if (t < ny) stop[t] = (uint8_t)max(ex, loc[q]);
+                }
             }
             __syncthreads();
             for (uint32_t k = threadIdx.x; k < nloc; k += blockDim.x) {
@@ -1395,6 +1408,83 @@ k_sort_keys(unsigned long long *keys, const uint32_t *count, uint32_t cap) {
         for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) keys[i] = sk[i];
 }
 
+// Multi-block bitonic sort for key sets that do not fit one CTA's shared memory (many-label grids: millions of
+// distinct contacts).  The capacity is a power of two; the live count is on the device, so every kernel works on
+// P = next power of two >= count and tiles beyond P leave at once.  Compare-exchange distances below BSORT_TILE run
+// in shared memory (one launch per merge size k), the larger ones take one launch per (k, j).
+#define BSORT_TILE 4096
+__device__ __forceinline__ uint32_t bsort_padded(const uint32_t *count, uint32_t cap) {
+    uint32_t n = min(*count, cap), P = 2;
+    while (P < n) P <<= 1;
+    return P;
+}
+__global__ void __launch_bounds__(256)
+k_bsort_pad(unsigned long long *keys, const uint32_t *count, uint32_t cap) {
+    const uint32_t n = min(*count, cap), P = bsort_padded(count, cap);
+    for (uint32_t i = n + blockIdx.x * blockDim.x + threadIdx.x; i < P; i += gridDim.x * blockDim.x) keys[i] = MDVC_KEY_EMPTY;
+}
+// k_lo == 0: sort every tile completely (k = 2 .. BSORT_TILE); otherwise the passes j = BSORT_TILE/2 .. 1 of merge size k_lo
+__global__ void __launch_bounds__(1024)
+k_bsort_local(unsigned long long *keys, const uint32_t *count, uint32_t cap, uint32_t k_lo) {
+    __shared__ unsigned long long sk[BSORT_TILE];
+    const uint32_t P = bsort_padded(count, cap);
+    const uint32_t base = blockIdx.x * BSORT_TILE;
+    if (base >= P || (k_lo && k_lo > P)) return;
+    const uint32_t m = min((uint32_t)BSORT_TILE, P - base);           // P < BSORT_TILE: one partial tile (power of two)
+    for (uint32_t i = threadIdx.x; i < m; i += blockDim.x) sk[i] = keys[base + i];
+    __syncthreads();
+    for (uint32_t k = k_lo ? k_lo : 2; k <= (k_lo ? k_lo : m); k <<= 1) {
+        for (uint32_t j = min(k >> 1, m >> 1); j > 0; j >>= 1) {
+            for (uint32_t i = threadIdx.x; i < m; i += blockDim.x) {
+                const uint32_t ixj = i ^ j;
+                if (ixj > i) {
+                    const unsigned long long u = sk[i], w = sk[ixj];
+                    const bool up = ((base + i) & k) == 0;
+                    if ((u > w) == up) { sk[i] = w; sk[ixj] = u; }
+                }
+            }
+            __syncthreads();
+        }
+    }
+    for (uint32_t i = threadIdx.x; i < m; i += blockDim.x) keys[base + i] = sk[i];
+}
+__global__ void __launch_bounds__(256)
+k_bsort_global(unsigned long long *keys, const uint32_t *count, uint32_t cap, uint32_t k, uint32_t j) {
+    const uint32_t P = bsort_padded(count, cap);
+    if (k > P) return;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < P; i += gridDim.x * blockDim.x) {
+        const uint32_t ixj = i ^ j;
+        if (ixj > i) {
+            const unsigned long long u = keys[i], w = keys[ixj];
+            const bool up = (i & k) == 0;
+            if ((u > w) == up) { keys[i] = w; keys[ixj] = u; }
+        }
+    }
+}
+
+// ascending sort of keys[0 .. *count): one CTA while the capacity is small, the multi-block network otherwise
+static int sort_keys(unsigned long long *keys, const uint32_t *count, uint32_t cap, cudaStream_t st) {
+    if (cap <= 4 * BSORT_TILE) {
+        k_sort_keys<<<1, 1024, 0, st>>>(keys, count, cap);
+        MDVC_LAUNCH_CHECK();
+        return MDVC_OK;
+    }
+    const unsigned tiles = cap / BSORT_TILE;
+    k_bsort_pad<<<mdvc_grid(cap, 256, 4), 256, 0, st>>>(keys, count, cap);
+    MDVC_LAUNCH_CHECK();
+    k_bsort_local<<<tiles, 1024, 0, st>>>(keys, count, cap, 0);
+    MDVC_LAUNCH_CHECK();
+    for (uint32_t k = 2 * BSORT_TILE; k != 0 && k <= cap; k <<= 1) {
+        for (uint32_t j = k >> 1; j >= BSORT_TILE; j >>= 1) {
+            k_bsort_global<<<mdvc_grid(cap, 256, 8), 256, 0, st>>>(keys, count, cap, k, j);
+            MDVC_LAUNCH_CHECK();
+        }
+        k_bsort_local<<<tiles, 1024, 0, st>>>(keys, count, cap, k);
+        MDVC_LAUNCH_CHECK();
+    }
+    return MDVC_OK;
+}
+
 __global__ void __launch_bounds__(256)
 k_decode_rows(const unsigned long long *__restrict__ keys, const uint32_t *count, uint32_t cap, int with_shift,
               int32_t *__restrict__ rows) {
@@ -1720,16 +1810,16 @@ extern "C" int mdvc_frame_pairs(const uint32_t *bits, int X, int Y, int Z, int p
     }
     k_compact_set<<<mdvc_grid(caps->contact_slots, 256, 4), 256, 0, st>>>(cset, caps->contact_slots, ckeys, &h->n_contacts);
     MDVC_LAUNCH_CHECK();
-    k_sort_keys<<<1, 1024, 0, st>>>(ckeys, &h->n_contacts, caps->contact_slots);
-    MDVC_LAUNCH_CHECK();
+    rc = sort_keys(ckeys, &h->n_contacts, caps->contact_slots, st);
+    if (rc) return rc;
     k_decode_rows<<<mdvc_grid(caps->contact_slots, 256, 4), 256, 0, st>>>(ckeys, &h->n_contacts, caps->contact_slots, 0,
                                                                           at<int32_t>(ws, L.crows));
     MDVC_LAUNCH_CHECK();
     if (periodic) {
         k_compact_set<<<mdvc_grid(caps->bridge_slots, 256, 4), 256, 0, st>>>(bset, caps->bridge_slots, bkeys, &h->n_bridges);
         MDVC_LAUNCH_CHECK();
-        k_sort_keys<<<1, 1024, 0, st>>>(bkeys, &h->n_bridges, caps->bridge_slots);
-        MDVC_LAUNCH_CHECK();
+        rc = sort_keys(bkeys, &h->n_bridges, caps->bridge_slots, st);
+        if (rc) return rc;
         k_decode_rows<<<mdvc_grid(caps->bridge_slots, 256, 4), 256, 0, st>>>(bkeys, &h->n_bridges, caps->bridge_slots, 1,
                                                                              at<int32_t>(ws, L.brows));
         MDVC_LAUNCH_CHECK();

@@ -263,6 +263,28 @@ def test_noise_grid_vs_oracle(dev):
     assert np.array_equal(vol[vals + h.n_false], cnt)
 
 
+def test_many_contacts_take_the_multi_block_sort(dev):
+    """Pure noise: tens of thousands of labels and more distinct contacts / bridges than one CTA sorts
+    (the key capacity grows past 4 * 4096 on retry, which selects the multi-block bitonic network)."""
+    rng = np.random.default_rng(33)
+    g = rng.random((96, 96, 100)) < 0.03
+    bits = dev.BitGrid.from_bool(g)
+    plan, h = dev.label_with_retry(bits)
+    assert h.flags == 0 and plan.caps.contact_slots > 16384 and h.n_contacts > 16384
+    want = vo.label_3d_grid(g).astype(np.int32)
+    labels = torch.empty(g.shape, dtype=torch.int32, device="cuda")
+    plan.expand(bits, labels, None)
+    assert np.array_equal(labels.cpu().numpy(), want)
+    assert np.array_equal(plan.contacts(), vo.find_label_contacts_c(want))
+    assert np.array_equal(plan.bridges(), vo.find_bridges_c(want))
+    # a capacity far above the count: the padded network only touches the live prefix
+    big = dev.FramePlan(g.shape, plan.caps.max_runs, plan.caps.max_labels, 1 << 21, 1 << 20)
+    big.label(bits)
+    big.pairs(bits)
+    big.header = big.read_header()
+    assert np.array_equal(big.contacts(), plan.contacts()) and np.array_equal(big.bridges(), plan.bridges())
+
+
 def test_dense_noise_takes_the_global_memory_fallback(dev):
     """More runs per 64-row strip than the shared-memory tiles hold (random voxels, long rows)."""
     rng = np.random.default_rng(21)
