@@ -438,6 +438,10 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
                      : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
     } while (!done);
 }
+__device__ __forceinline__ void mbar_fence_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
 __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
@@ -562,6 +566,133 @@ k_close_sweep(const uint32_t *__restrict__ in, uint32_t *__restrict__ out, int X
     }
 }
 
+// Two adjacent rows (j0 = 2*jr, j0+1) per thread: the raw rows j0-1 .. j0+2 serve both (4 LDS.128 instead of 6), the
+// exchange tile is read for j0-1 and j0+2 only, the edge bits of both rows travel in one pair of shuffles, and the
+// per-plane overhead (mbarrier wait, barrier, pointers) is paid once per two rows.
+template <int S, bool FULLZ>
+__global__ void __launch_bounds__(256)
+k_close_sweep2(const uint32_t *__restrict__ in, uint32_t *__restrict__ out, int X, int Y, int Z, int pitch, int nw,
+               int lq_log2, int JR, int TX) {
+    extern __shared__ __align__(128) unsigned char close_smem[];
+    const int LQ = 1 << lq_log2;
+    const int nq = pitch >> 2;
+    const int JT = 2 * JR, TY = JT - 4;
+    const int tile4 = JT * nq;
+    uint4 *raw = (uint4 *)close_smem;                             // [S][JT][nq]
+    uint4 *cmp = raw + S * tile4;                                 // [2][JT][nq]
+    uint64_t *full = (uint64_t *)(cmp + 2 * tile4);               // [S]
+    const int t = threadIdx.x;
+    const int jr = t >> lq_log2, l = t & (LQ - 1);
+    const int j0 = 2 * jr;
+    const bool lane_ok = jr < JR && l < nq;
+    const bool has_up = lane_ok && jr > 0, has_dn = lane_ok && jr < JR - 1;
+    const int y0 = blockIdx.x * TY;
+    const int xs = blockIdx.y * TX, xe = min(xs + TX, X);
+    const int n_in = xe - xs + 4;
+    const int last = (Z - 1) & 31;
+    const int klast = nw - 1 - 4 * l;
+    const int ktail = (klast >= 0 && klast < 3) ? klast : 3;
+    const int ush = (klast >= 0 && klast <= 3) ? last : 31;
+    uint4 vm = make_uint4(0u, 0u, 0u, 0u);
+    if (lane_ok) vm = make_uint4(mdvc_valid_mask(4 * l, Z), mdvc_valid_mask(4 * l + 1, Z), mdvc_valid_mask(4 * l + 2, Z),
+                                 mdvc_valid_mask(4 * l + 3, Z));
+    const int pl = l > 0 ? l - 1 : nq - 1, nl = l < nq - 1 ? l + 1 : 0;
+    const size_t plane = (size_t)Y * pitch;
+
+    auto issue = [&](int s, int stage) {
+        int x = xs - 2 + s;
+        x %= X; if (x < 0) x += X;
+        uint64_t *bar = full + stage;
+        uint32_t *dst = (uint32_t *)(raw + stage * tile4);
+        const uint32_t *pln = in + (size_t)x * plane;
+        mbar_expect_tx(bar, (uint32_t)tile4 * 16u);
+        int yy = (y0 - 2) % Y; if (yy < 0) yy += Y;
+        for (int r = 0; r < JT;) {
+            int len = min(JT - r, Y - yy);
+            bulk_g2s(dst + r * pitch, pln + (size_t)yy * pitch, (uint32_t)(len * pitch) * 4u, bar);
+            r += len; yy = 0;
+        }
+    };
+    auto edges = [&](uint4 v) -> uint32_t {                      // bit 0: top bit of the quad's last word, bit 1: its first bit
+        uint32_t hi;
+        if (FULLZ) hi = v.w >> 31;
+        else {
+            const uint32_t tw = ktail == 0 ? v.x : (ktail == 1 ? v.y : (ktail == 2 ? v.z : v.w));
+            hi = (tw >> ush) & 1u;
+        }
+        return hi | ((v.x & 1u) << 1);
+    };
+    auto spread = [&](uint4 v, uint32_t down, uint32_t up) -> uint4 {      // v | v<<1 | v>>1 along the periodic row
+        uint4 r;
+        r.x = v.x | ((v.x << 1) | down) | __funnelshift_r(v.x, v.y, 1);
+        r.y = v.y | __funnelshift_l(v.x, v.y, 1) | __funnelshift_r(v.y, v.z, 1);
+        r.z = v.z | __funnelshift_l(v.y, v.z, 1) | __funnelshift_r(v.z, v.w, 1);
+        r.w = v.w | __funnelshift_l(v.z, v.w, 1) | (v.w >> 1);
+        if (FULLZ) r.w |= up << 31;
+        else {
+            const uint32_t ub = up << ush;
+            r.x |= ktail == 0 ? ub : 0u; r.y |= ktail == 1 ? ub : 0u; r.z |= ktail == 2 ? ub : 0u; r.w |= ktail == 3 ? ub : 0u;
+            r = and4(r, vm);
+        }
+        return r;
+    };
+    auto zdil2 = [&](uint4 &a, uint4 &b) {                       // periodic z-dilation of two rows, one edge exchange
+        const uint32_t e = edges(a) | (edges(b) << 2);
+        const uint32_t pe = __shfl_sync(MDVC_FULL, e, pl, LQ);
+        const uint32_t ne = __shfl_sync(MDVC_FULL, e, nl, LQ);
+        a = spread(a, pe & 1u, (ne >> 1) & 1u);
+        b = spread(b, (pe >> 2) & 1u, (ne >> 3) & 1u);
+    };
+
+    if (t == 0) {
+        for (int i = 0; i < S; ++i) mbar_init(full + i, 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+    if (t == 0) for (int s = 0; s < S && s < n_in; ++s) issue(s, s);
+
+    const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
+    uint4 P0m1 = zero, P0m2 = zero, P1m1 = zero, P1m2 = zero, Q0m1 = zero, Q0m2 = zero, Q1m1 = zero, Q1m2 = zero;
+    const int yout0 = y0 + j0 - 2;
+    const bool out0 = lane_ok && j0 >= 2 && j0 <= JT - 3 && yout0 < Y;
+    const bool out1 = lane_ok && j0 + 1 >= 2 && j0 + 1 <= JT - 3 && yout0 + 1 < Y;
+    uint4 *op = (uint4 *)(out + (size_t)xs * plane + (size_t)((out0 || out1) ? yout0 : 0) * pitch) + l;
+    const size_t plane4 = plane >> 2;
+    const int me = j0 * nq + l;
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int s = 0; s < n_in; ++s) {
+        mbar_wait(full + stage, phase);
+        const uint4 *rw = raw + stage * tile4 + me;
+        uint4 a = zero, b = zero, c = zero, d = zero;
+        if (lane_ok) { b = rw[0]; c = rw[nq]; }
+        if (has_up) a = rw[-nq];
+        if (has_dn) d = rw[2 * nq];
+        const uint4 bc = or4(b, c);
+        uint4 P0 = or4(a, bc), P1 = or4(bc, d);
+        if (!FULLZ) { P0 = and4(P0, vm); P1 = and4(P1, vm); }
+        zdil2(P0, P1);
+        const uint4 n0 = and4(not4(or4(or4(P0m2, P0m1), P0)), vm), n1 = and4(not4(or4(or4(P1m2, P1m1), P1)), vm);
+        P0m2 = P0m1; P0m1 = P0; P1m2 = P1m1; P1m1 = P1;
+        uint4 *ex = cmp + (s & 1) * tile4 + me;
+        if (lane_ok) { ex[0] = n0; ex[nq] = n1; }
+        __syncthreads();
+        if (t == 0 && s + S < n_in) issue(s + S, stage);
+        const uint4 nn = or4(n0, n1);
+        uint4 Q0 = nn, Q1 = nn;
+        if (has_up) Q0 = or4(Q0, ex[-nq]);
+        if (has_dn) Q1 = or4(Q1, ex[2 * nq]);
+        zdil2(Q0, Q1);
+        if (s >= 4) {
+            if (out0) op[0] = and4(not4(or4(or4(Q0m2, Q0m1), Q0)), vm);
+            if (out1) op[nq] = and4(not4(or4(or4(Q1m2, Q1m1), Q1)), vm);
+            op += plane4;
+        }
+        Q0m2 = Q0m1; Q0m1 = Q0; Q1m2 = Q1m1; Q1m1 = Q1;
+        if (++stage == S) { stage = 0; phase ^= 1u; }
+    }
+}
+
 // 'd' immediately followed by 'e' on rows of at most 32 words.  Returns MDVC_OK with *done = 1 when the fused
 // kernel was launched, *done = 0 when the shape does not qualify (the caller then runs the two single steps).
 static int launch_close(const uint32_t *src, uint32_t *dst, int X, int Y, int Z, int pitch, cudaStream_t st, int *done) {
@@ -577,13 +708,17 @@ static int launch_close(const uint32_t *src, uint32_t *dst, int X, int Y, int Z,
         env_jt = getenv("MDVC_CLOSE_JT") ? atoi(getenv("MDVC_CLOSE_JT")) : 0;
         env_target = getenv("MDVC_CLOSE_TARGET") ? atoi(getenv("MDVC_CLOSE_TARGET")) : 0;
     }
-    int JT = CLOSE_THREADS / LQ;
+    static int env_rows = 0;
+    if (!env_rows) env_rows = getenv("MDVC_CLOSE_ROWS") ? atoi(getenv("MDVC_CLOSE_ROWS")) : 2;
+    const bool two = env_rows == 2;
+    int JT = two ? 2 * (256 / LQ) : CLOSE_THREADS / LQ;
     if (env_jt) JT = env_jt;
     if (JT > Y + 4) JT = Y + 4;                                   // one tile covers all of y
     size_t row_bytes = (size_t)(S + 2) * pitch * 4;
     int fit = (int)((48 * 1024 - S * 8) / row_bytes);
     if (JT > fit) JT = fit;
     if (JT < 5) JT = 5;
+    if (two) JT += JT & 1;                                        // an even number of rows, two per thread
     int TY = JT - 4;
     int ny = (Y + TY - 1) / TY;
     int target = env_target ? env_target : mdvc_num_sms() * 4;
@@ -593,11 +728,17 @@ static int launch_close(const uint32_t *src, uint32_t *dst, int X, int Y, int Z,
     if (xchunks > 65535) xchunks = 65535;
     int TX = (X + xchunks - 1) / xchunks;
     xchunks = (X + TX - 1) / TX;
-    int threads = ((JT * LQ + 31) / 32) * 32;
     size_t smem = (size_t)JT * row_bytes + S * 8;
     dim3 grid(ny, xchunks);
-    if (Z % 128 == 0) k_close_sweep<S, true><<<grid, threads, smem, st>>>(src, dst, X, Y, Z, pitch, nw, lq_log2, JT, TX);
-    else k_close_sweep<S, false><<<grid, threads, smem, st>>>(src, dst, X, Y, Z, pitch, nw, lq_log2, JT, TX);
+    if (two) {
+        int threads = (((JT / 2) * LQ + 31) / 32) * 32;
+        if (Z % 128 == 0) k_close_sweep2<S, true><<<grid, threads, smem, st>>>(src, dst, X, Y, Z, pitch, nw, lq_log2, JT / 2, TX);
+        else k_close_sweep2<S, false><<<grid, threads, smem, st>>>(src, dst, X, Y, Z, pitch, nw, lq_log2, JT / 2, TX);
+    } else {
+        int threads = ((JT * LQ + 31) / 32) * 32;
+        if (Z % 128 == 0) k_close_sweep<S, true><<<grid, threads, smem, st>>>(src, dst, X, Y, Z, pitch, nw, lq_log2, JT, TX);
+        else k_close_sweep<S, false><<<grid, threads, smem, st>>>(src, dst, X, Y, Z, pitch, nw, lq_log2, JT, TX);
+    }
     MDVC_LAUNCH_CHECK();
     *done = 1;
     return MDVC_OK;
