@@ -135,6 +135,24 @@ def test_binning_large_random_vs_oracle(dev):
     assert np.array_equal(p2.cpu().numpy().view(np.uint32), new_o.view(np.uint32))
 
 
+def test_binning_far_away_atoms_take_the_64_bit_path(dev):
+    """Voxel indices beyond 2^28 before wrapping (atoms thousands of box images away) leave the 32-bit fast path."""
+    rng = np.random.default_rng(18)
+    dims = np.array([60.0, 50.0, 45.0, 90, 90, 90], dtype=np.float32)
+    n = 4096
+    pos = (rng.random((n, 3)) * dims[:3]).astype(np.float32)
+    pos[::3] += np.float32(3.0e10)              # ~6e9 voxels away along every axis
+    pos[1::3] -= np.float32(7.5e9)
+    vox_o, nbox, new_o = vo.voxelate_fma(pos, dims, 0.5)
+    _, _, T, invT = vo.voxel_transform(dims, 0.5)
+    shape = tuple(int(v) for v in np.diagonal(nbox))
+    bits = dev.BitGrid(shape)
+    vox, newpos = dev.bin_atoms(torch.from_numpy(pos).cuda(), T, invT, nbox, bits, True, True)
+    assert np.array_equal(vox.cpu().numpy().astype(np.int64), vox_o)
+    assert np.array_equal(newpos.cpu().numpy().view(np.uint32), new_o.view(np.uint32))
+    assert np.array_equal(bits.to_bool().cpu().numpy(), vo.occupancy(vox_o, nbox))
+
+
 # ------------------------------------------------------------------------------------------ A5-A8 on runs
 def run_frame(dev, g, periodic=True, **plan_kw):
     bits = dev.BitGrid.from_bool(g)
