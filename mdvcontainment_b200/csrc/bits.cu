@@ -569,7 +569,8 @@ k_close_sweep(const uint32_t *__restrict__ in, uint32_t *__restrict__ out, int X
 // Two adjacent rows (j0 = 2*jr, j0+1) per thread: the raw rows j0-1 .. j0+2 serve both (4 LDS.128 instead of 6), the
 // exchange tile is read for j0-1 and j0+2 only, the edge bits of both rows travel in one pair of shuffles, and the
 // per-plane overhead (mbarrier wait, barrier, pointers) is paid once per two rows.
-template <int S, bool FULLZ>
+// E1 / E2: the first / second operation is an erosion (dilation of the complement); 'de' is <false, true>.
+template <int S, bool FULLZ, bool E1, bool E2>
 __global__ void __launch_bounds__(256)
 k_close_sweep2(const uint32_t *__restrict__ in, uint32_t *__restrict__ out, int X, int Y, int Z, int pitch, int nw,
                int lq_log2, int JR, int TX) {
@@ -668,11 +669,23 @@ k_close_sweep2(const uint32_t *__restrict__ in, uint32_t *__restrict__ out, int 
         if (lane_ok) { b = rw[0]; c = rw[nq]; }
         if (has_up) a = rw[-nq];
         if (has_dn) d = rw[2 * nq];
-        const uint4 bc = or4(b, c);
-        uint4 P0 = or4(a, bc), P1 = or4(bc, d);
-        if (!FULLZ) { P0 = and4(P0, vm); P1 = and4(P1, vm); }
+        uint4 P0, P1;
+        if (E1) {                                                 // dilate the complement: ~a | ~b | ~c = ~(a & b & c)
+            const uint4 ones = make_uint4(~0u, ~0u, ~0u, ~0u);
+            if (!has_up) a = ones;
+            if (!has_dn) d = ones;
+            const uint4 bc = and4(b, c);
+            P0 = and4(not4(and4(a, bc)), vm); P1 = and4(not4(and4(bc, d)), vm);
+        } else {
+            const uint4 bc = or4(b, c);
+            P0 = or4(a, bc); P1 = or4(bc, d);
+            if (!FULLZ) { P0 = and4(P0, vm); P1 = and4(P1, vm); }
+        }
         zdil2(P0, P1);
-        const uint4 n0 = and4(not4(or4(or4(P0m2, P0m1), P0)), vm), n1 = and4(not4(or4(or4(P1m2, P1m1), P1)), vm);
+        // the dilated plane x-1 of the first operation, handed to the second one complemented iff exactly one of
+        // the two operations is an erosion (erosion = complement, dilate, complement)
+        uint4 n0 = or4(or4(P0m2, P0m1), P0), n1 = or4(or4(P1m2, P1m1), P1);
+        if (E1 != E2) { n0 = and4(not4(n0), vm); n1 = and4(not4(n1), vm); }
         P0m2 = P0m1; P0m1 = P0; P1m2 = P1m1; P1m1 = P1;
         uint4 *ex = cmp + (s & 1) * tile4 + me;
         if (lane_ok) { ex[0] = n0; ex[nq] = n1; }
@@ -684,8 +697,10 @@ k_close_sweep2(const uint32_t *__restrict__ in, uint32_t *__restrict__ out, int 
         if (has_dn) Q1 = or4(Q1, ex[2 * nq]);
         zdil2(Q0, Q1);
         if (s >= 4) {
-            if (out0) op[0] = and4(not4(or4(or4(Q0m2, Q0m1), Q0)), vm);
-            if (out1) op[nq] = and4(not4(or4(or4(Q1m2, Q1m1), Q1)), vm);
+            uint4 o0 = or4(or4(Q0m2, Q0m1), Q0), o1 = or4(or4(Q1m2, Q1m1), Q1);
+            if (E2) { o0 = and4(not4(o0), vm); o1 = and4(not4(o1), vm); }
+            if (out0) op[0] = o0;
+            if (out1) op[nq] = o1;
             op += plane4;
         }
         Q0m2 = Q0m1; Q0m1 = Q0; Q1m2 = Q1m1; Q1m1 = Q1;
@@ -695,7 +710,8 @@ k_close_sweep2(const uint32_t *__restrict__ in, uint32_t *__restrict__ out, int 
 
 // 'd' immediately followed by 'e' on rows of at most 32 words.  Returns MDVC_OK with *done = 1 when the fused
 // kernel was launched, *done = 0 when the shape does not qualify (the caller then runs the two single steps).
-static int launch_close(const uint32_t *src, uint32_t *dst, int X, int Y, int Z, int pitch, cudaStream_t st, int *done) {
+static int launch_close(const uint32_t *src, uint32_t *dst, int X, int Y, int Z, int pitch, bool e1, bool e2, cudaStream_t st,
+                        int *done) {
     *done = 0;
     constexpr int S = 3;
     int nw = mdvc_words(Z);
@@ -711,6 +727,7 @@ static int launch_close(const uint32_t *src, uint32_t *dst, int X, int Y, int Z,
     static int env_rows = 0;
     if (!env_rows) env_rows = getenv("MDVC_CLOSE_ROWS") ? atoi(getenv("MDVC_CLOSE_ROWS")) : 2;
     const bool two = env_rows == 2;
+    if (!two && (e1 || !e2)) return MDVC_OK;                      // the one-row kernel only knows the closing
     int JT = two ? 2 * (256 / LQ) : CLOSE_THREADS / LQ;
     if (env_jt) JT = env_jt;
     if (JT > Y + 4) JT = Y + 4;                                   // one tile covers all of y
@@ -732,8 +749,19 @@ static int launch_close(const uint32_t *src, uint32_t *dst, int X, int Y, int Z,
     dim3 grid(ny, xchunks);
     if (two) {
         int threads = (((JT / 2) * LQ + 31) / 32) * 32;
-        if (Z % 128 == 0) k_close_sweep2<S, true><<<grid, threads, smem, st>>>(src, dst, X, Y, Z, pitch, nw, lq_log2, JT / 2, TX);
-        else k_close_sweep2<S, false><<<grid, threads, smem, st>>>(src, dst, X, Y, Z, pitch, nw, lq_log2, JT / 2, TX);
+#define MDVC_CLOSE2(FZ, A, B) k_close_sweep2<S, FZ, A, B><<<grid, threads, smem, st>>>(src, dst, X, Y, Z, pitch, nw, lq_log2, JT / 2, TX)
+        const int variant = (Z % 128 == 0 ? 4 : 0) | (e1 ? 2 : 0) | (e2 ? 1 : 0);
+        switch (variant) {
+            case 0: MDVC_CLOSE2(false, false, false); break;
+            case 1: MDVC_CLOSE2(false, false, true); break;
+            case 2: MDVC_CLOSE2(false, true, false); break;
+            case 3: MDVC_CLOSE2(false, true, true); break;
+            case 4: MDVC_CLOSE2(true, false, false); break;
+            case 5: MDVC_CLOSE2(true, false, true); break;
+            case 6: MDVC_CLOSE2(true, true, false); break;
+            default: MDVC_CLOSE2(true, true, true); break;
+        }
+#undef MDVC_CLOSE2
     } else {
         int threads = ((JT * LQ + 31) / 32) * 32;
         if (Z % 128 == 0) k_close_sweep<S, true><<<grid, threads, smem, st>>>(src, dst, X, Y, Z, pitch, nw, lq_log2, JT, TX);
@@ -789,11 +817,18 @@ extern "C" int mdvc_morph(const uint32_t *bits_in, uint32_t *bits_out, uint32_t 
     }
     if (n_ops > 1 && (!tmp || tmp == bits_in || tmp == bits_out)) return MDVC_ERR_BADARG;
     // ping-pong so that the last step lands in bits_out
-    // a 'd' directly followed by an 'e' (a closing) runs as one fused launch where the shape allows it
-    const bool can_fuse = mdvc_words(Z) <= 32 && !getenv("MDVC_NO_FUSED_CLOSE");
+    // two consecutive operations (the closing 'de' above all) run as one fused launch where the shape allows it
+    // (decided up front from the same conditions launch_close checks, so that the ping-pong plan below holds)
+    const int nw = mdvc_words(Z);
+    const uintptr_t all_ptrs = (uintptr_t)bits_in | (uintptr_t)bits_out | (uintptr_t)tmp;
+    const bool can_fuse = nw <= 32 && pitch == ((nw + 3) / 4) * 4 && (all_ptrs & 15) == 0 && !getenv("MDVC_NO_FUSED_CLOSE");
+    const bool any_pair = can_fuse && !(getenv("MDVC_CLOSE_ROWS") && atoi(getenv("MDVC_CLOSE_ROWS")) == 1);
+    auto pair_at = [&](size_t i) {
+        return can_fuse && i + 1 < n_ops && (any_pair || (ops[i] == 'd' && ops[i + 1] == 'e'));
+    };
     size_t n_launch = 0;
     for (size_t i = 0; i < n_ops; ++i, ++n_launch)
-        if (can_fuse && ops[i] == 'd' && i + 1 < n_ops && ops[i + 1] == 'e') ++i;
+        if (pair_at(i)) ++i;
     const uint32_t *src = bits_in;
     size_t k = 0;
     for (size_t i = 0; i < n_ops; ++i, ++k) {
@@ -801,11 +836,12 @@ extern "C" int mdvc_morph(const uint32_t *bits_in, uint32_t *bits_out, uint32_t 
         uint32_t *dst = to_out ? bits_out : tmp;
         if (!dst) return MDVC_ERR_BADARG;
         int fused = 0;
-        if (can_fuse && ops[i] == 'd' && i + 1 < n_ops && ops[i + 1] == 'e') {
-            int rc = launch_close(src, dst, X, Y, Z, pitch, st, &fused);
+        if (pair_at(i)) {
+            int rc = launch_close(src, dst, X, Y, Z, pitch, ops[i] == 'e', ops[i + 1] == 'e', st, &fused);
             if (rc) return rc;
         }
         if (fused) { ++i; src = dst; continue; }
+        if (pair_at(i)) { mdvc_set_error_msg("fused morph pair declined after planning"); return MDVC_ERR_BADARG; }
         int rc = launch_morph(src, dst, X, Y, Z, pitch, ops[i] == 'e', st);
         if (rc) return rc;
         src = dst;

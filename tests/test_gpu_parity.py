@@ -65,9 +65,9 @@ FUSED_CLOSE_SHAPES = [
 
 
 @pytest.mark.parametrize("shape", FUSED_CLOSE_SHAPES)
-@pytest.mark.parametrize("ops", ["de", "dde", "ded", "edde"])
+@pytest.mark.parametrize("ops", ["de", "dde", "ded", "edde", "dd", "ee", "ed", "eedd"])
 def test_fused_closing_tiles(dev, shape, ops):
-    """'d' directly followed by 'e' runs as one TMA-staged launch; shapes chosen to cross y tiles, x chunks,
+    """Two consecutive morph operations run as one TMA-staged launch; shapes chosen to cross y tiles, x chunks,
     the periodic wrap inside a tile, partial last words and non-power-of-two row lengths."""
     rng = np.random.default_rng(hash(shape) % 1000)
     for p in (0.02, 0.3, 0.8):
