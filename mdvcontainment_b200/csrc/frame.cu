@@ -1182,7 +1182,7 @@ __device__ __noinline__ void pairs_one_run_global(const uint32_t *__restrict__ b
 #define PT_ROWS (PT_TY + 2)
 #define PT_SLOTS (2 * PT_ROWS)
 #define PT_CAP 3072
-__global__ void __launch_bounds__(TILE_THREADS, 5)
+__global__ void __launch_bounds__(2 * PT_TY, 4)
 k_tile_pairs(const uint32_t *__restrict__ bits, Dims D, Hdr *h, const uint32_t *__restrict__ rowoff,
              const uint32_t *__restrict__ runstart, const int32_t *__restrict__ lab,
              unsigned long long *cset, uint32_t c_slots, unsigned long long *bset, uint32_t b_slots, int periodic) {
@@ -1258,9 +1258,12 @@ k_tile_pairs(const uint32_t *__restrict__ bits, Dims D, Hdr *h, const uint32_t *
                 }
             }
             __syncthreads();
-            // one thread per own row: its runs are visited in z order, so the position in each of the four
-            // neighbour rows only moves forward (merge walk, no searches); z-face steps once per row
-            for (int slot = 1 + (int)threadIdx.x; slot <= ny; slot += blockDim.x) {
+            // two threads per own row (thread groups of PT_TY): group 0 takes the in-row contacts, the neighbour row
+            // in the own plane and the z-face steps, group 1 the three neighbour rows of the other plane.  The runs
+            // are visited in z order, so the position in a neighbour row only moves forward (merge walk, no searches).
+            const int grp = (int)threadIdx.x / PT_TY;
+            const int q_lo = grp == 0 ? 0 : 1, q_hi = grp == 0 ? 1 : 4;
+            for (int slot = 1 + (int)threadIdx.x % PT_TY; slot <= ny; slot += PT_TY) {
                 const uint32_t rb0 = soff[slot], re0 = soff[slot + 1];
                 int nsl[4]; uint32_t pj[4], pe[4];
 #pragma unroll
@@ -1280,6 +1283,7 @@ k_tile_pairs(const uint32_t *__restrict__ bits, Dims D, Hdr *h, const uint32_t *
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
                     const int ns = nsl[q];
+                    if (q < q_lo || q >= q_hi) { pj[q] = pe[q]; continue; }
                     if (pj[q] == pe[q] || ((q == 0 ? 0 : sx_other) | ssy[ns])) continue;
                     const uint32_t n = re0 - rb0, pb = pj[q];
                     bool mirror = (pe[q] - pb) == n && spol[ns] == pol0;
@@ -1293,7 +1297,7 @@ k_tile_pairs(const uint32_t *__restrict__ bits, Dims D, Hdr *h, const uint32_t *
                     const int b = (k + 1 < re0) ? (int)tz[k + 1] - 1 : D.Z - 1;
                     const uint32_t pol = pol0 ^ ((k - rb0) & 1u);
                     const int la = tv[k];
-                    if (k > rb0) emit_contact(cs, tv[k - 1], la);
+                    if (grp == 0 && k > rb0) emit_contact(cs, tv[k - 1], la);
                     // Bridges take every run of the neighbour row within one voxel of [a, b].  Contacts only need the
                     // runs of the other value that overlap [a, b] itself: a run that merely touches diagonally sits
                     // next to a run of this run's value that overlaps it (same label as this run), so that pair is
@@ -1317,7 +1321,7 @@ k_tile_pairs(const uint32_t *__restrict__ bits, Dims D, Hdr *h, const uint32_t *
                         }
                     }
                 }
-                if (periodic) {
+                if (periodic && grp == 0) {
                     // z-face steps: nine records per row whose labels and wrap flags almost always repeat from
                     // the previous row this thread handled.  The nine keys cycle through the 2-key cache, so
                     // each would take the out-of-line set insertion; instead the row's z-face signature (the
@@ -1803,7 +1807,7 @@ extern "C" int mdvc_frame_pairs(const uint32_t *bits, int X, int Y, int Z, int p
     {
         long long tiles = (long long)D.X * ((D.Y + PT_TY - 1) / PT_TY);
         unsigned tgrid = (unsigned)(tiles < (long long)mdvc_num_sms() * 32 ? tiles : (long long)mdvc_num_sms() * 32);
-        k_tile_pairs<<<tgrid, TILE_THREADS, 0, st>>>(bits, D, h, at<uint32_t>(ws, L.rowoff), at<uint32_t>(ws, L.runstart),
+        k_tile_pairs<<<tgrid, 2 * PT_TY, 0, st>>>(bits, D, h, at<uint32_t>(ws, L.rowoff), at<uint32_t>(ws, L.runstart),
                                             at<int32_t>(ws, L.lab), cset, caps->contact_slots, bset,
                                             caps->bridge_slots, periodic);
         MDVC_LAUNCH_CHECK();
