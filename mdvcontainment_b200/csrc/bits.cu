@@ -738,7 +738,7 @@ static int launch_close(const uint32_t *src, uint32_t *dst, int X, int Y, int Z,
     if (two) JT += JT & 1;                                        // an even number of rows, two per thread
     int TY = JT - 4;
     int ny = (Y + TY - 1) / TY;
-    int target = env_target ? env_target : mdvc_num_sms() * 4;
+    int target = env_target ? env_target : mdvc_num_sms() * mdvc_cap_ctas(4);
     int xchunks = (target + ny - 1) / ny;
     if (xchunks > (X + 7) / 8) xchunks = (X + 7) / 8;
     if (xchunks < 1) xchunks = 1;

@@ -1758,7 +1758,7 @@ extern "C" int mdvc_frame_label(const uint32_t *bits, int X, int Y, int Z, int p
     {
         int spp = (D.Y + STRIP_TY - 1) / STRIP_TY;
         long long n_strips = (long long)D.X * spp;
-        unsigned sgrid = (unsigned)(n_strips < (long long)mdvc_num_sms() * 32 ? n_strips : (long long)mdvc_num_sms() * 32);
+        unsigned sgrid = (unsigned)(n_strips < (long long)mdvc_num_sms() * mdvc_cap_ctas(32) ? n_strips : (long long)mdvc_num_sms() * mdvc_cap_ctas(32));
         unsigned lgrid = mdvc_grid(caps->max_runs, 256, 4);
         k_strip_link<<<sgrid, TILE_THREADS, 0, st>>>(bits, D, h, rowoff, runstart, parent, rootlist);
         MDVC_LAUNCH_CHECK();
@@ -1771,7 +1771,7 @@ extern "C" int mdvc_frame_label(const uint32_t *bits, int X, int Y, int Z, int p
         }
         for (long long s = 1; s < D.X; s *= LINK_RADIX) {
             long long tiles = (long long)((D.X - 1) / s) * spp;
-            unsigned tgrid = (unsigned)(tiles < (long long)mdvc_num_sms() * 32 ? tiles : (long long)mdvc_num_sms() * 32);
+            unsigned tgrid = (unsigned)(tiles < (long long)mdvc_num_sms() * mdvc_cap_ctas(32) ? tiles : (long long)mdvc_num_sms() * mdvc_cap_ctas(32));
             k_tile_link_x<<<tgrid, TILE_THREADS, 0, st>>>(bits, D, h, rowoff, runstart, parent, (int)s, LINK_RADIX);
             MDVC_LAUNCH_CHECK();
             k_flatten_list<<<lgrid, 256, 0, st>>>(h, rootlist, parent);
@@ -1806,7 +1806,7 @@ extern "C" int mdvc_frame_pairs(const uint32_t *bits, int X, int Y, int Z, int p
     MDVC_CUDA_CHECK(cudaMemsetAsync(&h->n_contacts, 0, 2 * sizeof(uint32_t), st));
     {
         long long tiles = (long long)D.X * ((D.Y + PT_TY - 1) / PT_TY);
-        unsigned tgrid = (unsigned)(tiles < (long long)mdvc_num_sms() * 32 ? tiles : (long long)mdvc_num_sms() * 32);
+        unsigned tgrid = (unsigned)(tiles < (long long)mdvc_num_sms() * mdvc_cap_ctas(32) ? tiles : (long long)mdvc_num_sms() * mdvc_cap_ctas(32));
         k_tile_pairs<<<tgrid, 2 * PT_TY, 0, st>>>(bits, D, h, at<uint32_t>(ws, L.rowoff), at<uint32_t>(ws, L.runstart),
                                             at<int32_t>(ws, L.lab), cset, caps->contact_slots, bset,
                                             caps->bridge_slots, periodic);
