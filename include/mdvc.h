@@ -77,6 +77,13 @@ int mdvc_bin_atoms(const float *pos, long long n, const double *T_host, const do
  * ------------------------------------------------------------------------------------- */
 int mdvc_morph(const uint32_t *bits_in, uint32_t *bits_out, uint32_t *tmp, int X, int Y, int Z,
                int pitch, const char *ops, void *stream);
+/* mdvc_morph that also counts the z-runs of every row of the RESULT into row_counts[X*Y] when its last launch is a
+ * fused pair of operations (atomgroup_to_voxels.py:278-304 followed by the first pass of label.py:10-13): the rows
+ * are in registers there, which saves the labelling one pass over the grid.  *counted (host) = 1 if row_counts was
+ * filled, 0 if the shape or morph string did not allow it (then run mdvc_frame_label as usual). */
+int mdvc_morph_counted(const uint32_t *bits_in, uint32_t *bits_out, uint32_t *tmp, int X, int Y, int Z, int pitch,
+                       const char *ops, uint32_t *row_counts, int *counted, void *stream);
+
 
 /* ---------------------------------------------------------------------------------------
  * Frame pipeline on the bit grid (the fast path):  A5 labels (label.py:4-19), A7 contacts
@@ -113,6 +120,13 @@ size_t mdvc_frame_workspace_bytes(int X, int Y, int Z, const mdvc_frame_caps *ca
  * label numbering = rank of the component's first voxel in C-order, per polarity (scipy's). */
 int mdvc_frame_label(const uint32_t *bits, int X, int Y, int Z, int pitch,
                      void *workspace, size_t workspace_bytes, const mdvc_frame_caps *caps, void *stream);
+/* mdvc_frame_label whose stage 1a (z-runs per row, label.py:10-13 restated on runs) was already done by the kernel
+ * that produced the grid: rows_counted != 0 means mdvc_frame_row_counts_ptr() holds the count of every row. */
+int mdvc_frame_label_counted(const uint32_t *bits, int X, int Y, int Z, int pitch, void *workspace, size_t workspace_bytes,
+                             const mdvc_frame_caps *caps, int rows_counted, void *stream);
+/* Device array (uint32[X*Y + 2]) the label stage reads its per-row run counts from. */
+uint32_t *mdvc_frame_row_counts_ptr(void *workspace, int X, int Y, int Z, const mdvc_frame_caps *caps);
+
 /* Stage 2: unique contact pairs and bridge records, sorted like the reference's rows.
  * periodic = 0 skips bridges (the reference's slab=True path, containment_main.py:67-69); 1 = periodic in x, y
  * and z; 2 = periodic in y and z only (one slab of a slab-decomposed grid: the x faces are the caller's,

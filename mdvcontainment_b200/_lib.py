@@ -50,8 +50,11 @@ SIGNATURES = {
     "mdvc_popcount": (_I, [_P, _I, _I, _I, _I, _P, _P]),
     "mdvc_bin_atoms": (_I, [_P, _LL, _P, _P, _P, _P, _I, _P, _P, _P]),
     "mdvc_morph": (_I, [_P, _P, _P, _I, _I, _I, _I, ctypes.c_char_p, _P]),
+    "mdvc_morph_counted": (_I, [_P, _P, _P, _I, _I, _I, _I, ctypes.c_char_p, _P, _P, _P]),
     "mdvc_frame_workspace_bytes": (_SZ, [_I, _I, _I, _CAPS]),
     "mdvc_frame_label": (_I, [_P, _I, _I, _I, _I, _P, _SZ, _CAPS, _P]),
+    "mdvc_frame_label_counted": (_I, [_P, _I, _I, _I, _I, _P, _SZ, _CAPS, _I, _P]),
+    "mdvc_frame_row_counts_ptr": (_P, [_P, _I, _I, _I, _CAPS]),
     "mdvc_frame_pairs": (_I, [_P, _I, _I, _I, _I, _P, _SZ, _CAPS, _I, _P]),
     "mdvc_frame_components": (_I, [_I, _I, _I, _P, _SZ, _CAPS, _I, _P]),
     "mdvc_frame_set_lut": (_I, [_I, _I, _I, _P, _SZ, _CAPS, _P, _U32, _P]),

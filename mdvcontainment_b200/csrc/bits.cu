@@ -573,7 +573,7 @@ k_close_sweep(const uint32_t *__restrict__ in, uint32_t *__restrict__ out, int X
 template <int S, bool FULLZ, bool E1, bool E2>
 __global__ void __launch_bounds__(256)
 k_close_sweep2(const uint32_t *__restrict__ in, uint32_t *__restrict__ out, int X, int Y, int Z, int pitch, int nw,
-               int lq_log2, int JR, int TX) {
+               int lq_log2, int JR, int TX, uint32_t *__restrict__ row_counts) {
     extern __shared__ __align__(128) unsigned char close_smem[];
     const int LQ = 1 << lq_log2;
     const int nq = pitch >> 2;
@@ -702,6 +702,17 @@ k_close_sweep2(const uint32_t *__restrict__ in, uint32_t *__restrict__ out, int 
             if (out0) op[0] = o0;
             if (out1) op[nq] = o1;
             op += plane4;
+            if (row_counts) {
+                // stage 1a of the labelling for free: z-runs per finished row (every lane takes part in the shuffles)
+                const QuadStarts s0 = mdvc_quad_starts(o0, vm, l, LQ), s1 = mdvc_quad_starts(o1, vm, l, LQ);
+                uint32_t c0 = __popc(s0.s0) + __popc(s0.s1) + __popc(s0.s2) + __popc(s0.s3);
+                uint32_t c1 = __popc(s1.s0) + __popc(s1.s1) + __popc(s1.s2) + __popc(s1.s3);
+                uint32_t cc = c0 | (c1 << 16);                    // a row has at most 1024 runs here
+                for (int o = LQ >> 1; o > 0; o >>= 1) cc += __shfl_xor_sync(MDVC_FULL, cc, o, LQ);
+                const size_t row0 = (size_t)(xs + s - 4) * Y + yout0;
+                if (out0 && l == 0) row_counts[row0] = cc & 0xffffu;
+                if (out1 && l == 0) row_counts[row0 + 1] = cc >> 16;
+            }
         }
         Q0m2 = Q0m1; Q0m1 = Q0; Q1m2 = Q1m1; Q1m1 = Q1;
         if (++stage == S) { stage = 0; phase ^= 1u; }
@@ -711,7 +722,7 @@ k_close_sweep2(const uint32_t *__restrict__ in, uint32_t *__restrict__ out, int 
 // 'd' immediately followed by 'e' on rows of at most 32 words.  Returns MDVC_OK with *done = 1 when the fused
 // kernel was launched, *done = 0 when the shape does not qualify (the caller then runs the two single steps).
 static int launch_close(const uint32_t *src, uint32_t *dst, int X, int Y, int Z, int pitch, bool e1, bool e2, cudaStream_t st,
-                        int *done) {
+                        int *done, uint32_t *row_counts = nullptr, int *counted = nullptr) {
     *done = 0;
     constexpr int S = 3;
     int nw = mdvc_words(Z);
@@ -749,7 +760,7 @@ static int launch_close(const uint32_t *src, uint32_t *dst, int X, int Y, int Z,
     dim3 grid(ny, xchunks);
     if (two) {
         int threads = (((JT / 2) * LQ + 31) / 32) * 32;
-#define MDVC_CLOSE2(FZ, A, B) k_close_sweep2<S, FZ, A, B><<<grid, threads, smem, st>>>(src, dst, X, Y, Z, pitch, nw, lq_log2, JT / 2, TX)
+#define MDVC_CLOSE2(FZ, A, B) k_close_sweep2<S, FZ, A, B><<<grid, threads, smem, st>>>(src, dst, X, Y, Z, pitch, nw, lq_log2, JT / 2, TX, row_counts)
         const int variant = (Z % 128 == 0 ? 4 : 0) | (e1 ? 2 : 0) | (e2 ? 1 : 0);
         switch (variant) {
             case 0: MDVC_CLOSE2(false, false, false); break;
@@ -762,6 +773,7 @@ static int launch_close(const uint32_t *src, uint32_t *dst, int X, int Y, int Z,
             default: MDVC_CLOSE2(true, true, true); break;
         }
 #undef MDVC_CLOSE2
+        if (counted) *counted = row_counts != nullptr;
     } else {
         int threads = ((JT * LQ + 31) / 32) * 32;
         if (Z % 128 == 0) k_close_sweep<S, true><<<grid, threads, smem, st>>>(src, dst, X, Y, Z, pitch, nw, lq_log2, JT, TX);
@@ -803,8 +815,9 @@ static int launch_morph(const uint32_t *src, uint32_t *dst, int X, int Y, int Z,
     return MDVC_OK;
 }
 
-extern "C" int mdvc_morph(const uint32_t *bits_in, uint32_t *bits_out, uint32_t *tmp, int X, int Y, int Z,
-                          int pitch, const char *ops, void *stream) {
+static int morph_impl(const uint32_t *bits_in, uint32_t *bits_out, uint32_t *tmp, int X, int Y, int Z,
+                      int pitch, const char *ops, uint32_t *row_counts, int *counted, void *stream) {
+    if (counted) *counted = 0;
     if (!bits_in || !bits_out || !ops || bad_dims(X, Y, Z, pitch) || bits_in == bits_out) return MDVC_ERR_BADARG;
     cudaStream_t st = (cudaStream_t)stream;
     size_t n_ops = strlen(ops);
@@ -837,7 +850,9 @@ extern "C" int mdvc_morph(const uint32_t *bits_in, uint32_t *bits_out, uint32_t 
         if (!dst) return MDVC_ERR_BADARG;
         int fused = 0;
         if (pair_at(i)) {
-            int rc = launch_close(src, dst, X, Y, Z, pitch, ops[i] == 'e', ops[i + 1] == 'e', st, &fused);
+            const bool last = i + 2 == n_ops;                     // only the final grid's rows are worth counting
+            int rc = launch_close(src, dst, X, Y, Z, pitch, ops[i] == 'e', ops[i + 1] == 'e', st, &fused,
+                                  last ? row_counts : nullptr, last ? counted : nullptr);
             if (rc) return rc;
         }
         if (fused) { ++i; src = dst; continue; }
@@ -847,4 +862,15 @@ extern "C" int mdvc_morph(const uint32_t *bits_in, uint32_t *bits_out, uint32_t 
         src = dst;
     }
     return MDVC_OK;
+}
+
+extern "C" int mdvc_morph(const uint32_t *bits_in, uint32_t *bits_out, uint32_t *tmp, int X, int Y, int Z,
+                          int pitch, const char *ops, void *stream) {
+    return morph_impl(bits_in, bits_out, tmp, X, Y, Z, pitch, ops, nullptr, nullptr, stream);
+}
+
+extern "C" int mdvc_morph_counted(const uint32_t *bits_in, uint32_t *bits_out, uint32_t *tmp, int X, int Y, int Z,
+                                  int pitch, const char *ops, uint32_t *row_counts, int *counted, void *stream) {
+    if (!counted) return MDVC_ERR_BADARG;
+    return morph_impl(bits_in, bits_out, tmp, X, Y, Z, pitch, ops, row_counts, counted, stream);
 }

@@ -141,3 +141,21 @@ __device__ __forceinline__ void mdvc_uf_union(uint32_t *parent, uint32_t a, uint
     }
 }
 #endif  // __CUDACC__
+
+// --- run starts of a row held as 16-byte quads (4 words per lane, `width` lanes per row) ------------------
+struct QuadStarts { uint32_t s0, s1, s2, s3; };
+
+// Start mask of the quad: bit k of s_m set <=> a z-run starts at voxel 32*(4*ql+m)+k.  B must be masked to the
+// valid voxels; vm is the quad's valid mask; every lane of the warp has to call this (shuffle inside).
+__device__ __forceinline__ QuadStarts mdvc_quad_starts(uint4 B, uint4 vm, int ql, int width) {
+    uint32_t prev = __shfl_up_sync(MDVC_FULL, B.w, 1, width) >> 31;
+    if (ql == 0) prev = 0;
+    QuadStarts q;
+    q.s0 = B.x ^ ((B.x << 1) | prev);
+    if (ql == 0) q.s0 |= 1u;
+    q.s0 &= vm.x;
+    q.s1 = (B.y ^ __funnelshift_l(B.x, B.y, 1)) & vm.y;
+    q.s2 = (B.z ^ __funnelshift_l(B.y, B.z, 1)) & vm.z;
+    q.s3 = (B.w ^ __funnelshift_l(B.z, B.w, 1)) & vm.w;
+    return q;
+}

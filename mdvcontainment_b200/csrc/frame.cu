@@ -309,22 +309,6 @@ k_fill_runs(const uint32_t *__restrict__ bits, Dims D, const Hdr *__restrict__ h
 // lane.  Run starts inside the quad come from funnel shifts, only the quad's first word needs a neighbour lane;
 // about a third of the instructions per word of the word-per-lane kernels above.
 // ------------------------------------------------------------------------------------------
-struct QuadStarts { uint32_t s0, s1, s2, s3; };
-
-template <int LQ>
-__device__ __forceinline__ QuadStarts quad_starts(uint4 B, uint4 vm, int ql) {
-    uint32_t prev = __shfl_up_sync(MDVC_FULL, B.w, 1, LQ) >> 31;
-    if (ql == 0) prev = 0;
-    QuadStarts q;
-    q.s0 = B.x ^ ((B.x << 1) | prev);
-    if (ql == 0) q.s0 |= 1u;
-    q.s0 &= vm.x;
-    q.s1 = (B.y ^ __funnelshift_l(B.x, B.y, 1)) & vm.y;
-    q.s2 = (B.z ^ __funnelshift_l(B.y, B.z, 1)) & vm.z;
-    q.s3 = (B.w ^ __funnelshift_l(B.z, B.w, 1)) & vm.w;
-    return q;
-}
-
 __device__ __forceinline__ uint4 quad_valid_mask(int ql, int nq, int Z) {
     if (ql >= nq) return make_uint4(0u, 0u, 0u, 0u);
     return make_uint4(mdvc_valid_mask(4 * ql, Z), mdvc_valid_mask(4 * ql + 1, Z), mdvc_valid_mask(4 * ql + 2, Z),
@@ -351,7 +335,7 @@ k_count_runs_q(const uint32_t *__restrict__ bits, Dims D, uint32_t *__restrict__
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             long long row = rb + u * RPW + gi;
-            QuadStarts q = quad_starts<LQ>(B[u], vm, ql);
+            QuadStarts q = mdvc_quad_starts(B[u], vm, ql, LQ);
             uint32_t total = __popc(q.s0) + __popc(q.s1) + __popc(q.s2) + __popc(q.s3);
 #pragma unroll
             for (int o = LQ / 2; o > 0; o >>= 1) total += __shfl_xor_sync(MDVC_FULL, total, o, LQ);
@@ -397,7 +381,7 @@ k_fill_runs_q(const uint32_t *__restrict__ bits, Dims D, const Hdr *__restrict__
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             long long row = rb + u * RPW + gi;
-            QuadStarts q = quad_starts<LQ>(B[u], vm, ql);
+            QuadStarts q = mdvc_quad_starts(B[u], vm, ql, LQ);
             const uint32_t cnt = __popc(q.s0) + __popc(q.s1) + __popc(q.s2) + __popc(q.s3);
             uint32_t inc = cnt;
 #pragma unroll
@@ -1709,8 +1693,27 @@ static int check_ws(void *ws, size_t ws_bytes, const mdvc_frame_caps *caps, long
     return MDVC_OK;
 }
 
+static int frame_label(const uint32_t *bits, int X, int Y, int Z, int pitch, void *ws, size_t ws_bytes,
+                       const mdvc_frame_caps *caps, int rows_counted, void *stream);
+
 extern "C" int mdvc_frame_label(const uint32_t *bits, int X, int Y, int Z, int pitch, void *ws, size_t ws_bytes,
                                 const mdvc_frame_caps *caps, void *stream) {
+    return frame_label(bits, X, Y, Z, pitch, ws, ws_bytes, caps, 0, stream);
+}
+
+extern "C" int mdvc_frame_label_counted(const uint32_t *bits, int X, int Y, int Z, int pitch, void *ws, size_t ws_bytes,
+                                        const mdvc_frame_caps *caps, int rows_counted, void *stream) {
+    return frame_label(bits, X, Y, Z, pitch, ws, ws_bytes, caps, rows_counted, stream);
+}
+
+extern "C" uint32_t *mdvc_frame_row_counts_ptr(void *ws, int X, int Y, int Z, const mdvc_frame_caps *caps) {
+    if (!ws || !caps_ok(caps) || X <= 0 || Y <= 0 || Z <= 0) return nullptr;
+    Layout L = make_layout((long long)X * Y, caps);
+    return at<uint32_t>(ws, L.rowoff);
+}
+
+static int frame_label(const uint32_t *bits, int X, int Y, int Z, int pitch, void *ws, size_t ws_bytes,
+                       const mdvc_frame_caps *caps, int rows_counted, void *stream) {
     Dims D; Layout L;
     if (!bits || !make_dims(X, Y, Z, pitch, D)) return MDVC_ERR_BADARG;
     int rc = check_ws(ws, ws_bytes, caps, D.rows, L);
@@ -1733,13 +1736,16 @@ extern "C" int mdvc_frame_label(const uint32_t *bits, int X, int Y, int Z, int p
     while (lq < D.pitch / 4) lq <<= 1;
     const bool quad = lq <= 32 && D.pitch % 4 == 0 && (reinterpret_cast<uintptr_t>(bits) & 15) == 0 &&
                       !getenv("MDVC_NO_QUAD_RUNS");
-    if (quad) {
-        row_grid = mdvc_grid(D.rows * lq / 4, 256, 8);
+    if (quad) row_grid = mdvc_grid(D.rows * lq / 4, 256, 8);
+    if (rows_counted) {
+        // stage 1a was done by the kernel that produced the grid (mdvc_morph_counted)
+    } else if (quad) {
         MDVC_DISPATCH_LQ(lq, (k_count_runs_q<LQ><<<row_grid, 256, 0, st>>>(bits, D, rowoff)));
+        MDVC_LAUNCH_CHECK();
     } else {
         MDVC_DISPATCH_G(g, (k_count_runs<G><<<row_grid, 256, 0, st>>>(bits, D, rowoff)));
+        MDVC_LAUNCH_CHECK();
     }
-    MDVC_LAUNCH_CHECK();
     rc = mdvc_exclusive_scan<uint32_t>(rowoff, rowoff, nullptr, (uint32_t)D.rows, at<uint32_t>(ws, L.tile32),
                                        rowoff + D.rows, nullptr, st);
     if (rc) return rc;

@@ -153,9 +153,16 @@ class FramePlan:
     def _args(self):
         return _ptr(self.ws), ctypes.c_size_t(self.nbytes), ctypes.byref(self.caps)
 
-    def label(self, bits: BitGrid):
+    def label(self, bits: BitGrid, rows_counted: bool = False):
+        """Stage 1 (runs, linking, numbering).  ``rows_counted``: the per-row run counts are already in
+        ``row_counts_ptr()`` (written by ``mdvc_morph_counted``), so the first pass over the grid is skipped."""
         X, Y, Z = self.shape
-        check(self.lib.mdvc_frame_label(_ptr(bits.words), X, Y, Z, bits.pitch, *self._args(), _stream()), "mdvc_frame_label")
+        check(self.lib.mdvc_frame_label_counted(_ptr(bits.words), X, Y, Z, bits.pitch, *self._args(), int(rows_counted),
+                                                _stream()), "mdvc_frame_label_counted")
+
+    def row_counts_ptr(self) -> int:
+        X, Y, Z = self.shape
+        return self.lib.mdvc_frame_row_counts_ptr(_ptr(self.ws), X, Y, Z, ctypes.byref(self.caps))
 
     def pairs(self, bits: BitGrid, periodic=True):
         X, Y, Z = self.shape

@@ -63,6 +63,7 @@ class FramePipeline:
         self.ev_stage1 = torch.cuda.Event()
         self.expand_events = []                                   # (start, end) of every dense write
         self._bits = None
+        self._rows_counted = False
 
     # ---------------------------------------------------------------------------------------
     def _alloc_host(self):
@@ -91,18 +92,22 @@ class FramePipeline:
         """bin + morph; returns the final bit grid (device)."""
         self.bits_a.words.zero_()
         dev.bin_atoms(positions_dev, self.T, self.invT, self.nbox, self.bits_a)
+        self._rows_counted = False
         if not self.ops:
             return self.bits_a
         X, Y, Z = self.shape
-        rc = self.lib.mdvc_morph(self.bits_a.words.data_ptr(), self.bits_b.words.data_ptr(),
-                                 self.bits_tmp.words.data_ptr() if self.bits_tmp is not None else None,
-                                 X, Y, Z, self.bits_a.pitch, self.ops.encode(),
-                                 ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
-        _lib.check(rc, "mdvc_morph")
+        counted = ctypes.c_int(0)                  # the fused closing also counts the runs per row of its result
+        rc = self.lib.mdvc_morph_counted(self.bits_a.words.data_ptr(), self.bits_b.words.data_ptr(),
+                                         self.bits_tmp.words.data_ptr() if self.bits_tmp is not None else None,
+                                         X, Y, Z, self.bits_a.pitch, self.ops.encode(),
+                                         ctypes.c_void_p(self.plan.row_counts_ptr()), ctypes.byref(counted),
+                                         ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+        _lib.check(rc, "mdvc_morph_counted")
+        self._rows_counted = bool(counted.value)
         return self.bits_b
 
-    def _enqueue_stage1(self, bits: dev.BitGrid):
-        self.plan.label(bits)
+    def _enqueue_stage1(self, bits: dev.BitGrid, rows_counted: bool = False):
+        self.plan.label(bits, rows_counted)
         self.plan.pairs(bits, self.periodic)
         # small results: four async copies into pinned memory, waited for in finish()
         self.h_header.copy_(self.d_header, non_blocking=True)
@@ -124,7 +129,7 @@ class FramePipeline:
                 self.pos_dev[:n].copy_(host_positions, non_blocking=True)
                 positions_dev = self.pos_dev[:n]
             self._bits = self.voxelize(positions_dev)
-            self._enqueue_stage1(self._bits)
+            self._enqueue_stage1(self._bits, self._rows_counted)
 
     def finish(self) -> FrameOutput:
         """Wait for the small results, run the host graph stage, upload the LUT, enqueue the dense write."""

@@ -86,6 +86,39 @@ def test_fused_closing_equals_two_steps(dev, monkeypatch):
     assert np.array_equal(two.to_bool().cpu().numpy(), vo.morph(g, "de"))
 
 
+@pytest.mark.parametrize("shape", FUSED_CLOSE_SHAPES)
+def test_counted_morph_leaves_the_runs_per_row(dev, shape):
+    """mdvc_morph_counted: the fused kernel also counts the z-runs of every row of its result (stage 1a of the
+    labelling); mdvc_frame_label_counted on those counts gives the same labels as the plain call."""
+    import ctypes
+    from mdvcontainment_b200 import _lib
+    lib = _lib.load()
+    rng = np.random.default_rng(7 + sum(shape))
+    g = rng.random(shape) < 0.3
+    X, Y, Z = shape
+    for ops in ("de", "edde", "d"):
+        want = vo.morph(g, ops)
+        src = dev.BitGrid.from_bool(g)
+        out, tmp = dev.BitGrid(shape), dev.BitGrid(shape)
+        plan = dev.FramePlan(shape, max_runs=X * Y * Z + 16, max_labels=X * Y * Z + 16)
+        counted = ctypes.c_int(-1)
+        rc = lib.mdvc_morph_counted(src.words.data_ptr(), out.words.data_ptr(), tmp.words.data_ptr(), X, Y, Z, src.pitch,
+                                    ops.encode(), ctypes.c_void_p(plan.row_counts_ptr()), ctypes.byref(counted),
+                                    ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+        assert rc == 0 and counted.value == (1 if len(ops) % 2 == 0 else 0)
+        assert np.array_equal(out.to_bool().cpu().numpy(), want)
+        if counted.value:
+            runs = 1 + (want[:, :, 1:] != want[:, :, :-1]).sum(axis=2)
+            got = plan._view(plan.lib.mdvc_frame_row_counts_ptr, torch.int32, X * Y).cpu().numpy().reshape(X, Y)
+            assert np.array_equal(got, runs)
+        plan.label(out, rows_counted=bool(counted.value))
+        plan.header = plan.read_header()
+        assert plan.header.flags == 0
+        labels = torch.empty(shape, dtype=torch.int32, device="cuda")
+        plan.expand(out, labels, None)
+        assert np.array_equal(labels.cpu().numpy(), vo.label_3d_grid(want).astype(np.int32))
+
+
 def test_morph_rejects_unknown_op(dev):
     from mdvcontainment_b200._lib import MdvcError
     with pytest.raises(MdvcError):
