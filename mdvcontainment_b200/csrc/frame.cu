@@ -44,7 +44,7 @@ struct Dims {
 };
 
 struct Layout {
-    size_t hdr, rowoff, tile32, tile64, runstart, parent, lab, runcomp, scan64, vol, lparent, lut, lscan,
+    size_t hdr, rowoff, rowpol, tile32, tile64, runstart, parent, lab, runcomp, scan64, vol, lparent, lut, lscan,
         ccount, cset, bset, ckeys, bkeys, crows, brows, total;
 };
 
@@ -64,6 +64,7 @@ static Layout make_layout(long long rows, const mdvc_frame_caps *c) {
     if (NL > scan_cap) scan_cap = NL;
     L.hdr = take(sizeof(Hdr));
     L.rowoff = take(((size_t)rows + 2) * 4);
+    L.rowpol = take((size_t)rows + 4);                 // value of the first voxel of every row (1 byte each)
     L.tile32 = take(mdvc_scan_scratch_elems((uint32_t)scan_cap) * 4);
     L.tile64 = take(mdvc_scan_scratch_elems((uint32_t)scan_cap) * 8);
     L.runstart = take((M + 1) * 4);
@@ -241,7 +242,7 @@ __global__ void k_after_row_scan(Hdr *h, const uint32_t *rowoff, long long rows,
 template <int G>
 __global__ void __launch_bounds__(256)
 k_fill_runs(const uint32_t *__restrict__ bits, Dims D, const Hdr *__restrict__ h, const uint32_t *__restrict__ rowoff,
-            uint32_t *__restrict__ runstart, uint32_t *__restrict__ parent) {
+            uint32_t *__restrict__ runstart, uint32_t *__restrict__ parent, uint8_t *__restrict__ rowpol) {
     if (h->run_eff == 0) return;
     const int lane = threadIdx.x & 31, gl = lane & (G - 1), gi = lane / G;
     constexpr int GPW = 32 / G;
@@ -265,6 +266,7 @@ k_fill_runs(const uint32_t *__restrict__ bits, Dims D, const Hdr *__restrict__ h
                 long long row = rb + u * GPW + gi;
                 RowWalker<G> rw; rw.begin();
                 uint32_t S = rw.starts_single(B[u], gl, D.Z, gl);
+                if (row < D.rows && gl == 0) rowpol[row] = (uint8_t)(B[u] & 1u);
                 uint32_t id = base[u] + rw.exclusive(S, gl);
                 uint32_t lin0 = (uint32_t)(row * D.Z) + (uint32_t)(gl << 5);
                 if (row >= D.rows) S = 0;
@@ -289,6 +291,7 @@ k_fill_runs(const uint32_t *__restrict__ bits, Dims D, const Hdr *__restrict__ h
             int w = c * G + gl;
             uint32_t B = (rv && w < D.nw) ? (rp[w] & mdvc_valid_mask(w, D.Z)) : 0u;
             uint32_t S = rw.starts(B, w, D.Z, gl);
+            if (rv && w == 0) rowpol[row] = (uint8_t)(B & 1u);
             uint32_t ex = rw.exclusive(S, gl);
             uint32_t id = base + ex;
             uint32_t lin0 = (uint32_t)(row * D.Z) + (uint32_t)(w << 5);
@@ -359,7 +362,7 @@ __device__ __forceinline__ uint32_t emit_starts(uint32_t S, uint32_t id, uint32_
 template <int LQ>
 __global__ void __launch_bounds__(256)
 k_fill_runs_q(const uint32_t *__restrict__ bits, Dims D, const Hdr *__restrict__ h, const uint32_t *__restrict__ rowoff,
-              uint32_t *__restrict__ runstart, uint32_t *__restrict__ parent) {
+              uint32_t *__restrict__ runstart, uint32_t *__restrict__ parent, uint8_t *__restrict__ rowpol) {
     if (h->run_eff == 0) return;
     constexpr int RPW = 32 / LQ, U = 4;
     const int lane = threadIdx.x & 31, ql = lane & (LQ - 1), gi = lane / LQ;
@@ -390,6 +393,7 @@ k_fill_runs_q(const uint32_t *__restrict__ bits, Dims D, const Hdr *__restrict__
                 if (ql >= o) inc += t;
             }
             if (row >= D.rows) continue;
+            if (ql == 0) rowpol[row] = (uint8_t)(B[u].x & 1u);
             uint32_t id = base[u] + inc - cnt;
             const uint32_t lin0 = (uint32_t)(row * D.Z) + (uint32_t)(ql << 7);
             id = emit_starts(q.s0, id, lin0, runstart, parent);
@@ -639,7 +643,7 @@ __device__ __forceinline__ bool rows_mirror(const uint32_t *tz, uint32_t a0, uin
 
 __global__ void __launch_bounds__(TILE_THREADS, 8)
 k_strip_link(const uint32_t *__restrict__ bits, Dims D, Hdr *h, const uint32_t *__restrict__ rowoff,
-             const uint32_t *__restrict__ runstart, uint32_t *parent, uint32_t *rootlist) {
+             const uint8_t *__restrict__ rowpol, const uint32_t *__restrict__ runstart, uint32_t *parent, uint32_t *rootlist) {
     __shared__ uint32_t srow[STRIP_TY + 1];
     __shared__ uint32_t spol[STRIP_TY];
     __shared__ uint8_t smir[STRIP_TY], stop[STRIP_TY];
@@ -657,7 +661,7 @@ k_strip_link(const uint32_t *__restrict__ bits, Dims D, Hdr *h, const uint32_t *
         __syncthreads();                                   // previous strip fully consumed
         for (int t = threadIdx.x; t <= ny; t += blockDim.x) {
             srow[t] = rowoff[r0 + t];
-            if (t < ny) spol[t] = bits[(size_t)(r0 + t) * D.pitch] & 1u;
+            if (t < ny) spol[t] = rowpol[r0 + t];
         }
         __syncthreads();
         const uint32_t gbase = srow[0], nloc = srow[ny] - gbase;
@@ -781,7 +785,7 @@ k_flatten_list(const Hdr *__restrict__ h, const uint32_t *__restrict__ list, uin
 // in shared memory; only new (root,root) pairs of the CTA reach the global union.
 __global__ void __launch_bounds__(TILE_THREADS, 8)
 k_tile_link_x(const uint32_t *__restrict__ bits, Dims D, const Hdr *__restrict__ h, const uint32_t *__restrict__ rowoff,
-              const uint32_t *__restrict__ runstart, uint32_t *parent, int s, int radix) {
+              const uint8_t *__restrict__ rowpol, const uint32_t *__restrict__ runstart, uint32_t *parent, int s, int radix) {
     __shared__ uint32_t orow[STRIP_TY + 1], brow[STRIP_TY + 3];
     __shared__ uint32_t opol[STRIP_TY], bpol[STRIP_TY + 2];
     __shared__ uint32_t tz[STRIP_CAP], troot[STRIP_CAP];       // own runs first, then the other plane's
@@ -803,11 +807,11 @@ k_tile_link_x(const uint32_t *__restrict__ bits, Dims D, const Hdr *__restrict__
         __syncthreads();
         for (int t = threadIdx.x; t <= ny; t += blockDim.x) {
             orow[t] = rowoff[r0 + t];
-            if (t < ny) opol[t] = bits[(size_t)(r0 + t) * D.pitch] & 1u;
+            if (t < ny) opol[t] = rowpol[r0 + t];
         }
         for (int t = threadIdx.x; t <= nb; t += blockDim.x) {
             brow[t] = rowoff[q0 + t];
-            if (t < nb) bpol[t] = bits[(size_t)(q0 + t) * D.pitch] & 1u;
+            if (t < nb) bpol[t] = rowpol[q0 + t];
         }
         __syncthreads();
         const uint32_t go = orow[0], no = orow[ny] - go, gb = brow[0], nbr = brow[nb] - gb;
@@ -1168,7 +1172,7 @@ __device__ __noinline__ void pairs_one_run_global(const uint32_t *__restrict__ b
 #define PT_CAP 3072
 __global__ void __launch_bounds__(2 * PT_TY, 4)
 k_tile_pairs(const uint32_t *__restrict__ bits, Dims D, Hdr *h, const uint32_t *__restrict__ rowoff,
-             const uint32_t *__restrict__ runstart, const int32_t *__restrict__ lab,
+             const uint8_t *__restrict__ rowpol, const uint32_t *__restrict__ runstart, const int32_t *__restrict__ lab,
              unsigned long long *cset, uint32_t c_slots, unsigned long long *bset, uint32_t b_slots, int periodic) {
     __shared__ uint32_t srow[PT_SLOTS], sgb[PT_SLOTS], scnt[PT_SLOTS], soff[PT_SLOTS + 1], spol[PT_SLOTS];
     __shared__ int ssy[PT_SLOTS];
@@ -1200,7 +1204,7 @@ k_tile_pairs(const uint32_t *__restrict__ bits, Dims D, Hdr *h, const uint32_t *
             uint32_t rg = (uint32_t)xx * D.Y + yy;
             uint32_t g0 = valid ? rowoff[rg] : 0u, g1 = valid ? rowoff[rg + 1] : 0u;
             srow[t] = rg; sgb[t] = g0; scnt[t] = g1 - g0; ssy[t] = sy;
-            spol[t] = valid ? (bits[(size_t)rg * D.pitch] & 1u) : 0u;
+            spol[t] = valid ? rowpol[rg] : 0u;
         }
         __syncthreads();
         if (threadIdx.x < 32) {                              // exclusive scan of the slot counts by one warp
@@ -1721,6 +1725,7 @@ static int frame_label(const uint32_t *bits, int X, int Y, int Z, int pitch, voi
     cudaStream_t st = (cudaStream_t)stream;
     Hdr *h = at<Hdr>(ws, L.hdr);
     uint32_t *rowoff = at<uint32_t>(ws, L.rowoff);
+    uint8_t *rowpol = at<uint8_t>(ws, L.rowpol);
     uint32_t *runstart = at<uint32_t>(ws, L.runstart);
     uint32_t *parent = at<uint32_t>(ws, L.parent);
     int32_t *lab = at<int32_t>(ws, L.lab);
@@ -1752,9 +1757,9 @@ static int frame_label(const uint32_t *bits, int X, int Y, int Z, int pitch, voi
     k_after_row_scan<<<1, 1, 0, st>>>(h, rowoff, D.rows, caps->max_runs, runstart, D.N);
     MDVC_LAUNCH_CHECK();
     if (quad) {
-        MDVC_DISPATCH_LQ(lq, (k_fill_runs_q<LQ><<<row_grid, 256, 0, st>>>(bits, D, h, rowoff, runstart, parent)));
+        MDVC_DISPATCH_LQ(lq, (k_fill_runs_q<LQ><<<row_grid, 256, 0, st>>>(bits, D, h, rowoff, runstart, parent, rowpol)));
     } else {
-        MDVC_DISPATCH_G(g, (k_fill_runs<G><<<row_grid, 256, 0, st>>>(bits, D, h, rowoff, runstart, parent)));
+        MDVC_DISPATCH_G(g, (k_fill_runs<G><<<row_grid, 256, 0, st>>>(bits, D, h, rowoff, runstart, parent, rowpol)));
     }
     MDVC_LAUNCH_CHECK();
     unsigned run_grid = mdvc_grid(caps->max_runs, 256, 8);
@@ -1766,7 +1771,7 @@ static int frame_label(const uint32_t *bits, int X, int Y, int Z, int pitch, voi
         long long n_strips = (long long)D.X * spp;
         unsigned sgrid = (unsigned)(n_strips < (long long)mdvc_num_sms() * mdvc_cap_ctas(32) ? n_strips : (long long)mdvc_num_sms() * mdvc_cap_ctas(32));
         unsigned lgrid = mdvc_grid(caps->max_runs, 256, 4);
-        k_strip_link<<<sgrid, TILE_THREADS, 0, st>>>(bits, D, h, rowoff, runstart, parent, rootlist);
+        k_strip_link<<<sgrid, TILE_THREADS, 0, st>>>(bits, D, h, rowoff, rowpol, runstart, parent, rootlist);
         MDVC_LAUNCH_CHECK();
         if (D.Y > STRIP_TY) {
             long long items = (long long)D.X * ((D.Y - 1) / STRIP_TY);
@@ -1778,7 +1783,7 @@ static int frame_label(const uint32_t *bits, int X, int Y, int Z, int pitch, voi
         for (long long s = 1; s < D.X; s *= LINK_RADIX) {
             long long tiles = (long long)((D.X - 1) / s) * spp;
             unsigned tgrid = (unsigned)(tiles < (long long)mdvc_num_sms() * mdvc_cap_ctas(32) ? tiles : (long long)mdvc_num_sms() * mdvc_cap_ctas(32));
-            k_tile_link_x<<<tgrid, TILE_THREADS, 0, st>>>(bits, D, h, rowoff, runstart, parent, (int)s, LINK_RADIX);
+            k_tile_link_x<<<tgrid, TILE_THREADS, 0, st>>>(bits, D, h, rowoff, rowpol, runstart, parent, (int)s, LINK_RADIX);
             MDVC_LAUNCH_CHECK();
             k_flatten_list<<<lgrid, 256, 0, st>>>(h, rootlist, parent);
             MDVC_LAUNCH_CHECK();
@@ -1813,7 +1818,7 @@ extern "C" int mdvc_frame_pairs(const uint32_t *bits, int X, int Y, int Z, int p
     {
         long long tiles = (long long)D.X * ((D.Y + PT_TY - 1) / PT_TY);
         unsigned tgrid = (unsigned)(tiles < (long long)mdvc_num_sms() * mdvc_cap_ctas(32) ? tiles : (long long)mdvc_num_sms() * mdvc_cap_ctas(32));
-        k_tile_pairs<<<tgrid, 2 * PT_TY, 0, st>>>(bits, D, h, at<uint32_t>(ws, L.rowoff), at<uint32_t>(ws, L.runstart),
+        k_tile_pairs<<<tgrid, 2 * PT_TY, 0, st>>>(bits, D, h, at<uint32_t>(ws, L.rowoff), at<uint8_t>(ws, L.rowpol), at<uint32_t>(ws, L.runstart),
                                             at<int32_t>(ws, L.lab), cset, caps->contact_slots, bset,
                                             caps->bridge_slots, periodic);
         MDVC_LAUNCH_CHECK();
