@@ -1817,7 +1817,9 @@ extern "C" int mdvc_frame_pairs(const uint32_t *bits, int X, int Y, int Z, int p
     MDVC_CUDA_CHECK(cudaMemsetAsync(&h->n_contacts, 0, 2 * sizeof(uint32_t), st));
     {
         long long tiles = (long long)D.X * ((D.Y + PT_TY - 1) / PT_TY);
-        unsigned tgrid = (unsigned)(tiles < (long long)mdvc_num_sms() * mdvc_cap_ctas(32) ? tiles : (long long)mdvc_num_sms() * mdvc_cap_ctas(32));
+        // four CTAs are resident per SM; 16 per SM keeps the tail short while the per-CTA set-up (clearing the two
+        // key caches) is paid four times less often than with one CTA per tile (measured: 0.219 -> 0.198 ms)
+        unsigned tgrid = (unsigned)(tiles < (long long)mdvc_num_sms() * mdvc_cap_ctas(16) ? tiles : (long long)mdvc_num_sms() * mdvc_cap_ctas(16));
         k_tile_pairs<<<tgrid, 2 * PT_TY, 0, st>>>(bits, D, h, at<uint32_t>(ws, L.rowoff), at<uint8_t>(ws, L.rowpol), at<uint32_t>(ws, L.runstart),
                                             at<int32_t>(ws, L.lab), cset, caps->contact_slots, bset,
                                             caps->bridge_slots, periodic);
