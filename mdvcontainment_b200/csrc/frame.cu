@@ -1268,17 +1268,33 @@ k_tile_pairs(const uint32_t *__restrict__ bits, Dims D, Hdr *h, const uint32_t *
                 // reaches its runs k-1 and k+1, whose labels are this row's own neighbours' labels, so every
                 // cross-row contact is already among the in-row contacts emitted below.  True for most row
                 // pairs of smooth structures; anything else takes the walk.
+                // All candidate rows are checked in one sweep over this row's starts (each own start is loaded once
+                // for the up to three neighbours, each neighbour start once: every row starts at z = 0).
+                const uint32_t n = re0 - rb0;
+                bool mir[4];
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
                     const int ns = nsl[q];
-                    if (q < q_lo || q >= q_hi) { pj[q] = pe[q]; continue; }
-                    if (pj[q] == pe[q] || ((q == 0 ? 0 : sx_other) | ssy[ns])) continue;
-                    const uint32_t n = re0 - rb0, pb = pj[q];
-                    bool mirror = (pe[q] - pb) == n && spol[ns] == pol0;
-                    for (uint32_t k = 0; mirror && k < n; ++k) {
-                        mirror = k + 1 >= n || (tz[pb + k] < tz[rb0 + k + 1] && tz[rb0 + k] < tz[pb + k + 1]);
+                    if (q < q_lo || q >= q_hi) { pj[q] = pe[q]; mir[q] = false; continue; }
+                    mir[q] = pj[q] != pe[q] && !((q == 0 ? 0 : sx_other) | ssy[ns]) && (pe[q] - pj[q]) == n && spol[ns] == pol0;
+                }
+                if (mir[0] | mir[1] | mir[2] | mir[3]) {
+                    uint32_t a_k = 0, b_k[4] = {0, 0, 0, 0};
+                    for (uint32_t k = 0; k + 1 < n; ++k) {
+                        const uint32_t a_k1 = tz[rb0 + k + 1];
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            if (!mir[q]) continue;
+                            const uint32_t b_k1 = tz[pj[q] + k + 1];
+                            mir[q] = b_k[q] < a_k1 && a_k < b_k1;
+                            b_k[q] = b_k1;
+                        }
+                        a_k = a_k1;
+                        if (!(mir[0] | mir[1] | mir[2] | mir[3])) break;
                     }
-                    if (mirror) pj[q] = pe[q];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q)
+                        if (mir[q]) pj[q] = pe[q];
                 }
                 for (uint32_t k = rb0; k < re0; ++k) {
                     const int a = (int)tz[k];
