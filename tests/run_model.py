@@ -5,7 +5,10 @@ numbering, the "walk the runs of each raster-predecessor row that intersect [a-1
 rule of the link and pair kernels, the two-directional z-face enumeration of k_tile_pairs, the
 min-root union-find numbering and the periodic-component numbering of
 k_label_lut -- so the *rules* can be validated against the oracle on the CPU box, where no
-kernel can run.  It is not a fallback: the product never imports it.
+kernel can run.  ``shortcuts=True`` additionally applies the three rules the kernels use to skip work:
+mirror rows link run m to run m without a search (k_strip_link / k_tile_link_x), mirror rows emit no
+cross-row contacts, and contacts come from voxel-on-voxel overlaps only (k_tile_pairs).
+It is not a fallback: the product never imports it.
 """
 import numpy as np
 
@@ -50,7 +53,18 @@ def run_at(runstart, rowoff, Z, row, z):
 BACKWARD = ((-1, -1), (-1, 0), (-1, 1), (0, -1))     # raster-order predecessors among the 8 neighbour rows
 
 
-def label_runs(grid):
+def rows_mirror(runstart, rowoff, flat, Z, r1, r2):
+    """Same run count, same first value, interleaving starts (csrc/frame.cu: rows_mirror)."""
+    a0, a1, b0, b1 = rowoff[r1], rowoff[r1 + 1], rowoff[r2], rowoff[r2 + 1]
+    n = a1 - a0
+    if b1 - b0 != n or flat[r1 * Z] != flat[r2 * Z]:
+        return False
+    za = [int(runstart[a0 + m]) - r1 * Z for m in range(n)]
+    zb = [int(runstart[b0 + m]) - r2 * Z for m in range(n)]
+    return all(zb[m] < za[m + 1] and za[m] < zb[m + 1] for m in range(n - 1))
+
+
+def label_runs(grid, shortcuts=False):
     X, Y, Z = grid.shape
     flat = grid.reshape(-1)
     runstart, rowoff = runs_of(grid)
@@ -65,6 +79,9 @@ def label_runs(grid):
             if nx < 0 or ny < 0 or ny >= Y:
                 continue
             r2 = nx * Y + ny
+            if shortcuts and rows_mirror(runstart, rowoff, flat, Z, r, r2):
+                uf.union(i, rowoff[r2] + (i - rowoff[r]))      # the partner of run m is run m
+                continue
             j = run_at(runstart, rowoff, Z, r2, lo)
             if flat[r2 * Z + lo] != v:
                 j += 1
@@ -92,7 +109,7 @@ def expand(grid, runstart, lab):
     return out.reshape(grid.shape)
 
 
-def pairs(grid, runstart, rowoff, lab, periodic=True):
+def pairs(grid, runstart, rowoff, lab, periodic=True, shortcuts=False):
     X, Y, Z = grid.shape
     flat = grid.reshape(-1)
     bit = lambda row, z: flat[row * Z + z]
@@ -127,6 +144,17 @@ def pairs(grid, runstart, rowoff, lab, periodic=True):
             if wraps and not periodic:
                 continue
             r2 = nx * Y + ny
+            if shortcuts and not wraps:
+                # mirror rows: every cross-row contact is one of the in-row contacts; otherwise only the runs of
+                # the other value that overlap [a, b] voxel on voxel (a diagonal touch is an in-row contact of r2)
+                if rows_mirror(runstart, rowoff, flat, Z, r, r2):
+                    continue
+                j = run_at(runstart, rowoff, Z, r2, a)
+                if flat[r2 * Z + a] == v:
+                    j += 1
+                while j < rowoff[r2 + 1] and runstart[j] <= r2 * Z + b:
+                    emit_c(la, int(lab[j])); j += 2
+                continue
             j = run_at(runstart, rowoff, Z, r2, lo)
             if not wraps:
                 if flat[r2 * Z + lo] == v:
