@@ -82,9 +82,9 @@ class DeviceMapping:
     # --- compatibility with the reference's mapping dict ---------------------------------------
     def _as_dict(self):
         if self._dict is None:
-            vox = self.voxels_dev.cpu().numpy()
-            order = self.csr.order.cpu().numpy()
-            keys = self.csr.keys.cpu().numpy()
+            vox = dev.to_numpy(self.voxels_dev)
+            order = dev.to_numpy(self.csr.order)
+            keys = dev.to_numpy(self.csr.keys)
             v2a = {}
             if len(order):
                 brk = np.flatnonzero(keys[1:] != keys[:-1]) + 1
@@ -118,7 +118,7 @@ def voxelize_on_device(atomgroup, resolution, max_offset=0.05, want_mapping=True
         positions_dev = torch.from_numpy(host).cuda(non_blocking=True)
     bits = dev.BitGrid(shape)
     vox, newpos = dev.bin_atoms(positions_dev, T, invT, nbox, bits, want_voxels=want_mapping, want_positions=True)
-    atomgroup.positions = newpos.cpu().numpy()
+    atomgroup.positions = dev.to_numpy(newpos)
     return bits, vox, newpos
 
 
@@ -128,7 +128,7 @@ def voxelize_on_device(atomgroup, resolution, max_offset=0.05, want_mapping=True
 def create_voxels(atomgroup, resolution, max_offset=0.05, return_mapping=True):
     """atomgroup_to_voxels.py:168-204 -> (bool ndarray [X,Y,Z], mapping | None)."""
     bits, vox, _ = voxelize_on_device(atomgroup, resolution, max_offset, want_mapping=return_mapping)
-    explicit = bits.to_bool().cpu().numpy()
+    explicit = dev.to_numpy(bits.to_bool())
     if return_mapping:
         return explicit, DeviceMapping(vox, atomgroup.ix, bits.shape)
     return explicit, None
@@ -152,7 +152,7 @@ def morph_voxels(voxels, morph_str='de'):
     voxels = np.asarray(voxels)
     if not morph_str:
         return voxels
-    return dev.morph(dev.BitGrid.from_bool(voxels), morph_str).to_bool().cpu().numpy()
+    return dev.to_numpy(dev.morph(dev.BitGrid.from_bool(voxels), morph_str).to_bool())
 
 
 def dilate_voxels(voxels):

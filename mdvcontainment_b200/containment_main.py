@@ -109,8 +109,8 @@ def calc_containment_graph(boolean_grid, verbose=False, write_structures=False, 
     if verbose:
         print(f'Unique labels in labeled_grid: {nonp_unique_labels}')
     if write_structures:
-        _write_grid('input.gro', bits.to_bool().cpu().numpy())
-        _write_grid('nonp_labels.gro', fr.labels().cpu().numpy())
+        _write_grid('input.gro', dev.to_numpy(bits.to_bool()))
+        _write_grid('nonp_labels.gro', dev.to_numpy(fr.labels()))
 
     t0 = time.perf_counter()
     if not slab:
@@ -142,7 +142,7 @@ def calc_containment_graph(boolean_grid, verbose=False, write_structures=False, 
         component_contact_graph = nx.Graph(sol["label_graph"].to_networkx())
         unique_components = nonp_unique_labels
     if write_structures:
-        _write_grid('components.gro', fr.components_dev.cpu().numpy())
+        _write_grid('components.gro', dev.to_numpy(fr.components_dev))
     if draw_graphs:
         print('=== NON PERIODIC LABEL CONTACT GRAPH ===')
         _draw_graph(sol["label_graph"].to_networkx())
@@ -153,7 +153,7 @@ def calc_containment_graph(boolean_grid, verbose=False, write_structures=False, 
     fr.timings["host_graph_s"] = time.perf_counter() - t0
     if _want_frame:
         return containment_graph, component_contact_graph, fr, component_ranks, sol["label_graph"]
-    return (containment_graph, component_contact_graph, fr.components_dev.cpu().numpy(), component_ranks,
+    return (containment_graph, component_contact_graph, dev.to_numpy(fr.components_dev), component_ranks,
             sol["label_graph"].to_networkx())
 
 
@@ -322,7 +322,7 @@ class VoxelContainmentBase:
         lo, n = self._member_span()
         _, mask = dev.grid_select(self._base._frame.components_dev, self._resolve_nodes_to_original(nodes), lo, n,
                                   want_mask=True, want_positions=False)
-        return mask.cpu().numpy()
+        return dev.to_numpy(mask)
 
     def get_voxel_positions(self, nodes):
         """np.where of the mask as an (M,3) int64 array in C-order (containment_main.py:370-378)."""
@@ -393,12 +393,12 @@ class VoxelContainment(VoxelContainmentBase):
 
     def _get_grid(self):
         if isinstance(self._grid, dev.BitGrid):
-            return self._grid.to_bool().cpu().numpy()
+            return dev.to_numpy(self._grid.to_bool())
         return self._grid
 
     def _get_components_grid(self):
         if self._components_grid is None:
-            self._components_grid = self._frame.components_dev.cpu().numpy()
+            self._components_grid = dev.to_numpy(self._frame.components_dev)
         return self._components_grid
 
     def _get_label_graph(self):

@@ -72,7 +72,7 @@ class ContainmentBase:
         """NumPy bool array [X,Y,Z] (unpacked from the device bit grid on first access)."""
         b = self._base
         if b._boolean_grid is None:
-            b._boolean_grid = b._bits.to_bool().cpu().numpy()
+            b._boolean_grid = dev.to_numpy(b._bits.to_bool())
         return b._boolean_grid
 
     @property
@@ -124,7 +124,7 @@ class ContainmentBase:
             raise ValueError("set_betafactors requires no_mapping='False'.")
         vc = self.voxel_containment
         mapping: DeviceMapping = self.voxel2atom
-        comp = dev.atom_components(mapping.voxels_dev, vc.components_grid_device).cpu().numpy()
+        comp = dev.to_numpy(dev.atom_components(mapping.voxels_dev, vc.components_grid_device))
         betafactors = np.zeros(len(self.universe.atoms))
         is_view = isinstance(self, ContainmentView)
         if is_view:

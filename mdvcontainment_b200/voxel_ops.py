@@ -19,7 +19,7 @@ def label_3d_grid(grid):
     plan, _ = dev.label_with_retry(bits, want_pairs=False)
     labels = torch.empty(bits.shape, dtype=torch.int32, device="cuda")
     plan.expand(bits, labels, None)
-    return labels.cpu().numpy()
+    return dev.to_numpy(labels)
 
 
 def find_label_contacts(labeled_grid):
@@ -50,4 +50,4 @@ def create_components_grid(nonp_labeled_grid, component2labels):
     for comp, ls in component2labels.items():
         for l in ls:
             lut[int(l) - lo] = comp
-    return dev.grid_relabel(L, lut, lo).cpu().numpy()
+    return dev.to_numpy(dev.grid_relabel(L, lut, lo))

@@ -43,6 +43,20 @@ def test_pack_unpack_popcount(dev):
             assert not (words[:, :, w] & ~mask).any()
 
 
+def test_to_numpy_staged_copy(dev, monkeypatch):
+    """Large device tensors reach NumPy through two pinned staging buffers; same bytes as .cpu().numpy()."""
+    monkeypatch.setattr(dev, "_PINNED_BYTES", 1 << 20)
+    monkeypatch.setattr(dev, "_PINNED", [])
+    g = torch.Generator(device="cuda").manual_seed(3)
+    a = torch.randint(-2 ** 31, 2 ** 31 - 1, (130, 77, 301), dtype=torch.int32, device="cuda", generator=g)   # 12 MB, ragged last chunk
+    for t in (a, a > 0, a.to(torch.int64), a.float(), a[:, ::2, :], a.permute(2, 0, 1)):
+        got = dev.to_numpy(t)
+        want = t.cpu().numpy()
+        assert got.dtype == want.dtype and got.shape == want.shape and np.array_equal(got, want)
+    small = a[:2]
+    assert np.array_equal(dev.to_numpy(small), small.cpu().numpy())
+
+
 # ------------------------------------------------------------------------------------------ A3/A4
 @pytest.mark.parametrize("ops", ["d", "e", "de", "ed", "dde", "deed", ""])
 def test_morph_matches_oracle(dev, ops):
