@@ -114,8 +114,7 @@ def voxelize_on_device(atomgroup, resolution, max_offset=0.05, want_mapping=True
     _check_resolution(atomgroup, resolution, max_offset, box, nbox)
     shape = tuple(int(v) for v in np.diagonal(nbox))
     if positions_dev is None:
-        host = np.ascontiguousarray(atomgroup.positions, dtype=np.float32)
-        positions_dev = torch.from_numpy(host).cuda(non_blocking=True)
+        positions_dev = dev.to_device(np.ascontiguousarray(atomgroup.positions, dtype=np.float32))
     bits = dev.BitGrid(shape)
     vox, newpos = dev.bin_atoms(positions_dev, T, invT, nbox, bits, want_voxels=want_mapping, want_positions=True)
     atomgroup.positions = dev.to_numpy(newpos)

@@ -58,8 +58,8 @@ class BitGrid:
         """Pack a bool/uint8 array (NumPy or torch, host or device)."""
         _require_cuda()
         if isinstance(grid, np.ndarray):
-            t = torch.from_numpy(np.ascontiguousarray(grid).view(np.uint8) if grid.dtype == np.bool_
-                                 else np.ascontiguousarray(grid != 0).view(np.uint8)).cuda()
+            t = to_device(np.ascontiguousarray(grid).view(np.uint8) if grid.dtype == np.bool_
+                          else np.ascontiguousarray(grid != 0).view(np.uint8))
         else:
             t = grid.to(device="cuda")
             t = (t if t.dtype == torch.bool else (t != 0)).contiguous().view(torch.uint8)
@@ -151,6 +151,34 @@ def to_numpy(t: torch.Tensor) -> np.ndarray:
     if as_bool:
         out = out.view(np.bool_)
     return out.reshape(tuple(t.shape))
+
+
+def to_device(a: np.ndarray, device="cuda") -> torch.Tensor:
+    """``torch.from_numpy(a).cuda()`` for large host arrays: pageable memory goes through the same two pinned
+    staging buffers (host copy of chunk i+1 overlaps the DMA of chunk i)."""
+    a = np.ascontiguousarray(a)
+    if a.nbytes < (8 << 20):
+        return torch.from_numpy(a).to(device)
+    as_bool = a.dtype == np.bool_
+    src = torch.from_numpy(a.view(np.uint8) if as_bool else a).reshape(-1)
+    if not _PINNED:
+        _PINNED.extend(torch.empty(_PINNED_BYTES, dtype=torch.uint8, pin_memory=True) for _ in range(2))
+    ce = _PINNED_BYTES // src.element_size()
+    out = torch.empty(src.numel(), dtype=src.dtype, device=device)
+    bufs = [b.view(src.dtype)[:ce] for b in _PINNED]
+    evs = [torch.cuda.Event(), torch.cuda.Event()]
+    n = src.numel()
+    for i, s0 in enumerate(range(0, n, ce)):
+        e0 = min(s0 + ce, n)
+        if i >= 2:
+            evs[i % 2].synchronize()                  # the DMA that last read this staging buffer is done
+        bufs[i % 2][:e0 - s0].copy_(src[s0:e0])
+        out[s0:e0].copy_(bufs[i % 2][:e0 - s0], non_blocking=True)
+        evs[i % 2].record()
+    for e in evs:
+        e.synchronize()                                # the staging buffers are shared: leave nothing in flight
+    out = out.view(torch.bool) if as_bool else out
+    return out.reshape(a.shape)
 
 
 # ---------------------------------------------------------------------------------------------
@@ -295,7 +323,7 @@ def label_with_retry(bits: BitGrid, plan: FramePlan | None = None, periodic=True
 # ---------------------------------------------------------------------------------------------
 def _as_cuda_i32(grid):
     if isinstance(grid, np.ndarray):
-        return torch.from_numpy(np.ascontiguousarray(grid, dtype=np.int32)).cuda()
+        return to_device(np.ascontiguousarray(grid, dtype=np.int32))
     return grid.to(device="cuda", dtype=torch.int32).contiguous()
 
 

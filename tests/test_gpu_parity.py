@@ -55,6 +55,9 @@ def test_to_numpy_staged_copy(dev, monkeypatch):
         assert got.dtype == want.dtype and got.shape == want.shape and np.array_equal(got, want)
     small = a[:2]
     assert np.array_equal(dev.to_numpy(small), small.cpu().numpy())
+    for h in (a.cpu().numpy(), (a > 0).cpu().numpy(), a.float().cpu().numpy(), a.cpu().numpy()[:, ::3, :]):
+        d = dev.to_device(h)
+        assert d.is_cuda and d.shape == h.shape and np.array_equal(d.cpu().numpy(), h)
 
 
 # ------------------------------------------------------------------------------------------ A3/A4

@@ -40,6 +40,9 @@ def main():
         timed(f"[{rep}] c.get_atomgroup_from_nodes([1], containment=True)", lambda: c.get_atomgroup_from_nodes([1], containment=True))
         timed(f"[{rep}] c.voxel_containment.components_grid (D2H of the int32 grid)", lambda: c.voxel_containment.components_grid)
         timed(f"[{rep}] str(c)", lambda: str(c))
+        grid = timed(f"[{rep}] c.boolean_grid (1 GB bool to NumPy)", lambda: c.boolean_grid)
+        from mdvcontainment_b200 import VoxelContainment
+        timed(f"[{rep}] VoxelContainment(numpy bool grid)", quiet(lambda: VoxelContainment(grid)))
         del c
         torch.cuda.empty_cache()
 
