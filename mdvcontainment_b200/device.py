@@ -283,21 +283,21 @@ class FramePlan:
 
     def contacts(self) -> np.ndarray:
         h = self.header
-        return self._view(self.lib.mdvc_frame_contacts_ptr, torch.int32, h.n_contacts, 2).cpu().numpy()
+        return to_numpy(self._view(self.lib.mdvc_frame_contacts_ptr, torch.int32, h.n_contacts, 2))
 
     def bridges(self) -> np.ndarray:
         h = self.header
         if h.n_bridges == 0:
             return np.array([], dtype=np.int32)
-        return self._view(self.lib.mdvc_frame_bridges_ptr, torch.int32, h.n_bridges, 5).cpu().numpy()
+        return to_numpy(self._view(self.lib.mdvc_frame_bridges_ptr, torch.int32, h.n_bridges, 5))
 
     def label_volumes(self) -> np.ndarray:
         h = self.header
-        return self._view(self.lib.mdvc_frame_label_volumes_ptr, torch.int64, h.n_true + h.n_false + 1).cpu().numpy()
+        return to_numpy(self._view(self.lib.mdvc_frame_label_volumes_ptr, torch.int64, h.n_true + h.n_false + 1))
 
     def lut(self) -> np.ndarray:
         h = self.header
-        return self._view(self.lib.mdvc_frame_lut_ptr, torch.int32, h.n_true + h.n_false + 1).cpu().numpy()
+        return to_numpy(self._view(self.lib.mdvc_frame_lut_ptr, torch.int32, h.n_true + h.n_false + 1))
 
     def component_counts(self) -> np.ndarray:
         h = self.header
@@ -396,7 +396,7 @@ def grid_select(grid: torch.Tensor, values, lo: int, n_values: int, want_mask=Fa
         if m:
             check(lib.mdvc_grid_select(_ptr(G), X, Y, Z, _ptr(member), int(lo), int(n_values), _ptr(scratch), _ptr(pos_t),
                                        m, _ptr(n_out), None, _stream()), "mdvc_grid_select")
-        pos = pos_t.cpu().numpy()
+        pos = to_numpy(pos_t)
     return pos, (mask.view(torch.bool) if mask is not None else None)
 
 
@@ -435,7 +435,7 @@ class AtomCSR:
         n_out = torch.zeros(1, dtype=torch.int64, device=grid.device)
         check(lib.mdvc_atom_select(_ptr(self.order), _ptr(self.keys), n, _ptr(grid), _ptr(member), int(lo), int(n_values),
                                    _ptr(atom_ix), _ptr(scratch), _ptr(out), _ptr(n_out), _stream()), "mdvc_atom_select")
-        return out[: int(n_out.item())].cpu().numpy()
+        return to_numpy(out[: int(n_out.item())])
 
     def gather_voxels(self, query_voxels, atom_ix: torch.Tensor | None) -> np.ndarray:
         """Atoms of an explicit voxel list (query order, then atom order) -> int64 atom indices."""
@@ -456,4 +456,4 @@ class AtomCSR:
             return np.array([], dtype=np.int64)
         out = torch.empty(total, dtype=torch.int64, device=dev_)
         check(lib.mdvc_atom_gather_voxels(*args, _ptr(out), total, _ptr(n_out), _stream()), "mdvc_atom_gather_voxels")
-        return out.cpu().numpy()
+        return to_numpy(out)

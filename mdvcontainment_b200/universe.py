@@ -35,10 +35,17 @@ class AtomGroup:
     def __init__(self, universe: "Universe", ix):
         self._u = universe
         self._ix = np.asarray(ix, dtype=np.int64).reshape(-1)
-        n = len(self._ix)
-        # contiguous index ranges (e.g. universe.atoms) read and write positions as slices, not gathers
-        self._range = (int(self._ix[0]), int(self._ix[0]) + n) if n and int(self._ix[-1]) - int(self._ix[0]) == n - 1 \
-            and bool(np.all(self._ix[1:] - self._ix[:-1] == 1)) else None
+        self._range_cache = False         # decided on first use: creating a 10 M atom group should not scan it
+
+    @property
+    def _range(self):
+        """(start, stop) when the group is a contiguous index range (e.g. universe.atoms): positions are then read
+        and written as slices instead of gathers."""
+        if self._range_cache is False:
+            ix, n = self._ix, len(self._ix)
+            self._range_cache = (int(ix[0]), int(ix[0]) + n) if n and int(ix[-1]) - int(ix[0]) == n - 1 \
+                and bool(np.all(ix[1:] - ix[:-1] == 1)) else None
+        return self._range_cache
 
     # --- identity -------------------------------------------------------
     @property
