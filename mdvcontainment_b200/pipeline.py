@@ -64,6 +64,7 @@ class FramePipeline:
         self.expand_events = []                                   # (start, end) of every dense write
         self._bits = None
         self._rows_counted = False
+        self._solved = {}                                         # memoised graph stage, see _finish
 
     # ---------------------------------------------------------------------------------------
     def _alloc_host(self):
@@ -170,16 +171,27 @@ class FramePipeline:
         uniq = np.concatenate([np.arange(-n_false, 0, dtype=np.int32), np.arange(1, n_true + 1, dtype=np.int32)])
 
         out = FrameOutput()
-        if self.periodic:
+        if not self.periodic:
+            raise NotImplementedError("slab frames go through VoxelContainment(slab=True)")
+        # The graph stage is a pure function of (label counts, contacts, bridges); consecutive trajectory frames almost
+        # always repeat them (same topology, different volumes), so the solution and the label -> component table are
+        # memoised (small LRU).  At 512^3 this host stage was most of a frame's wall-clock.
+        key = (n_true, n_false, contacts.tobytes(), bridges.tobytes())
+        hit = self._solved.get(key)
+        if hit is None:
             sol = hg.solve_periodic(uniq, contacts, bridges)
             c2l = sol["component2labels"]
             lut = np.zeros(nl, dtype=np.int32)
             for comp, labs in c2l.items():
                 lut[np.asarray(labs, dtype=np.int64) + n_false] = comp
             unique_components = np.array(sorted(int(c) for c in c2l), dtype=np.int32)
-            ccg = sol["component_contact_graph"]
+            if len(self._solved) >= 32:
+                self._solved.pop(next(iter(self._solved)))
+            self._solved[key] = (sol, lut, unique_components)
         else:
-            raise NotImplementedError("slab frames go through VoxelContainment(slab=True)")
+            self._solved[key] = self._solved.pop(key)              # most recently used last
+            sol, lut, unique_components = hit
+        ccg = sol["component_contact_graph"]
         # LUT to the device and the single dense write
         if nl <= self.h_lut.numel():
             self.h_lut[:nl].copy_(torch.from_numpy(lut))
@@ -202,7 +214,7 @@ class FramePipeline:
         np.add.at(acc, lut.astype(np.int64) - lo, volumes)
         out.voxel_counts = {np.int32(lo + k): np.int64(v) for k, v in enumerate(acc) if v}
         out.containment_graph = hg.containment_graph(sol["is_contained"], unique_components, ccg)
-        out.component_ranks = sol["component_ranks"]
+        out.component_ranks = dict(sol["component_ranks"])
         out.contacts, out.bridges, out.n_true, out.n_false = contacts, bridges, n_true, n_false
         out.labels_dev, out.components_dev, out.bits = self.labels, self.components, bits
         out.timings = {"device_label_pairs_s": t1 - t0, "host_lut_s": t2 - t1, "host_dag_s": time.perf_counter() - t2}

@@ -170,3 +170,28 @@ def test_translation_invariance_of_the_containment_hierarchy():
         assert sorted(lab.values()) == sorted(ref_lab.values())
         nx.set_node_attributes(g, lab, "sig"); nx.set_node_attributes(ref_g, ref_lab, "sig")
         assert nx.is_isomorphic(nx.DiGraph(g), nx.DiGraph(ref_g), node_match=lambda a, b: a["sig"] == b["sig"])
+
+
+def test_pipeline_memoised_graph_stage_is_keyed_by_topology():
+    """The pipeline memoises the host graph stage on (label counts, contacts, bridges): alternating scenes with
+    different topologies through ONE pipeline must give what a fresh pipeline gives for each."""
+    import torch
+    from mdvcontainment_b200 import synth
+    from mdvcontainment_b200.pipeline import FramePipeline
+    a, dims = synth.vesicle_scene(box_nm=24.0, seed=3)
+    rng = np.random.default_rng(4)
+    b = (rng.random((4000, 3)) * dims[:3]).astype(np.float32)            # sparse random beads: many small components
+    c = a[: len(a) // 3]                                                 # only part of the slab: a different hierarchy
+    pipe = FramePipeline(dims, 0.5, closing=True)
+    seen = {}
+    for name, pos in [("a", a), ("b", b), ("a", a), ("c", c), ("b", b), ("c", c), ("a", a)]:
+        out = pipe.run(torch.from_numpy(pos).cuda())
+        got = (str(out), {int(k): int(v) for k, v in out.voxel_counts.items()},
+               {int(k): int(v) for k, v in out.component_ranks.items()}, sha(out.components_dev.cpu().numpy()))
+        if name not in seen:
+            fresh = FramePipeline(dims, 0.5, closing=True).run(torch.from_numpy(pos).cuda())
+            seen[name] = (str(fresh), {int(k): int(v) for k, v in fresh.voxel_counts.items()},
+                          {int(k): int(v) for k, v in fresh.component_ranks.items()}, sha(fresh.components_dev.cpu().numpy()))
+        assert got == seen[name], name
+    assert len({v[0] for v in seen.values()}) == 3                       # the three scenes really differ
+    assert 1 <= len(pipe._solved) <= 3
