@@ -226,7 +226,7 @@ def run_ours(args):
             p.expand_elapsed_ms()
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        l0 = lib.mdvc_launch_count()
+        l0 = lib.mdvc_launch_count() + sum(p.replayed_launches for p in pipes)
         e0.record()
         run_frames(steps, host)
         for p in pipes:                                   # the default-stream end event must follow all pipelines
@@ -241,15 +241,16 @@ def run_ours(args):
             ms = float(t.item())
         em = [p.expand_elapsed_ms() for p in pipes]
         em = [v for v in em if v > 0]
-        return ms, lib.mdvc_launch_count() - l0, sum(em) / max(1, len(em))
+        return ms, lib.mdvc_launch_count() + sum(p.replayed_launches for p in pipes) - l0, sum(em) / max(1, len(em))
 
-    run_frames(args.warmup, False)
+    # every pipeline in flight gets its warm-up frames (the second one captures its CUDA graph)
+    run_frames(max(args.warmup, 3) * n_flight, False)
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
     ms_dev, launches, expand_ms = timed(args.steps, False)
     clocks = sampler.stop() if rank == 0 else None
-    run_frames(args.warmup, True)
+    run_frames(max(args.warmup, 3) * n_flight, True)
     ms_e2e, _, _ = timed(args.steps, True)
     # the dominant kernel alone (one frame at a time, nothing else on the GPU), for the roofline's context
     iso = []
@@ -261,7 +262,7 @@ def run_ours(args):
     # (containment_main.py:91,134; the non-periodic label grid is a local there) -- is materialised
     for p in pipes:
         p.labels, p.write_labels = None, False
-    run_frames(max(1, args.warmup // 2), False)
+    run_frames(3 * n_flight, False)
     ms_conly, _, _ = timed(args.steps, False)
 
     if rank != 0:

@@ -8,6 +8,7 @@ shards a trajectory with no cross-GPU traffic.
 from __future__ import annotations
 
 import ctypes
+import os
 import time
 
 import numpy as np
@@ -36,7 +37,7 @@ class FramePipeline:
     HEAD_VOLUMES = 8192
 
     def __init__(self, dimensions, resolution, closing=True, morph="", periodic=True, max_atoms=0,
-                 write_labels=True, device="cuda"):
+                 write_labels=True, device="cuda", use_graph=True):
         self.device = torch.device(device)
         self.dimensions = np.asarray(dimensions, dtype=np.float32)
         self.resolution = resolution
@@ -65,6 +66,12 @@ class FramePipeline:
         self._bits = None
         self._rows_counted = False
         self._solved = {}                                         # memoised graph stage, see _finish
+        self.use_graph = use_graph and os.environ.get("MDVC_PIPELINE_GRAPH", "1") != "0"
+        self._graph = self._graph_bits = None
+        self._graphs = {}
+        self.replayed_launches = 0
+        self._graph_failed = False
+        self._frames_seen = 0
 
     # ---------------------------------------------------------------------------------------
     def _alloc_host(self):
@@ -86,6 +93,7 @@ class FramePipeline:
 
     def _regrow(self, header):
         self.plan = self.plan.grown(header)
+        self._graphs.clear()                                      # captured against the old workspace
         self._alloc_host()
 
     # ---------------------------------------------------------------------------------------
@@ -107,7 +115,7 @@ class FramePipeline:
         self._rows_counted = bool(counted.value)
         return self.bits_b
 
-    def _enqueue_stage1(self, bits: dev.BitGrid, rows_counted: bool = False):
+    def _enqueue_stage1(self, bits: dev.BitGrid, rows_counted: bool = False, record: bool = True):
         self.plan.label(bits, rows_counted)
         self.plan.pairs(bits, self.periodic)
         # small results: four async copies into pinned memory, waited for in finish()
@@ -115,7 +123,8 @@ class FramePipeline:
         self.h_contacts.copy_(self.d_contacts, non_blocking=True)
         self.h_bridges.copy_(self.d_bridges, non_blocking=True)
         self.h_volumes.copy_(self.d_volumes, non_blocking=True)
-        self.ev_stage1.record()
+        if record:
+            self.ev_stage1.record()
 
     def begin(self, positions_dev: torch.Tensor, host_positions: torch.Tensor | None = None):
         """Enqueue bin -> morph -> label -> pairs and the small read-backs on this pipeline's stream; returns
@@ -129,8 +138,54 @@ class FramePipeline:
                     self.pos_dev = torch.empty((n, 3), dtype=torch.float32, device=self.device)
                 self.pos_dev[:n].copy_(host_positions, non_blocking=True)
                 positions_dev = self.pos_dev[:n]
-            self._bits = self.voxelize(positions_dev)
-            self._enqueue_stage1(self._bits, self._rows_counted)
+            if not self._run_graph(positions_dev):
+                self._bits = self.voxelize(positions_dev)
+                self._enqueue_stage1(self._bits, self._rows_counted)
+
+    # ---------------------------------------------------------------------------------------
+    # Stage 1 is ~27 launches whose grids depend only on the capacities: for small frames (512^3: 0.26 ms of device
+    # work) enqueueing them from Python (0.22 ms) is what limits a GPU.  After one eager frame the sequence
+    # bin -> morph -> label -> pairs -> read-backs is captured into a CUDA graph per (bead count, position buffer) and
+    # replayed with one launch.  Anything unexpected during capture switches the pipeline back to eager launches.
+    def _run_graph(self, positions_dev: torch.Tensor) -> bool:
+        if not self.use_graph or self._graph_failed:
+            return False
+        self._frames_seen += 1
+        if self._frames_seen < 2:                                 # the first frame settles the capacities eagerly
+            return False
+        n = int(positions_dev.shape[0])
+        key = (n, positions_dev.data_ptr(), id(self.plan))
+        if key not in self._graphs and len(self._graphs) >= 4:
+            # too many different position buffers: funnel them through one fixed buffer (one more copy per frame)
+            if self.pos_dev is None or self.pos_dev.shape[0] < n:
+                self.pos_dev = torch.empty((n, 3), dtype=torch.float32, device=self.device)
+            if positions_dev.data_ptr() != self.pos_dev.data_ptr():
+                self.pos_dev[:n].copy_(positions_dev, non_blocking=True)
+            positions_dev = self.pos_dev[:n]
+            key = (n, positions_dev.data_ptr(), id(self.plan))
+        if key not in self._graphs:
+            try:
+                g = torch.cuda.CUDAGraph()
+                l0 = int(self.lib.mdvc_launch_count())
+                with torch.cuda.graph(g, stream=self.stream):
+                    bits = self.voxelize(positions_dev)
+                    self._enqueue_stage1(bits, self._rows_counted, record=False)
+                n_launch = int(self.lib.mdvc_launch_count()) - l0
+                if len(self._graphs) >= 5:
+                    self._graphs.pop(next(iter(self._graphs)))
+                self._graphs[key] = (g, bits, positions_dev, n_launch)    # keeps the captured input buffer alive
+                self.replayed_launches -= n_launch                        # the capture itself counted them once
+            except Exception:                                              # noqa: BLE001 - stay on the eager path
+                self._graph_failed = True
+                self._graphs.clear()
+                torch.cuda.synchronize()
+                return False
+        self._graph, self._graph_bits, _, n_launch = self._graphs[key]
+        self._graph.replay()
+        self.replayed_launches += n_launch                        # kernels of this library launched by the replay
+        self._bits = self._graph_bits
+        self.ev_stage1.record()
+        return True
 
     def finish(self) -> FrameOutput:
         """Wait for the small results, run the host graph stage, upload the LUT, enqueue the dense write."""
