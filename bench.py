@@ -294,6 +294,7 @@ def run_ours(args):
                    "grid": [size] * 3, "atoms": n_atoms, "frames_per_gpu_per_step": 1,
                    "l2": f"no flush: each step streams {frame_bytes / 1e9:.2f} GB (> 126 MB L2)",
                    "frames_in_flight_per_gpu": n_flight,
+                   "stage1_cuda_graph": bool(all(len(p._graphs) > 0 for p in pipes)),
                    "parallelism": f"frames sharded over {world} GPU(s), no collective on the data path"},
         "gvoxel_per_s": value * N / 1e9,
         "frame_algorithmic_gbs": frame_bytes * value / world / 1e9,

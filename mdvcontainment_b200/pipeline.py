@@ -167,7 +167,8 @@ class FramePipeline:
             try:
                 g = torch.cuda.CUDAGraph()
                 l0 = int(self.lib.mdvc_launch_count())
-                with torch.cuda.graph(g, stream=self.stream):
+                # thread_local: a NCCL watchdog thread polling its events must not invalidate the capture
+                with torch.cuda.graph(g, stream=self.stream, capture_error_mode="thread_local"):
                     bits = self.voxelize(positions_dev)
                     self._enqueue_stage1(bits, self._rows_counted, record=False)
                 n_launch = int(self.lib.mdvc_launch_count()) - l0
