@@ -66,6 +66,7 @@ class FramePipeline:
         self._bits = None
         self._rows_counted = False
         self._solved = {}                                         # memoised graph stage, see _finish
+        self._lut_key = None                                      # key of the table currently in lut_dev
         self.use_graph = use_graph and os.environ.get("MDVC_PIPELINE_GRAPH", "1") != "0"
         self._graph = self._graph_bits = None
         self._graphs = {}
@@ -94,6 +95,7 @@ class FramePipeline:
     def _regrow(self, header):
         self.plan = self.plan.grown(header)
         self._graphs.clear()                                      # captured against the old workspace
+        self._lut_key = None
         self._alloc_host()
 
     # ---------------------------------------------------------------------------------------
@@ -241,17 +243,19 @@ class FramePipeline:
             for comp, labs in c2l.items():
                 lut[np.asarray(labs, dtype=np.int64) + n_false] = comp
             unique_components = np.array(sorted(int(c) for c in c2l), dtype=np.int32)
+            dag = hg.containment_graph(sol["is_contained"], unique_components, sol["component_contact_graph"])
             if len(self._solved) >= 32:
                 self._solved.pop(next(iter(self._solved)))
-            self._solved[key] = (sol, lut, unique_components)
+            self._solved[key] = (sol, lut, unique_components, dag)
         else:
             self._solved[key] = self._solved.pop(key)              # most recently used last
-            sol, lut, unique_components = hit
-        ccg = sol["component_contact_graph"]
+            sol, lut, unique_components, dag = hit
         # LUT to the device and the single dense write
         if nl <= self.h_lut.numel():
-            self.h_lut[:nl].copy_(torch.from_numpy(lut))
-            self.lut_dev[:nl].copy_(self.h_lut[:nl], non_blocking=True)
+            if self._lut_key != key:                               # same table as the previous frame: already on the device
+                self.h_lut[:nl].copy_(torch.from_numpy(lut))
+                self.lut_dev[:nl].copy_(self.h_lut[:nl], non_blocking=True)
+                self._lut_key = key
             lut_dev = self.lut_dev[:nl]
         else:
             lut_dev = torch.from_numpy(lut).to(self.device)
@@ -269,7 +273,7 @@ class FramePipeline:
         acc = np.zeros(int(lut.max()) - lo + 1, dtype=np.int64)
         np.add.at(acc, lut.astype(np.int64) - lo, volumes)
         out.voxel_counts = {np.int32(lo + k): np.int64(v) for k, v in enumerate(acc) if v}
-        out.containment_graph = hg.containment_graph(sol["is_contained"], unique_components, ccg)
+        out.containment_graph = dag.copy()                        # the caller owns its graph; the memo keeps the original
         out.component_ranks = dict(sol["component_ranks"])
         out.contacts, out.bridges, out.n_true, out.n_false = contacts, bridges, n_true, n_false
         out.labels_dev, out.components_dev, out.bits = self.labels, self.components, bits
