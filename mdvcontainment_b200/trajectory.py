@@ -48,24 +48,42 @@ def gather_results(local: dict, n_frames: int, rank: int, world: int):
 
 
 def run_trajectory(frames, dimensions, resolution, closing=True, morph="", n_frames=None,
-                   frame_fn: Callable | None = None):
+                   frame_fn: Callable | None = None, in_flight: int = 3):
     """Process every frame of a trajectory, sharded over the ranks of the current process group.
 
-    ``frame_fn(positions) -> summary dict`` defaults to one FramePipeline per rank (CUDA); tests inject
-    a CPU function to exercise the sharding/gathering logic without a GPU."""
+    Default (CUDA): ``in_flight`` FramePipelines per rank, each with its own streams and a reusable pinned staging
+    buffer, so that the copy / device stages of frame f+1.. overlap the host graph stage of frame f.
+    ``frame_fn(positions) -> summary dict`` replaces all of that; tests inject a CPU function to exercise the
+    sharding/gathering logic without a GPU."""
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if n_frames is None:
         n_frames = len(frames)
     get = frames if callable(frames) else (lambda f: frames[f])
-    if frame_fn is None:
-        import torch
-        from .pipeline import FramePipeline
-        torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
-        pipe = FramePipeline(dimensions, resolution, closing=closing, morph=morph)
+    mine = frames_of_rank(n_frames, rank, world)
+    if frame_fn is not None:
+        local = {f: frame_fn(get(f)) for f in mine}
+        return gather_results(local, n_frames, rank, world)
 
-        def frame_fn(pos):
-            t = torch.from_numpy(np.ascontiguousarray(pos, dtype=np.float32)).pin_memory()
-            return summarise(pipe.run_host(t))
-    local = {f: frame_fn(get(f)) for f in frames_of_rank(n_frames, rank, world)}
+    import torch
+    from .pipeline import FramePipeline
+    torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
+    depth = max(1, min(int(in_flight), len(mine) or 1))
+    pipes = [FramePipeline(dimensions, resolution, closing=closing, morph=morph) for _ in range(depth)]
+    pins = [None] * depth
+    local, pending = {}, []
+    for k, f in enumerate(mine):
+        i = k % depth
+        if len(pending) == depth:                       # the oldest frame in flight is the one that used slot i
+            f0, i0 = pending.pop(0)
+            local[f0] = summarise(pipes[i0].finish())
+        pos = torch.from_numpy(np.ascontiguousarray(get(f), dtype=np.float32).reshape(-1, 3))
+        n = pos.shape[0]
+        if pins[i] is None or pins[i].shape[0] < n:
+            pins[i] = torch.empty((max(n, 1), 3), dtype=torch.float32, pin_memory=True)
+        pins[i][:n].copy_(pos)
+        pipes[i].begin(None, host_positions=pins[i][:n])
+        pending.append((f, i))
+    for f0, i0 in pending:
+        local[f0] = summarise(pipes[i0].finish())
     return gather_results(local, n_frames, rank, world)
