@@ -239,6 +239,21 @@ int mdvc_atom_gather_voxels(const int32_t *query, long long m, int X, int Y, int
                             const unsigned long long *keys, long long n, const long long *atom_ix, uint32_t *scratch,
                             long long *out, unsigned long long out_cap, unsigned long long *n_out_dev, void *stream);
 
+/* ---------------------------------------------------------------------------------------
+ * N3  host graph stage (HOST function: plain host pointers, no stream, no GPU).  The label-level core of
+ *     get_subgraphs / get_rank / get_ranks (graph_logic.py:101-127, rank_logic.py:5-110, 136-181): connected pieces
+ *     of a graph whose directed edges u -> v carry an image shift s (phi(v) = phi(u) + s; contacts have s = 0,
+ *     a bridge row (l1, l2, s) is the edge l1 -> l2) and the rank 0..3 of the lattice spanned by the shift sums of
+ *     each piece's closed walks -- what the reference obtains from an Eulerian circuit + SVD.
+ *  edge_u/edge_v int32[n_edges] node indices in [0, n_nodes); edge_shift int32[n_edges][3] (NULL = all zero);
+ *  skip_node uint8[n_nodes] (optional): nodes -- and every edge touching them -- left out (complement of a component);
+ *  outputs (each optional): root_out[n_nodes] = smallest node index of the node's piece (-1 for skipped nodes),
+ *  rank_out[n_nodes] = rank of the node's piece (-1 skipped), *max_rank_out = largest rank over all pieces.
+ * ------------------------------------------------------------------------------------- */
+int mdvc_host_shift_graph_ranks(long long n_nodes, const int32_t *edge_u_host, const int32_t *edge_v_host,
+                                const int32_t *edge_shift_host, long long n_edges, const uint8_t *skip_node_host,
+                                int32_t *root_out_host, int8_t *rank_out_host, int32_t *max_rank_out_host);
+
 #ifdef __cplusplus
 }
 #endif

@@ -12,7 +12,7 @@ import sys
 PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG, "csrc")
 LIB = os.path.join(PKG, "libmdvc.so")
-SOURCES = ("bits.cu", "frame.cu", "gridops.cu")
+SOURCES = ("bits.cu", "frame.cu", "gridops.cu", "hostgraph.cpp")
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC,-O2", "--use_fast_math=false"]
 
@@ -39,7 +39,7 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
     flags = [f for f in NVCC_FLAGS if not f.startswith("--use_fast_math")]
     flags += os.environ.get("MDVC_NVCC_EXTRA", "").split()          # e.g. -DSTRIP_TY=128 for tuning experiments
     for src in SOURCES:
-        obj = os.path.join(CSRC, src.replace(".cu", ".o"))
+        obj = os.path.join(CSRC, os.path.splitext(src)[0] + ".o")
         cmd = [_nvcc(), *flags, "-c", os.path.join(CSRC, src), "-o", obj]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")

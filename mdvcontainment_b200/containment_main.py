@@ -53,13 +53,17 @@ def label_frame(bits: dev.BitGrid, periodic=True, plan: dev.FramePlan | None = N
     return fr
 
 
-def apply_component_lut(fr: FrameResult, component2labels, also_labels=False):
-    """create_components_grid (label.py:21-38) as one LUT pass fused into the dense write."""
+def apply_component_lut(fr: FrameResult, lut, also_labels=False):
+    """create_components_grid (label.py:21-38) as one LUT pass fused into the dense write.  ``lut``: int32
+    [n_false + n_true + 1], index = label + n_false (``PeriodicSolution.lut``), or the reference's
+    ``component2labels`` dict."""
     h = fr.header
     nf = int(h.n_false)
-    lut = np.zeros(int(h.n_true) + nf + 1, dtype=np.int32)
-    for comp, labs in component2labels.items():
-        lut[np.asarray(labs, dtype=np.int64) + nf] = comp
+    if isinstance(lut, dict):
+        table = np.zeros(int(h.n_true) + nf + 1, dtype=np.int32)
+        for comp, labs in lut.items():
+            table[np.asarray(labs, dtype=np.int64) + nf] = comp
+        lut = table
     fr.lut = lut
     fr.plan.set_lut(torch.from_numpy(lut).to(fr.bits.words.device))
     fr.components_dev = torch.empty(fr.bits.shape, dtype=torch.int32, device=fr.bits.words.device)
@@ -115,22 +119,21 @@ def calc_containment_graph(boolean_grid, verbose=False, write_structures=False, 
     t0 = time.perf_counter()
     if not slab:
         sol = hg.solve_periodic(nonp_unique_labels, fr.contacts, fr.bridges)
-        c2l = sol["component2labels"]
         if verbose:
+            c2l = sol["component2labels"]
             labels2component = {labs: comp for comp, labs in c2l.items()}
             print(f'component2labels {c2l}')
             print(f'labels2component {labels2component}')
             print(f'label2component {sol["label2component"]}')
-        apply_component_lut(fr, c2l)
+        apply_component_lut(fr, sol.lut(int(fr.header.n_false), int(fr.header.n_true)))
         component_ranks = sol["component_ranks"]
         if verbose:
             print(f'All rank of components: {component_ranks}')
             print(f'Complement ranks: {sol["complement_ranks"]}')
             print(f'Containment status: {sol["is_contained"]}')
-        is_contained = sol["is_contained"]
-        component_contact_graph = sol["component_contact_graph"]
-        # np.unique(components_grid) (:132): every component owns at least one voxel
-        unique_components = np.array(sorted(int(c) for c in c2l), dtype=np.int32)
+        # np.unique(components_grid) (:132): every component owns at least one voxel -> the DAG's node array
+        containment_graph = sol.containment_dag()                  # arrays; networkx form on demand
+        component_contact_graph = None                              # sol["component_contact_graph"], on demand
     else:
         labels_dev = fr.labels()
         fr.components_dev = labels_dev
@@ -140,7 +143,7 @@ def calc_containment_graph(boolean_grid, verbose=False, write_structures=False, 
             _write_grid('mask.gro', _slab_mask(bits.shape))
         component_ranks, is_contained = sol["component_ranks"], sol["is_contained"]
         component_contact_graph = nx.Graph(sol["label_graph"].to_networkx())
-        unique_components = nonp_unique_labels
+        containment_graph = hg.containment_graph(is_contained, nonp_unique_labels, component_contact_graph)
     if write_structures:
         _write_grid('components.gro', dev.to_numpy(fr.components_dev))
     if draw_graphs:
@@ -148,11 +151,12 @@ def calc_containment_graph(boolean_grid, verbose=False, write_structures=False, 
         _draw_graph(sol["label_graph"].to_networkx())
         if not slab:
             print('=== COMPONENT CONTACTS GRAPH ===')
-            _draw_graph(component_contact_graph)
-    containment_graph = hg.containment_graph(is_contained, unique_components, component_contact_graph)
+            _draw_graph(sol["component_contact_graph"])
     fr.timings["host_graph_s"] = time.perf_counter() - t0
     if _want_frame:
-        return containment_graph, component_contact_graph, fr, component_ranks, sol["label_graph"]
+        return containment_graph, (component_contact_graph if slab else sol), fr, component_ranks, sol["label_graph"]
+    if not slab:
+        containment_graph, component_contact_graph = containment_graph.to_networkx(), sol["component_contact_graph"]
     return (containment_graph, component_contact_graph, dev.to_numpy(fr.components_dev), component_ranks,
             sol["label_graph"].to_networkx())
 
@@ -186,7 +190,10 @@ class VoxelContainmentBase:
     Subclasses provide ``_base`` (the data owner) and ``containment_graph``."""
 
     def __str__(self):
-        return format_dag_structure(self.containment_graph, self.component_ranks, self.voxel_counts, unit='nvoxels')
+        return format_dag_structure(self._format_graph(), self.component_ranks, self.voxel_counts, unit='nvoxels')
+
+    def _format_graph(self):
+        return self.containment_graph
 
     # --- data owned by the base --------------------------------------------------------------
     @property
@@ -199,7 +206,10 @@ class VoxelContainmentBase:
 
     @property
     def component_contact_graph(self):
-        return self._base._component_contact_graph
+        ccg = self._base._component_contact_graph
+        if isinstance(ccg, hg.PeriodicSolution):                  # built on first use
+            ccg = self._base._component_contact_graph = ccg["component_contact_graph"]
+        return ccg
 
     @property
     def components_grid(self):
@@ -384,12 +394,8 @@ class VoxelContainment(VoxelContainmentBase):
         if grid is not None:
             return self.get_counts(grid)
         fr = self._frame
-        vol = fr.label_volumes
-        lut = fr.lut
-        lo = int(lut.min())
-        acc = np.zeros(int(lut.max()) - lo + 1, dtype=np.int64)
-        np.add.at(acc, lut.astype(np.int64) - lo, vol)
-        return {np.int32(lo + k): np.int64(v) for k, v in enumerate(acc) if v}
+        ids, counts = hg.counts_by_component(fr.lut, fr.label_volumes)
+        return {np.int32(k): np.int64(v) for k, v in zip(ids.tolist(), counts.tolist())}
 
     def _get_grid(self):
         if isinstance(self._grid, dev.BitGrid):
@@ -417,7 +423,13 @@ class VoxelContainment(VoxelContainmentBase):
 
     @property
     def containment_graph(self):
+        if isinstance(self._containment_graph, hg.CompactDAG):    # networkx form on first use
+            self._dag = self._containment_graph
+            self._containment_graph = self._dag.to_networkx()
         return self._containment_graph
+
+    def _format_graph(self):
+        return self._containment_graph                            # CompactDAG or networkx: both print
 
     @property
     def voxel_counts(self):

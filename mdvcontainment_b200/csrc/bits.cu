@@ -450,122 +450,6 @@ __device__ __forceinline__ uint4 or4(uint4 a, uint4 b) { return make_uint4(a.x |
 __device__ __forceinline__ uint4 and4(uint4 a, uint4 b) { return make_uint4(a.x & b.x, a.y & b.y, a.z & b.z, a.w & b.w); }
 __device__ __forceinline__ uint4 not4(uint4 a) { return make_uint4(~a.x, ~a.y, ~a.z, ~a.w); }
 
-#define CLOSE_THREADS 512
-// FULLZ: Z is a multiple of 128 (every word of every quad is a full word) -- the masks and the tail fix-ups fold away
-template <int S, bool FULLZ>
-__global__ void __launch_bounds__(CLOSE_THREADS)
-k_close_sweep(const uint32_t *__restrict__ in, uint32_t *__restrict__ out, int X, int Y, int Z, int pitch, int nw,
-              int lq_log2, int JT, int TX) {
-    extern __shared__ __align__(128) unsigned char close_smem[];
-    const int LQ = 1 << lq_log2;                                  // lanes reserved per row (power of two)
-    const int nq = pitch >> 2;                                    // quads per row (<= LQ)
-    const int TY = JT - 4;
-    const int tile4 = JT * nq;                                    // uint4 per plane tile
-    uint4 *raw = (uint4 *)close_smem;                             // [S][JT][nq]
-    uint4 *cmp = raw + S * tile4;                                 // [2][JT][nq]
-    uint64_t *full = (uint64_t *)(cmp + 2 * tile4);               // [S]
-    const int t = threadIdx.x;
-    const int j = t >> lq_log2, l = t & (LQ - 1);
-    const bool lane_ok = j < JT && l < nq;
-    const bool has_up = lane_ok && j > 0, has_dn = lane_ok && j < JT - 1;
-    const int y0 = blockIdx.x * TY;
-    const int xs = blockIdx.y * TX, xe = min(xs + TX, X);
-    const int n_in = xe - xs + 4;                                 // input planes xs-2 .. xe+1
-    const int last = (Z - 1) & 31;
-    const int klast = nw - 1 - 4 * l;                             // position of the row's last word inside this quad
-    const int ktail = (klast >= 0 && klast < 3) ? klast : 3;      // the word of this quad that takes the lane-above carry
-    const int ush = (klast >= 0 && klast <= 3) ? last : 31;       // ... and the bit it lands on
-    uint4 vm = make_uint4(0u, 0u, 0u, 0u);
-    if (lane_ok) vm = make_uint4(mdvc_valid_mask(4 * l, Z), mdvc_valid_mask(4 * l + 1, Z), mdvc_valid_mask(4 * l + 2, Z),
-                                 mdvc_valid_mask(4 * l + 3, Z));
-    const int pl = l > 0 ? l - 1 : nq - 1, nl = l < nq - 1 ? l + 1 : 0;
-    const size_t plane = (size_t)Y * pitch;
-
-    auto issue = [&](int s, int stage) {                          // elected thread: stream plane s of the chunk
-        int x = xs - 2 + s;
-        x %= X; if (x < 0) x += X;
-        uint64_t *bar = full + stage;
-        uint32_t *dst = (uint32_t *)(raw + stage * tile4);
-        const uint32_t *pln = in + (size_t)x * plane;
-        mbar_expect_tx(bar, (uint32_t)tile4 * 16u);
-        int yy = (y0 - 2) % Y; if (yy < 0) yy += Y;
-        for (int r = 0; r < JT;) {
-            int len = min(JT - r, Y - yy);
-            bulk_g2s(dst + r * pitch, pln + (size_t)yy * pitch, (uint32_t)(len * pitch) * 4u, bar);
-            r += len; yy = 0;
-        }
-    };
-    // periodic z-dilation of the row; v holds zeros in invalid words and bits
-    auto zdil = [&](uint4 v) -> uint4 {
-        uint32_t hi;
-        if (FULLZ) hi = v.w >> 31;
-        else {
-            const uint32_t tw = ktail == 0 ? v.x : (ktail == 1 ? v.y : (ktail == 2 ? v.z : v.w));
-            hi = (tw >> ush) & 1u;
-        }
-        const uint32_t e = hi | ((v.x & 1u) << 1);
-        const uint32_t pe = __shfl_sync(MDVC_FULL, e, pl, LQ);
-        const uint32_t ne = __shfl_sync(MDVC_FULL, e, nl, LQ);
-        const uint32_t down = pe & 1u, up = (ne >> 1) & 1u;
-        uint4 r;
-        r.x = v.x | ((v.x << 1) | down) | __funnelshift_r(v.x, v.y, 1);
-        r.y = v.y | __funnelshift_l(v.x, v.y, 1) | __funnelshift_r(v.y, v.z, 1);
-        r.z = v.z | __funnelshift_l(v.y, v.z, 1) | __funnelshift_r(v.z, v.w, 1);
-        r.w = v.w | __funnelshift_l(v.z, v.w, 1) | (v.w >> 1);
-        if (FULLZ) r.w |= up << 31;
-        else {
-            const uint32_t ub = up << ush;
-            r.x |= ktail == 0 ? ub : 0u; r.y |= ktail == 1 ? ub : 0u; r.z |= ktail == 2 ? ub : 0u; r.w |= ktail == 3 ? ub : 0u;
-            r = and4(r, vm);
-        }
-        return r;
-    };
-
-    if (t == 0) {
-        for (int i = 0; i < S; ++i) mbar_init(full + i, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    }
-    __syncthreads();
-    if (t == 0) for (int s = 0; s < S && s < n_in; ++s) issue(s, s);
-
-    const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
-    uint4 Pm1 = zero, Pm2 = zero, Qm1 = zero, Qm2 = zero;
-    const int yout = y0 + j - 2;
-    const bool is_out = lane_ok && j >= 2 && j <= JT - 3 && yout < Y;
-    uint4 *op = (uint4 *)(out + (size_t)xs * plane + (size_t)(is_out ? yout : 0) * pitch) + l;
-    const size_t plane4 = plane >> 2;
-    const int me = j * nq + l;
-    int stage = 0;
-    uint32_t phase = 0;
-    for (int s = 0; s < n_in; ++s) {
-        mbar_wait(full + stage, phase);
-        const uint4 *rw = raw + stage * tile4 + me;
-        uint4 v = zero;
-        if (lane_ok) v = rw[0];
-        if (has_up) v = or4(v, rw[-nq]);
-        if (has_dn) v = or4(v, rw[nq]);
-        if (!FULLZ) v = and4(v, vm);
-        const uint4 P = zdil(v);
-        const uint4 n = and4(not4(or4(or4(Pm2, Pm1), P)), vm);     // complement of the dilated plane x-1
-        Pm2 = Pm1; Pm1 = P;
-        uint4 *ex = cmp + (s & 1) * tile4 + me;
-        if (lane_ok) ex[0] = n;
-        __syncthreads();
-        if (t == 0 && s + S < n_in) issue(s + S, stage);          // every thread has consumed this stage
-        uint4 q = n;
-        if (has_up) q = or4(q, ex[-nq]);
-        if (has_dn) q = or4(q, ex[nq]);
-        const uint4 Q = zdil(q);
-        if (s >= 4) {
-            if (is_out) *op = and4(not4(or4(or4(Qm2, Qm1), Q)), vm);
-            op += plane4;
-        }
-        Qm2 = Qm1; Qm1 = Q;
-        if (++stage == S) { stage = 0; phase ^= 1u; }
-    }
-}
-
 // Two adjacent rows (j0 = 2*jr, j0+1) per thread: the raw rows j0-1 .. j0+2 serve both (4 LDS.128 instead of 6), the
 // exchange tile is read for j0-1 and j0+2 only, the edge bits of both rows travel in one pair of shuffles, and the
 // per-plane overhead (mbarrier wait, barrier, pointers) is paid once per two rows.
@@ -730,26 +614,16 @@ static int launch_close(const uint32_t *src, uint32_t *dst, int X, int Y, int Z,
     int nq = pitch / 4, lq_log2 = 0;
     while ((1 << lq_log2) < nq) ++lq_log2;
     int LQ = 1 << lq_log2;
-    static int env_jt = -1, env_target = 0;
-    if (env_jt < 0) {
-        env_jt = getenv("MDVC_CLOSE_JT") ? atoi(getenv("MDVC_CLOSE_JT")) : 0;
-        env_target = getenv("MDVC_CLOSE_TARGET") ? atoi(getenv("MDVC_CLOSE_TARGET")) : 0;
-    }
-    static int env_rows = 0;
-    if (!env_rows) env_rows = getenv("MDVC_CLOSE_ROWS") ? atoi(getenv("MDVC_CLOSE_ROWS")) : 2;
-    const bool two = env_rows == 2;
-    if (!two && (e1 || !e2)) return MDVC_OK;                      // the one-row kernel only knows the closing
-    int JT = two ? 2 * (256 / LQ) : CLOSE_THREADS / LQ;
-    if (env_jt) JT = env_jt;
+    int JT = 2 * (256 / LQ);
     if (JT > Y + 4) JT = Y + 4;                                   // one tile covers all of y
     size_t row_bytes = (size_t)(S + 2) * pitch * 4;
     int fit = (int)((48 * 1024 - S * 8) / row_bytes);
     if (JT > fit) JT = fit;
     if (JT < 5) JT = 5;
-    if (two) JT += JT & 1;                                        // an even number of rows, two per thread
+    JT += JT & 1;                                                 // an even number of rows, two per thread
     int TY = JT - 4;
     int ny = (Y + TY - 1) / TY;
-    int target = env_target ? env_target : mdvc_num_sms() * mdvc_cap_ctas(4);
+    int target = mdvc_num_sms() * 4;
     int xchunks = (target + ny - 1) / ny;
     if (xchunks > (X + 7) / 8) xchunks = (X + 7) / 8;
     if (xchunks < 1) xchunks = 1;
@@ -758,27 +632,21 @@ static int launch_close(const uint32_t *src, uint32_t *dst, int X, int Y, int Z,
     xchunks = (X + TX - 1) / TX;
     size_t smem = (size_t)JT * row_bytes + S * 8;
     dim3 grid(ny, xchunks);
-    if (two) {
-        int threads = (((JT / 2) * LQ + 31) / 32) * 32;
+    int threads = (((JT / 2) * LQ + 31) / 32) * 32;
 #define MDVC_CLOSE2(FZ, A, B) k_close_sweep2<S, FZ, A, B><<<grid, threads, smem, st>>>(src, dst, X, Y, Z, pitch, nw, lq_log2, JT / 2, TX, row_counts)
-        const int variant = (Z % 128 == 0 ? 4 : 0) | (e1 ? 2 : 0) | (e2 ? 1 : 0);
-        switch (variant) {
-            case 0: MDVC_CLOSE2(false, false, false); break;
-            case 1: MDVC_CLOSE2(false, false, true); break;
-            case 2: MDVC_CLOSE2(false, true, false); break;
-            case 3: MDVC_CLOSE2(false, true, true); break;
-            case 4: MDVC_CLOSE2(true, false, false); break;
-            case 5: MDVC_CLOSE2(true, false, true); break;
-            case 6: MDVC_CLOSE2(true, true, false); break;
-            default: MDVC_CLOSE2(true, true, true); break;
-        }
-#undef MDVC_CLOSE2
-        if (counted) *counted = row_counts != nullptr;
-    } else {
-        int threads = ((JT * LQ + 31) / 32) * 32;
-        if (Z % 128 == 0) k_close_sweep<S, true><<<grid, threads, smem, st>>>(src, dst, X, Y, Z, pitch, nw, lq_log2, JT, TX);
-        else k_close_sweep<S, false><<<grid, threads, smem, st>>>(src, dst, X, Y, Z, pitch, nw, lq_log2, JT, TX);
+    const int variant = (Z % 128 == 0 ? 4 : 0) | (e1 ? 2 : 0) | (e2 ? 1 : 0);
+    switch (variant) {
+        case 0: MDVC_CLOSE2(false, false, false); break;
+        case 1: MDVC_CLOSE2(false, false, true); break;
+        case 2: MDVC_CLOSE2(false, true, false); break;
+        case 3: MDVC_CLOSE2(false, true, true); break;
+        case 4: MDVC_CLOSE2(true, false, false); break;
+        case 5: MDVC_CLOSE2(true, false, true); break;
+        case 6: MDVC_CLOSE2(true, true, false); break;
+        default: MDVC_CLOSE2(true, true, true); break;
     }
+#undef MDVC_CLOSE2
+    if (counted) *counted = row_counts != nullptr;
     MDVC_LAUNCH_CHECK();
     *done = 1;
     return MDVC_OK;
@@ -834,10 +702,9 @@ static int morph_impl(const uint32_t *bits_in, uint32_t *bits_out, uint32_t *tmp
     // (decided up front from the same conditions launch_close checks, so that the ping-pong plan below holds)
     const int nw = mdvc_words(Z);
     const uintptr_t all_ptrs = (uintptr_t)bits_in | (uintptr_t)bits_out | (uintptr_t)tmp;
-    const bool can_fuse = nw <= 32 && pitch == ((nw + 3) / 4) * 4 && (all_ptrs & 15) == 0 && !getenv("MDVC_NO_FUSED_CLOSE");
-    const bool any_pair = can_fuse && !(getenv("MDVC_CLOSE_ROWS") && atoi(getenv("MDVC_CLOSE_ROWS")) == 1);
+    const bool can_fuse = nw <= 32 && pitch == ((nw + 3) / 4) * 4 && (all_ptrs & 15) == 0;
     auto pair_at = [&](size_t i) {
-        return can_fuse && i + 1 < n_ops && (any_pair || (ops[i] == 'd' && ops[i + 1] == 'e'));
+        return can_fuse && i + 1 < n_ops;
     };
     size_t n_launch = 0;
     for (size_t i = 0; i < n_ops; ++i, ++n_launch)

@@ -41,22 +41,10 @@ static inline int mdvc_num_sms() {
     return sms;
 }
 
-// Experiment switch: MDVC_S1_MAX_CTAS=k caps every grid-stride / tile kernel except the dense write at k CTAs per
-// SM, so that the dense write of another frame can stay resident next to them (0 = no cap).
-static inline int mdvc_s1_max_ctas() {
-    static int v = -1;
-    if (v < 0) v = getenv("MDVC_S1_MAX_CTAS") ? atoi(getenv("MDVC_S1_MAX_CTAS")) : 0;
-    return v;
-}
-static inline int mdvc_cap_ctas(int blocks_per_sm) {
-    int k = mdvc_s1_max_ctas();
-    return (k > 0 && blocks_per_sm < 256 && blocks_per_sm > k) ? k : blocks_per_sm;
-}
-
 // grid for a grid-stride kernel: enough blocks for `work` items, capped at `waves` blocks per SM
 static inline unsigned mdvc_grid(long long work, int block, int blocks_per_sm = 16) {
     long long need = (work + block - 1) / block;
-    long long cap = (long long)mdvc_num_sms() * mdvc_cap_ctas(blocks_per_sm);
+    long long cap = (long long)mdvc_num_sms() * blocks_per_sm;
     if (need < 1) need = 1;
     return (unsigned)(need < cap ? need : cap);
 }

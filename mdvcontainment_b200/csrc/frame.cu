@@ -91,6 +91,7 @@ static bool make_dims(int X, int Y, int Z, int pitch, Dims &D) {
     if (X <= 0 || Y <= 0 || Z <= 0 || pitch < mdvc_words(Z)) return false;
     unsigned long long N = (unsigned long long)X * Y * Z;
     if (N >= (1ull << 31)) return false;
+    if (Z >= (1 << 24)) return false;      // the link / pair kernels pack a run's z-start into 24 bits (ZMASK)
     D.X = X; D.Y = Y; D.Z = Z; D.pitch = pitch; D.nw = mdvc_words(Z);
     D.rows = (long long)X * Y; D.N = N;
     return true;
@@ -1755,8 +1756,7 @@ static int frame_label(const uint32_t *bits, int X, int Y, int Z, int pitch, voi
     // rows of at most 128 words on 16-byte aligned grids: the quad-per-lane kernels
     int lq = 1;
     while (lq < D.pitch / 4) lq <<= 1;
-    const bool quad = lq <= 32 && D.pitch % 4 == 0 && (reinterpret_cast<uintptr_t>(bits) & 15) == 0 &&
-                      !getenv("MDVC_NO_QUAD_RUNS");
+    const bool quad = lq <= 32 && D.pitch % 4 == 0 && (reinterpret_cast<uintptr_t>(bits) & 15) == 0;
     if (quad) row_grid = mdvc_grid(D.rows * lq / 4, 256, 8);
     if (rows_counted) {
         // stage 1a was done by the kernel that produced the grid (mdvc_morph_counted)
@@ -1785,7 +1785,7 @@ static int frame_label(const uint32_t *bits, int X, int Y, int Z, int pitch, voi
     {
         int spp = (D.Y + STRIP_TY - 1) / STRIP_TY;
         long long n_strips = (long long)D.X * spp;
-        unsigned sgrid = (unsigned)(n_strips < (long long)mdvc_num_sms() * mdvc_cap_ctas(32) ? n_strips : (long long)mdvc_num_sms() * mdvc_cap_ctas(32));
+        unsigned sgrid = (unsigned)(n_strips < (long long)mdvc_num_sms() * 32 ? n_strips : (long long)mdvc_num_sms() * 32);
         unsigned lgrid = mdvc_grid(caps->max_runs, 256, 4);
         k_strip_link<<<sgrid, TILE_THREADS, 0, st>>>(bits, D, h, rowoff, rowpol, runstart, parent, rootlist);
         MDVC_LAUNCH_CHECK();
@@ -1798,7 +1798,7 @@ static int frame_label(const uint32_t *bits, int X, int Y, int Z, int pitch, voi
         }
         for (long long s = 1; s < D.X; s *= LINK_RADIX) {
             long long tiles = (long long)((D.X - 1) / s) * spp;
-            unsigned tgrid = (unsigned)(tiles < (long long)mdvc_num_sms() * mdvc_cap_ctas(32) ? tiles : (long long)mdvc_num_sms() * mdvc_cap_ctas(32));
+            unsigned tgrid = (unsigned)(tiles < (long long)mdvc_num_sms() * 32 ? tiles : (long long)mdvc_num_sms() * 32);
             k_tile_link_x<<<tgrid, TILE_THREADS, 0, st>>>(bits, D, h, rowoff, rowpol, runstart, parent, (int)s, LINK_RADIX);
             MDVC_LAUNCH_CHECK();
             k_flatten_list<<<lgrid, 256, 0, st>>>(h, rootlist, parent);
@@ -1835,7 +1835,7 @@ extern "C" int mdvc_frame_pairs(const uint32_t *bits, int X, int Y, int Z, int p
         long long tiles = (long long)D.X * ((D.Y + PT_TY - 1) / PT_TY);
         // four CTAs are resident per SM; 16 per SM keeps the tail short while the per-CTA set-up (clearing the two
         // key caches) is paid four times less often than with one CTA per tile (measured: 0.219 -> 0.198 ms)
-        unsigned tgrid = (unsigned)(tiles < (long long)mdvc_num_sms() * mdvc_cap_ctas(16) ? tiles : (long long)mdvc_num_sms() * mdvc_cap_ctas(16));
+        unsigned tgrid = (unsigned)(tiles < (long long)mdvc_num_sms() * 16 ? tiles : (long long)mdvc_num_sms() * 16);
         k_tile_pairs<<<tgrid, 2 * PT_TY, 0, st>>>(bits, D, h, at<uint32_t>(ws, L.rowoff), at<uint8_t>(ws, L.rowpol), at<uint32_t>(ws, L.runstart),
                                             at<int32_t>(ws, L.lab), cset, caps->contact_slots, bset,
                                             caps->bridge_slots, periodic);

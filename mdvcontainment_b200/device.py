@@ -43,6 +43,8 @@ class BitGrid:
             raise ValueError(f"grid must be a non-empty 3D array, got shape {self.shape}")
         if int(np.prod(self.shape, dtype=np.int64)) >= 2 ** 31:
             raise ValueError("grids with >= 2^31 voxels need slab decomposition")
+        if self.shape[2] >= 1 << 24:
+            raise ValueError("rows of >= 2^24 voxels are not supported (run z-starts are packed into 24 bits)")
         self.pitch = pitch_words(self.shape[2])
         if words is None:
             words = torch.zeros((self.shape[0], self.shape[1], self.pitch), dtype=torch.int32,

@@ -20,11 +20,61 @@ from .atomgroup_to_voxels import voxel_transform
 
 
 class FrameOutput:
-    __slots__ = ("containment_graph", "component_ranks", "voxel_counts", "contacts", "bridges", "n_true", "n_false",
-                 "labels_dev", "components_dev", "bits", "timings")
+    """Result of one frame.  ``labels_dev`` / ``components_dev`` / ``bits`` are LEASED views of the pipeline's reusable
+    device buffers: they are valid until the next ``begin()`` / ``run()`` on the same pipeline overwrites them.  Call
+    ``own()`` to detach private copies (8 B/voxel more HBM) when a result has to outlive the next frame.
+
+    The graph results are held as arrays (``dag``: host_graph.CompactDAG, ``solution``: host_graph.PeriodicSolution,
+    ``count_ids`` / ``count_values``); the reference's forms -- ``containment_graph`` (networkx MultiDiGraph),
+    ``component_ranks`` and ``voxel_counts`` (dicts) -- are built on first access."""
+
+    def __init__(self):
+        self.dag = self.solution = self.count_ids = self.count_values = None
+        self.contacts = self.bridges = None
+        self.n_true = self.n_false = 0
+        self.labels_dev = self.components_dev = self.bits = None
+        self.timings = {}
+        self._graph = self._ranks = self._counts = None
+
+    @property
+    def containment_graph(self):
+        if self._graph is None:
+            self._graph = self.dag.to_networkx().copy()       # the caller owns its graph; the pipeline memoises the DAG
+        return self._graph
+
+    @property
+    def component_ranks(self):
+        if self._ranks is None:
+            self._ranks = dict(self.solution["component_ranks"])
+        return self._ranks
+
+    @property
+    def voxel_counts(self):
+        if self._counts is None:
+            self._counts = {np.int32(k): np.int64(v) for k, v in zip(self.count_ids.tolist(), self.count_values.tolist())}
+        return self._counts
 
     def __str__(self):
-        return hg.format_dag_structure(self.containment_graph, self.component_ranks, self.voxel_counts)
+        return hg.format_dag_structure(self.dag, self.component_ranks, self.voxel_counts)
+
+    def own(self):
+        """Replace the leased grids by private copies (device-to-device, on the current stream)."""
+        if self.labels_dev is not None:
+            self.labels_dev = self.labels_dev.clone()
+        if self.components_dev is not None:
+            self.components_dev = self.components_dev.clone()
+        if self.bits is not None:
+            self.bits = dev.BitGrid(self.bits.shape, self.bits.words.clone())
+        return self
+
+
+def _check_positions(positions_dev):
+    if positions_dev.dtype != torch.float32 or positions_dev.dim() != 2 or positions_dev.shape[1] != 3:
+        raise ValueError(f"positions must be float32 [n,3], got {positions_dev.dtype} {tuple(positions_dev.shape)}")
+    if not positions_dev.is_contiguous():
+        raise ValueError("positions must be contiguous")
+    if not positions_dev.is_cuda:
+        raise ValueError("positions_dev must be a CUDA tensor (pinned host positions go through host_positions=)")
 
 
 class FramePipeline:
@@ -35,9 +85,14 @@ class FramePipeline:
     HEAD_CONTACT_ROWS = 2048
     HEAD_BRIDGE_ROWS = 8192
     HEAD_VOLUMES = 8192
+    MAX_REGROW = 8
+    MEMO_SIZE = 32                      # memoised graph-stage solutions (0 switches the memo off)
 
     def __init__(self, dimensions, resolution, closing=True, morph="", periodic=True, max_atoms=0,
                  write_labels=True, device="cuda", use_graph=True):
+        if not periodic:
+            raise NotImplementedError("FramePipeline handles periodic frames; slab frames go through "
+                                      "VoxelContainment(slab=True)")
         self.device = torch.device(device)
         self.dimensions = np.asarray(dimensions, dtype=np.float32)
         self.resolution = resolution
@@ -66,6 +121,7 @@ class FramePipeline:
         self._bits = None
         self._rows_counted = False
         self._solved = {}                                         # memoised graph stage, see _finish
+        self.memo_lookups = self.memo_hits = 0
         self._lut_key = None                                      # key of the table currently in lut_dev
         self.use_graph = use_graph and os.environ.get("MDVC_PIPELINE_GRAPH", "1") != "0"
         self._graph = self._graph_bits = None
@@ -75,6 +131,20 @@ class FramePipeline:
         self._frames_seen = 0
 
     # ---------------------------------------------------------------------------------------
+    def set_dimensions(self, dimensions) -> bool:
+        """New box for the next frame (NPT trajectories: the reference recomputes the transform from
+        ``atomgroup.dimensions`` on every constructor, atomgroup_to_voxels.py:112-131).  Returns False -- and changes
+        nothing -- when the new box rounds to a different grid shape: the caller then needs another pipeline."""
+        dimensions = np.asarray(dimensions, dtype=np.float32)
+        if np.array_equal(dimensions, self.dimensions):
+            return True
+        _, nbox, T, invT = voxel_transform(dimensions, self.resolution)
+        if tuple(int(v) for v in np.diagonal(nbox)) != self.shape:
+            return False
+        self.dimensions, self.nbox, self.T, self.invT = dimensions, nbox, T, invT
+        self._graphs.clear()                                      # the captured launches hold the old transform by value
+        return True
+
     def _alloc_host(self):
         c = self.plan.caps
         self.n_head_c = min(self.HEAD_CONTACT_ROWS, c.contact_slots)
@@ -133,6 +203,12 @@ class FramePipeline:
         immediately so the caller can finish() another pipeline's frame meanwhile."""
         self._t0 = time.perf_counter()
         self.stream.wait_stream(self.stream_x)               # the previous frame's dense write still reads our buffers
+        # whatever produced positions_dev on the caller's stream (a unit conversion, .cuda(non_blocking=True)) must
+        # be complete before the binning reads it on this pipeline's side stream
+        self.stream.wait_stream(torch.cuda.current_stream(self.device))
+        if positions_dev is not None:
+            _check_positions(positions_dev)
+            positions_dev.record_stream(self.stream)         # the caching allocator must not recycle it under us
         with torch.cuda.stream(self.stream):
             if host_positions is not None:
                 n = host_positions.shape[0]
@@ -201,26 +277,28 @@ class FramePipeline:
     def analyse(self, bits: dev.BitGrid) -> FrameOutput:
         """label -> pairs -> (one sync) host graph -> LUT -> dense write, on the current stream."""
         self._t0 = time.perf_counter()
+        torch.cuda.current_stream(self.device).wait_stream(self.stream_x)   # a previous frame's dense write
         self._enqueue_stage1(bits)
         return self._finish(bits)
 
     def _finish(self, bits: dev.BitGrid) -> FrameOutput:
         t0 = self._t0
-        while True:
+        for attempt in range(self.MAX_REGROW + 1):
             self.ev_stage1.synchronize()
             hdr = self.h_header.numpy()
             total_runs, n_true, n_false, flags, n_c, n_b = (int(v) for v in hdr[:6].view(np.uint32))
             if flags == 0:
                 break
+            if attempt == self.MAX_REGROW:
+                raise _lib.MdvcError(f"frame workspace still overflowing after {attempt} regrows (flags={flags}, "
+                                     f"runs={total_runs}, labels={n_true + n_false}, contacts={n_c}, bridges={n_b})")
             h = _lib.FrameHeader(total_runs, n_true, n_false, flags, n_c, n_b, 0, 0)
             self._regrow(h)
             self._enqueue_stage1(bits)
         t1 = time.perf_counter()
         self.plan.header = _lib.FrameHeader(total_runs, n_true, n_false, 0, n_c, n_b, 0, 0)
         contacts = self.h_contacts.numpy()[:n_c].copy() if n_c <= self.n_head_c else self.plan.contacts()
-        if not self.periodic:
-            bridges = None
-        elif n_b <= self.n_head_b:
+        if n_b <= self.n_head_b:
             bridges = self.h_bridges.numpy()[:n_b].copy() if n_b else np.array([], dtype=np.int32)
         else:
             bridges = self.plan.bridges()
@@ -229,27 +307,24 @@ class FramePipeline:
         uniq = np.concatenate([np.arange(-n_false, 0, dtype=np.int32), np.arange(1, n_true + 1, dtype=np.int32)])
 
         out = FrameOutput()
-        if not self.periodic:
-            raise NotImplementedError("slab frames go through VoxelContainment(slab=True)")
         # The graph stage is a pure function of (label counts, contacts, bridges); consecutive trajectory frames almost
         # always repeat them (same topology, different volumes), so the solution and the label -> component table are
         # memoised (small LRU).  At 512^3 this host stage was most of a frame's wall-clock.
         key = (n_true, n_false, contacts.tobytes(), bridges.tobytes())
         hit = self._solved.get(key)
+        self.memo_lookups += 1
         if hit is None:
             sol = hg.solve_periodic(uniq, contacts, bridges)
-            c2l = sol["component2labels"]
-            lut = np.zeros(nl, dtype=np.int32)
-            for comp, labs in c2l.items():
-                lut[np.asarray(labs, dtype=np.int64) + n_false] = comp
-            unique_components = np.array(sorted(int(c) for c in c2l), dtype=np.int32)
-            dag = hg.containment_graph(sol["is_contained"], unique_components, sol["component_contact_graph"])
-            if len(self._solved) >= 32:
-                self._solved.pop(next(iter(self._solved)))
-            self._solved[key] = (sol, lut, unique_components, dag)
+            lut = sol.lut(n_false, n_true)
+            dag = sol.containment_dag(max_iterations=None)         # no 100 000-component guard on this path
+            if self.MEMO_SIZE:
+                if len(self._solved) >= self.MEMO_SIZE:
+                    self._solved.pop(next(iter(self._solved)))
+                self._solved[key] = (sol, lut, dag)
         else:
+            self.memo_hits += 1
             self._solved[key] = self._solved.pop(key)              # most recently used last
-            sol, lut, unique_components, dag = hit
+            sol, lut, dag = hit
         # LUT to the device and the single dense write
         if nl <= self.h_lut.numel():
             if self._lut_key != key:                               # same table as the previous frame: already on the device
@@ -269,12 +344,8 @@ class FramePipeline:
             e1.record()
         self.expand_events.append((e0, e1))
         t2 = time.perf_counter()
-        lo = int(lut.min())
-        acc = np.zeros(int(lut.max()) - lo + 1, dtype=np.int64)
-        np.add.at(acc, lut.astype(np.int64) - lo, volumes)
-        out.voxel_counts = {np.int32(lo + k): np.int64(v) for k, v in enumerate(acc) if v}
-        out.containment_graph = dag.copy()                        # the caller owns its graph; the memo keeps the original
-        out.component_ranks = dict(sol["component_ranks"])
+        out.count_ids, out.count_values = hg.counts_by_component(lut, volumes)
+        out.dag, out.solution = dag, sol
         out.contacts, out.bridges, out.n_true, out.n_false = contacts, bridges, n_true, n_false
         out.labels_dev, out.components_dev, out.bits = self.labels, self.components, bits
         out.timings = {"device_label_pairs_s": t1 - t0, "host_lut_s": t2 - t1, "host_dag_s": time.perf_counter() - t2}

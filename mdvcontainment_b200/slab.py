@@ -66,63 +66,46 @@ def merge_slabs(n_true, n_false, boundary_rows, local_contacts, local_bridges, l
 
     Returns dict(luts=[int32 arrays, index = local label + n_false[g] -> global label], n_true, n_false,
     contacts int32 [K,2], bridges int32 [K,5] (shape (0,) when empty), volumes int64)."""
+    from . import host_graph as hg
     G = len(n_true)
-    parent = {}
+    nt = np.asarray([int(v) for v in n_true], dtype=np.int64)
+    nf = np.asarray([int(v) for v in n_false], dtype=np.int64)
+    # one node per (slab, local label), positives first, each polarity in (slab, |label|) order: the smallest node
+    # index of a merged group is then the group's first voxel in C order, which is the root the union-find keeps
+    base_pos = np.concatenate([[0], np.cumsum(nt)])
+    base_neg = base_pos[-1] + np.concatenate([[0], np.cumsum(nf)])
+    n_nodes = int(base_neg[-1])
 
-    def find(k):
-        root = k
-        while parent.setdefault(root, root) != root:
-            root = parent[root]
-        while parent[k] != root:
-            parent[k], k = root, parent[k]
-        return root
+    def node(g, lab):
+        lab = np.asarray(lab, dtype=np.int64)
+        return np.where(lab > 0, base_pos[g] + lab - 1, base_neg[g] - lab - 1)
 
+    eu, ev = [], []
     for g in range(G):
         rows = np.asarray(boundary_rows[g]).reshape(-1, 5)
         h = (g + 1) % G
-        inbox = ~rows[:, 2:].any(axis=1)
-        for la, lb in rows[inbox][:, :2].tolist():
-            if (la > 0) == (lb > 0):                       # same value on both sides of an in-box step: one label
-                ra, rb = find((g, la)), find((h, lb))
-                if ra != rb:
-                    # the smaller (slab, |label|) stays root = the group's first voxel in C order
-                    if (ra[0], abs(ra[1])) > (rb[0], abs(rb[1])):
-                        ra, rb = rb, ra
-                    parent[rb] = ra
-    nonrep = [[[], []] for _ in range(G)]                  # [g][0]: positive locals merged away, [g][1]: |negative|
-    rep_of = {}
-    for k in list(parent):
-        r = find(k)
-        if r != k:
-            nonrep[k[0]][0 if k[1] > 0 else 1].append(abs(k[1]))
-            rep_of[k] = r
-
-    luts, base_pos, base_neg = [], 0, 0
-    pos_tab, neg_tab = [], []                               # per slab: global number of local label k (k = 1..n)
+        # same value on both sides of an in-box step: one label
+        join = ~rows[:, 2:].any(axis=1) & ((rows[:, 0] > 0) == (rows[:, 1] > 0))
+        if join.any():
+            eu.append(node(g, rows[join, 0])); ev.append(node(h, rows[join, 1]))
+    if eu:
+        root, _, _ = hg.shift_graph_ranks(n_nodes, np.concatenate(eu), np.concatenate(ev))
+        root = root.astype(np.int64)
+    else:
+        root = np.arange(n_nodes, dtype=np.int64)
+    is_root = root == np.arange(n_nodes)
+    NT = int(is_root[:base_pos[-1]].sum())
+    NF = int(is_root[base_pos[-1]:].sum())
+    number = np.empty(n_nodes, dtype=np.int64)                   # global |label| of every node
+    number[:base_pos[-1]] = np.cumsum(is_root[:base_pos[-1]])
+    number[base_pos[-1]:] = np.cumsum(is_root[base_pos[-1]:])
+    number = number[root]                                        # merged-away labels take their representative's number
+    luts = []
     for g in range(G):
-        tabs = []
-        for sign_idx, (n, base) in enumerate(((int(n_true[g]), base_pos), (int(n_false[g]), base_neg))):
-            gone = np.zeros(n + 1, dtype=np.int64)
-            if nonrep[g][sign_idx]:
-                gone[np.asarray(nonrep[g][sign_idx], dtype=np.int64)] = 1
-            k = np.arange(n + 1, dtype=np.int64)
-            tab = base + k - np.cumsum(gone)                # valid for representatives; fixed below for the others
-            tabs.append((tab, gone))
-        pos_tab.append(tabs[0]); neg_tab.append(tabs[1])
-        base_pos += int(n_true[g]) - len(nonrep[g][0])
-        base_neg += int(n_false[g]) - len(nonrep[g][1])
-    for (g, l), (rg, rl) in rep_of.items():                 # merged-away labels take their representative's number
-        if l > 0:
-            pos_tab[g][0][l] = pos_tab[rg][0][rl]
-        else:
-            neg_tab[g][0][-l] = neg_tab[rg][0][-rl]
-    for g in range(G):
-        nt, nf = int(n_true[g]), int(n_false[g])
-        lut = np.zeros(nf + nt + 1, dtype=np.int32)
-        lut[nf + 1:] = pos_tab[g][0][1:]
-        lut[:nf] = -neg_tab[g][0][1:][::-1]                 # index 0 is local label -nf
+        lut = np.zeros(int(nf[g] + nt[g]) + 1, dtype=np.int32)
+        lut[int(nf[g]) + 1:] = number[base_pos[g]:base_pos[g + 1]]
+        lut[:int(nf[g])] = -number[base_neg[g]:base_neg[g + 1]][::-1]      # index 0 is local label -nf
         luts.append(lut)
-    NT, NF = base_pos, base_neg
 
     contacts, bridges = [], []
     volumes = np.zeros(NF + NT + 1, dtype=np.int64)
@@ -135,7 +118,7 @@ def merge_slabs(n_true, n_false, boundary_rows, local_contacts, local_bridges, l
         b = np.asarray(local_bridges[g]).reshape(-1, 5).astype(np.int64)
         if len(b):
             bridges.append(_normalise_bridges(lut[b[:, 0] + nf], lut[b[:, 1] + nf], b[:, 2:]))
-        np.add.at(volumes, lut.astype(np.int64) + NF, np.asarray(local_volumes[g], dtype=np.int64))
+        volumes += hg.sum_by_index(lut.astype(np.int64) + NF, local_volumes[g], NF + NT + 1)
         rows = np.asarray(boundary_rows[g]).reshape(-1, 5).astype(np.int64)
         if len(rows):
             h = (g + 1) % G
@@ -200,12 +183,37 @@ class DistGather:
 
 
 class SlabResult:
-    __slots__ = ("containment_graph", "component_ranks", "voxel_counts", "contacts", "bridges", "n_true", "n_false",
-                 "labels", "components", "extents", "merge")
+    """Like pipeline.FrameOutput: arrays first (``dag``, ``solution``, ``count_ids`` / ``count_values``), the
+    reference's networkx / dict forms on first access."""
+
+    def __init__(self):
+        self.dag = self.solution = self.count_ids = self.count_values = None
+        self.contacts = self.bridges = None
+        self.n_true = self.n_false = 0
+        self.labels = self.components = self.extents = self.merge = None
+        self._graph = self._ranks = self._counts = None
+
+    @property
+    def containment_graph(self):
+        if self._graph is None:
+            self._graph = self.dag.to_networkx()
+        return self._graph
+
+    @property
+    def component_ranks(self):
+        if self._ranks is None:
+            self._ranks = self.solution["component_ranks"]
+        return self._ranks
+
+    @property
+    def voxel_counts(self):
+        if self._counts is None:
+            self._counts = {np.int32(k): np.int64(v) for k, v in zip(self.count_ids.tolist(), self.count_values.tolist())}
+        return self._counts
 
     def __str__(self):
         from . import host_graph as hg
-        return hg.format_dag_structure(self.containment_graph, self.component_ranks, self.voxel_counts)
+        return hg.format_dag_structure(self.dag, self.component_ranks, self.voxel_counts)
 
 
 def _plane_pairs(dev, plane_a, plane_b, sx_boundary, n_slots=1 << 12):
@@ -306,19 +314,13 @@ def analyse_slabs(slab_bits: dict, shape, gather=None, morph_ops: str = "", want
     NT, NF = merged["n_true"], merged["n_false"]
     uniq = np.concatenate([np.arange(-NF, 0, dtype=np.int32), np.arange(1, NT + 1, dtype=np.int32)])
     sol = hg.solve_periodic(uniq, merged["contacts"], merged["bridges"])
-    c2l = sol["component2labels"]
-    comp_lut = np.zeros(NF + NT + 1, dtype=np.int32)
-    for comp, labs in c2l.items():
-        comp_lut[np.asarray(labs, dtype=np.int64) + NF] = comp
-    unique_components = np.array(sorted(int(c) for c in c2l), dtype=np.int32)
+    comp_lut = sol.lut(NF, NT)
 
     res = SlabResult()
-    lo_c = int(comp_lut.min())
-    acc = np.zeros(int(comp_lut.max()) - lo_c + 1, dtype=np.int64)
-    np.add.at(acc, comp_lut.astype(np.int64) - lo_c, merged["volumes"])
-    res.voxel_counts = {np.int32(lo_c + k): np.int64(v) for k, v in enumerate(acc) if v}
-    res.containment_graph = hg.containment_graph(sol["is_contained"], unique_components, sol["component_contact_graph"])
-    res.component_ranks = sol["component_ranks"]
+    res.count_ids, res.count_values = hg.counts_by_component(comp_lut, merged["volumes"])
+    # grids beyond the reference's reach (it raises at >= 2^31 voxels and gives up orienting more than 100 000
+    # components): no guard here
+    res.dag, res.solution = sol.containment_dag(max_iterations=None), sol
     res.contacts, res.bridges, res.n_true, res.n_false = merged["contacts"], merged["bridges"], NT, NF
     res.extents, res.merge = ext, merged
 

@@ -6,6 +6,9 @@ communication is gathering the tiny per-frame results on rank 0.
 
 ``frames`` is an indexable of float32 [n,3] position arrays (A) -- or a callable ``f -> positions`` plus
 ``n_frames`` -- and ``results[f]`` is a dict with the frame's DAG text, nodes, edges, ranks and voxel counts.
+``dimensions`` is one float32[6] box for the whole trajectory (NVT), a [n_frames, 6] array, or a callable
+``f -> float32[6]`` (NPT: the box -- and with it the transform, possibly the grid shape -- changes per frame, as in
+the reference, which reads ``atomgroup.dimensions`` in every constructor).
 """
 from __future__ import annotations
 
@@ -22,13 +25,12 @@ def frames_of_rank(n_frames: int, rank: int, world: int):
 
 def summarise(out) -> dict:
     """Small, picklable summary of a FrameOutput."""
-    g = out.containment_graph
     return {
         "str": str(out),
-        "nodes": [int(n) for n in g.nodes],
-        "edges": [(int(a), int(b)) for a, b in g.edges()],
+        "nodes": out.dag.nodes.tolist(),
+        "edges": out.dag.edges(),
         "ranks": {int(k): int(v) for k, v in out.component_ranks.items()},
-        "counts": {int(k): int(v) for k, v in out.voxel_counts.items()},
+        "counts": {int(k): int(v) for k, v in zip(out.count_ids.tolist(), out.count_values.tolist())},
     }
 
 
@@ -45,6 +47,49 @@ def gather_results(local: dict, n_frames: int, rank: int, world: int):
     for part in parts:
         merged.update(part)
     return [merged[f] for f in range(n_frames)]
+
+
+def dimensions_of_frame(dimensions, f: int) -> np.ndarray:
+    """Box of frame ``f`` from a fixed box, a per-frame array or a callable."""
+    if callable(dimensions):
+        d = dimensions(f)
+    else:
+        d = np.asarray(dimensions, dtype=np.float32)
+        if d.ndim == 2:
+            d = d[f]
+    d = np.asarray(d, dtype=np.float32).reshape(-1)
+    if d.shape != (6,):
+        raise ValueError(f"dimensions of frame {f} must be 6 numbers (lengths in A, angles in degrees), got {d.shape}")
+    return d
+
+
+class _PipelinePool:
+    """``depth`` FramePipelines per grid shape (at most ``max_shapes`` shapes alive: an NPT box that hovers around a
+    rounding boundary alternates between two shapes); a box change that keeps the shape only updates the transform."""
+
+    def __init__(self, resolution, closing, morph, depth, max_shapes=2):
+        self.args = (resolution, closing, morph)
+        self.depth, self.max_shapes = depth, max_shapes
+        self.by_shape = {}                                      # shape -> [pipelines]
+
+    def get(self, slot: int, dims: np.ndarray):
+        from .atomgroup_to_voxels import voxel_transform
+        from .pipeline import FramePipeline
+        resolution, closing, morph = self.args
+        _, nbox, _, _ = voxel_transform(dims, resolution)
+        shape = tuple(int(v) for v in np.diagonal(nbox))
+        pipes = self.by_shape.get(shape)
+        if pipes is None:
+            while len(self.by_shape) >= self.max_shapes:        # oldest shape goes (its frames are finished by now)
+                self.by_shape.pop(next(iter(self.by_shape)))
+            pipes = self.by_shape[shape] = [None] * self.depth
+        else:
+            self.by_shape[shape] = self.by_shape.pop(shape)      # most recently used last
+        if pipes[slot] is None:
+            pipes[slot] = FramePipeline(dims, resolution, closing=closing, morph=morph)
+        elif not pipes[slot].set_dimensions(dims):
+            raise AssertionError("shape bookkeeping out of sync")
+        return pipes[slot]
 
 
 def run_trajectory(frames, dimensions, resolution, closing=True, morph="", n_frames=None,
@@ -66,24 +111,36 @@ def run_trajectory(frames, dimensions, resolution, closing=True, morph="", n_fra
         return gather_results(local, n_frames, rank, world)
 
     import torch
-    from .pipeline import FramePipeline
     torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
     depth = max(1, min(int(in_flight), len(mine) or 1))
-    pipes = [FramePipeline(dimensions, resolution, closing=closing, morph=morph) for _ in range(depth)]
+    pool = _PipelinePool(resolution, closing, morph, depth)
     pins = [None] * depth
     local, pending = {}, []
     for k, f in enumerate(mine):
         i = k % depth
         if len(pending) == depth:                       # the oldest frame in flight is the one that used slot i
-            f0, i0 = pending.pop(0)
-            local[f0] = summarise(pipes[i0].finish())
+            f0, p0 = pending.pop(0)
+            local[f0] = summarise(p0.finish())
         pos = torch.from_numpy(np.ascontiguousarray(get(f), dtype=np.float32).reshape(-1, 3))
         n = pos.shape[0]
         if pins[i] is None or pins[i].shape[0] < n:
             pins[i] = torch.empty((max(n, 1), 3), dtype=torch.float32, pin_memory=True)
         pins[i][:n].copy_(pos)
-        pipes[i].begin(None, host_positions=pins[i][:n])
-        pending.append((f, i))
-    for f0, i0 in pending:
-        local[f0] = summarise(pipes[i0].finish())
+        dims = dimensions_of_frame(dimensions, f)
+        # a pipeline of a shape that is about to be evicted may still have a frame in flight: drain first
+        if _shape_of(dims, resolution) not in pool.by_shape and len(pool.by_shape) >= pool.max_shapes:
+            for f0, p0 in pending:
+                local[f0] = summarise(p0.finish())
+            pending = []
+        pipe = pool.get(i, dims)
+        pipe.begin(None, host_positions=pins[i][:n])
+        pending.append((f, pipe))
+    for f0, p0 in pending:
+        local[f0] = summarise(p0.finish())
     return gather_results(local, n_frames, rank, world)
+
+
+def _shape_of(dims, resolution):
+    from .atomgroup_to_voxels import voxel_transform
+    _, nbox, _, _ = voxel_transform(dims, resolution)
+    return tuple(int(v) for v in np.diagonal(nbox))

@@ -268,3 +268,77 @@ def voxels_to_universe(grid, resolution_nm=1.0) -> Universe:
     names = [str(v) for v in grid.reshape(-1)]
     dims = np.array([s * 10.0 * resolution_nm for s in grid.shape] + [90, 90, 90], dtype=np.float32)
     return Universe(pos.astype(np.float32), dims, names)
+
+
+def voxels_to_gro(path, arr, scale=1.0, place_in_center=True, universe=None):
+    """Debug dump of a voxel grid as a ``.gro`` with one pseudo-atom per voxel, atom name = str(value) -- the
+    behaviour of the reference's ``voxels_to_gro`` (``voxels_to_gro.py:6-40``): voxel edge = ``scale`` nm, or the
+    universe's box divided by the grid shape when a universe is given; atoms in the voxel centre when
+    ``place_in_center``; box = shape * edge, truncated to whole Angstrom like the reference's int32 cast (``:32``)."""
+    arr = np.asarray(arr)
+    edge = np.full(3, scale * 10.0) if universe is None else np.asarray(universe.dimensions[:3], dtype=np.float64) / arr.shape
+    idx = np.indices(arr.shape).reshape(3, -1).T.astype(np.float64)
+    pos = idx * edge + (edge / 2 if place_in_center else 0.0)
+    dims = np.array([*(np.array(arr.shape) * edge), 90, 90, 90]).astype(np.int32).astype(np.float32)
+    n = len(pos)
+    write_gro(path, Universe(pos.astype(np.float32), dims, [str(v) for v in arr.reshape(-1)], ["UNK"] * n))
+
+
+# ---------------------------------------------------------------------------
+# .pdb I/O (fixed columns; Angstrom on disk and in memory).  Only what the voxel path needs: CRYST1 box,
+# ATOM/HETATM names, residue names/ids, coordinates and the temperature factor column that
+# ``Containment.set_betafactors`` fills (mda_containment.py:179-220).
+# ---------------------------------------------------------------------------
+def read_pdb(path) -> Universe:
+    pos, names, resnames, resids, temps = [], [], [], [], []
+    dims = None
+    with open(path) as fh:
+        for ln in fh:
+            rec = ln[:6]
+            if rec == "CRYST1":
+                dims = np.array([float(ln[6:15]), float(ln[15:24]), float(ln[24:33]),
+                                 float(ln[33:40]), float(ln[40:47]), float(ln[47:54])], dtype=np.float32)
+            elif rec in ("ATOM  ", "HETATM"):
+                names.append(ln[12:16].strip())
+                resnames.append(ln[17:21].strip())
+                rid = ln[22:26].strip()
+                resids.append(int(rid) if rid.lstrip("-").isdigit() else 0)
+                pos.append((float(ln[30:38]), float(ln[38:46]), float(ln[46:54])))
+                tf = ln[60:66].strip() if len(ln) >= 66 else ""
+                temps.append(float(tf) if tf else 0.0)
+            elif rec.startswith("ENDMDL"):
+                break                                   # first model only
+    if dims is None:
+        raise ValueError(f"{path}: no CRYST1 record (a periodic box is required)")
+    u = Universe(np.asarray(pos, dtype=np.float32).reshape(-1, 3), dims, names, resnames, resids)
+    u.add_TopologyAttr("tempfactors", np.asarray(temps, dtype=np.float64))
+    return u
+
+
+def write_pdb(path, universe_or_group, title="mdvcontainment_b200"):
+    ag = universe_or_group.atoms
+    pos, dims = ag.positions, ag.dimensions
+    try:
+        temps = ag.tempfactors
+    except AttributeError:
+        temps = np.zeros(len(ag))
+    with open(path, "w") as fh:
+        fh.write(f"TITLE     {title}\n")
+        fh.write("CRYST1%9.3f%9.3f%9.3f%7.2f%7.2f%7.2f P 1           1\n" % tuple(float(v) for v in dims))
+        for i in range(len(ag)):
+            name = str(ag.names[i])[:4]
+            name = name if len(name) == 4 else " " + name.ljust(3)
+            fh.write("ATOM  %5d %4s %-4s%1s%4d    %8.3f%8.3f%8.3f%6.2f%6.2f\n" % (
+                (i + 1) % 100000, name, str(ag.resnames[i])[:4], "X", int(ag.resids[i]) % 10000,
+                pos[i, 0], pos[i, 1], pos[i, 2], 1.0, float(temps[i])))
+        fh.write("END\n")
+
+
+def load(path) -> Universe:
+    """``Universe`` from a ``.gro`` or ``.pdb`` file (the stand-in for ``MDAnalysis.Universe(path)``)."""
+    p = str(path).lower()
+    if p.endswith(".gro"):
+        return read_gro(path)
+    if p.endswith(".pdb"):
+        return read_pdb(path)
+    raise ValueError(f"unsupported structure format: {path}")

@@ -39,13 +39,16 @@ def test_host_stage_matches_golden(name):
 def test_host_stage_matches_live_reference_on_random_grids(ref):
     from mdvcontainment.containment_main import calc_containment_graph
     rng = np.random.default_rng(77)
-    for k in range(120):
-        shape = tuple(int(v) for v in rng.integers(1, 11, 3))
-        g = rng.random(shape) < rng.choice([0.15, 0.35, 0.5, 0.65, 0.85])
+    for k in range(150):
+        hi = 11 if k < 120 else 19                      # the last ones have hundreds of labels
+        shape = tuple(int(v) for v in rng.integers(1, hi, 3))
+        g = rng.random(shape) < rng.choice([0.15, 0.35, 0.5, 0.65, 0.85] if k < 120 else [0.06, 0.15, 0.9])
         cg, ccg, comps_ref, ranks_ref, lcg = calc_containment_graph(g)
         labels, sol, comps, dag, counts = solve(g)
         assert np.array_equal(comps, comps_ref), shape
         assert list(dag.nodes) == list(cg.nodes) and list(dag.edges()) == list(cg.edges()), shape
+        fast = sol.containment_dag()
+        assert fast.nodes.tolist() == [int(n) for n in cg.nodes] and fast.edges() == [(int(u), int(v)) for u, v in cg.edges()]
         assert {int(a): int(b) for a, b in sol["component_ranks"].items()} == {int(a): int(b) for a, b in ranks_ref.items()}
         assert list(sol["component_ranks"]) == list(ranks_ref)
         assert list(sol["component_contact_graph"].nodes) == list(ccg.nodes)
@@ -55,9 +58,117 @@ def test_host_stage_matches_live_reference_on_random_grids(ref):
         assert [(u, v, str(d["label"])) for u, v, d in nxg.edges(data=True)] == [(u, v, str(d["label"])) for u, v, d in lcg.edges(data=True)]
 
 
-def test_integer_rank():
-    assert hg._int_rank([]) == 0
-    assert hg._int_rank([(0, 0, 1), (0, 0, -1)]) == 1
-    assert hg._int_rank([(1, 1, 0), (1, -1, 0), (2, 0, 0)]) == 2
-    assert hg._int_rank([(1, 0, 0), (0, 1, 0), (1, 1, 1)]) == 3
-    assert hg._int_rank([(2, 4, 6), (1, 2, 3)]) == 1
+def test_shift_graph_ranks_small_cases():
+    """mdvc_host_shift_graph_ranks on hand-made graphs: rank of the lattice of closed-walk shift sums."""
+    def ranks(n, edges):
+        eu = [e[0] for e in edges]; ev = [e[1] for e in edges]; es = [e[2] for e in edges]
+        root, rank, best = hg.shift_graph_ranks(n, eu, ev, es if edges else None)
+        return root.tolist(), rank.tolist(), best
+    assert ranks(3, []) == ([0, 1, 2], [0, 0, 0], 0)
+    # a self bridge through z in both directions: rank 1
+    assert ranks(1, [(0, 0, (0, 0, 1)), (0, 0, (0, 0, -1))])[1:] == ([1], 1)
+    # two labels joined through a face and back inside the box: the loop 0 -> 1 -> 0 sums to (1, 0, 0)
+    assert ranks(2, [(0, 1, (1, 0, 0)), (1, 0, (0, 0, 0))]) == ([0, 0], [1, 1], 1)
+    # the same joined twice with opposite shifts only: a tree plus its reverse, no net displacement
+    assert ranks(2, [(0, 1, (1, 0, 0)), (1, 0, (-1, 0, 0))]) == ([0, 0], [0, 0], 0)
+    # three independent loops on one node, a dependent fourth
+    loops = [(0, 0, (1, 1, 0)), (0, 0, (1, -1, 0)), (0, 0, (2, 0, 0))]
+    assert ranks(1, loops)[2] == 2
+    assert ranks(1, loops + [(0, 0, (1, 1, 1))])[2] == 3
+    assert ranks(1, [(0, 0, (2, 4, 6)), (0, 0, (1, 2, 3))])[2] == 1
+    # pieces are independent; skipped nodes cut the graph
+    edges = [(0, 1, (0, 0, 0)), (1, 2, (0, 1, 0)), (2, 0, (0, 0, 0)), (3, 4, (0, 0, 0))]
+    assert ranks(5, edges) == ([0, 0, 0, 3, 3], [1, 1, 1, 0, 0], 1)
+    root, rank, best = hg.shift_graph_ranks(5, [e[0] for e in edges], [e[1] for e in edges], [e[2] for e in edges],
+                                            skip=np.array([0, 1, 0, 0, 0], dtype=np.uint8))
+    assert root.tolist() == [0, -1, 0, 3, 3] and rank.tolist() == [0, -1, 0, 0, 0] and best == 0
+    # long chains keep exact potentials (path compression with offsets)
+    n = 5000
+    eu = list(range(n - 1)) + [n - 1]; ev = list(range(1, n)) + [0]
+    es = [(1, 0, 0)] * (n - 1) + [(0, 0, 0)]
+    assert hg.shift_graph_ranks(n, eu, ev, es)[2] == 1
+    es[-1] = (-(n - 1), 0, 0)
+    assert hg.shift_graph_ranks(n, eu, ev, es)[2] == 0
+
+
+def test_view_order_is_what_networkx_iterates():
+    """The numbering of the minority polarity follows the iteration order of a node-filtered networkx view."""
+    import networkx as nx
+    rng = np.random.default_rng(1)
+    for n_neg, n_pos in [(1, 1), (3, 1), (1, 9), (5, 40), (40, 5), (300, 100), (7, 7), (2000, 30), (17, 5000), (0, 4), (4, 0)]:
+        labels = np.concatenate([np.arange(-n_neg, 0), np.arange(1, n_pos + 1)]).astype(np.int32)
+        g = nx.MultiDiGraph()
+        g.add_nodes_from(int(v) for v in labels)
+        for sub in (labels[labels > 0], labels[labels < 0]):
+            want = [int(v) for v in g.subgraph(sub)]
+            got = sub[hg._view_order(len(labels), sub.astype(np.int64))].tolist()
+            assert got == want, (n_neg, n_pos)
+    # arbitrary (non-contiguous) label values
+    vals = np.unique(rng.integers(-5000, 5000, 600)).astype(np.int32)
+    vals = vals[vals != 0]
+    g = nx.MultiDiGraph()
+    g.add_nodes_from(int(v) for v in vals)
+    for sub in (vals[vals > 0][:50], vals[vals < 0][:37]):
+        assert sub[hg._view_order(len(vals), sub.astype(np.int64))].tolist() == [int(v) for v in g.subgraph(sub)]
+
+
+def _compare_with_model(grid):
+    import host_graph_model as model
+    labels = vo.label_3d_grid(grid).astype(np.int32)
+    uniq = np.unique(labels)
+    contacts, bridges = vo.find_label_contacts_c(labels), vo.find_bridges_c(labels)
+    sol = hg.solve_periodic(uniq, contacts, bridges)
+    ref = model.solve_periodic(uniq, contacts, bridges)
+    assert {int(k): v for k, v in sol["component2labels"].items()} == {int(k): v for k, v in ref["component2labels"].items()}
+    assert list(sol["component2labels"]) == list(ref["component2labels"])
+    assert sol["component_ranks"] == ref["component_ranks"] and sol["complement_ranks"] == ref["complement_ranks"]
+    assert sol["is_contained"] == ref["is_contained"]
+    a, b = sol["component_contact_graph"], ref["component_contact_graph"]
+    assert list(a.nodes) == list(b.nodes)
+    assert [list(a.neighbors(n)) for n in a.nodes] == [list(b.neighbors(n)) for n in b.nodes]
+    nf = int(max(-labels.min(), 0)); nt = int(max(labels.max(), 0))
+    lut = sol.lut(nf, nt)
+    for comp, labs in ref["component2labels"].items():
+        assert (lut[np.asarray(labs) + nf] == comp).all()
+    comps = np.unique(lut[lut != 0]) if (lut != 0).any() else np.array([], dtype=np.int32)
+    want = model.containment_graph(ref["is_contained"], comps.astype(np.int32), ref["component_contact_graph"])
+    dag = sol.containment_dag()
+    assert dag.nodes.tolist() == [int(n) for n in want.nodes]
+    assert dag.edges() == [(int(u), int(v)) for u, v in want.edges()]
+    nxd = dag.to_networkx()
+    assert list(nxd.nodes) == list(want.nodes) and list(nxd.edges()) == list(want.edges())
+    counts = {int(c): 1 for c in comps}
+    assert hg.format_dag_structure(dag, sol["component_ranks"], counts) == \
+        model.format_dag_structure(want, ref["component_ranks"], counts)
+    return len(uniq)
+
+
+def test_array_solver_matches_the_plain_python_model_on_many_label_grids():
+    rng = np.random.default_rng(5)
+    seen = 0
+    for shape, p in [((24, 24, 24), 0.05), ((24, 24, 24), 0.12), ((20, 26, 22), 0.3), ((16, 16, 40), 0.5),
+                     ((30, 12, 18), 0.7), ((22, 22, 22), 0.93), ((9, 40, 11), 0.2), ((32, 32, 8), 0.08), ((48, 48, 48), 0.04)]:
+        seen = max(seen, _compare_with_model(rng.random(shape) < p))
+    assert seen > 2000                                 # the cases really have many labels
+    from mdvcontainment_b200 import synth
+    _compare_with_model(synth.salt_noise_grid((40, 24, 72), salt=0.05, seed=6))
+
+
+def test_orientation_guard_and_level_sweep():
+    """More than 100 000 components: the reference's orientation loop asserts; with the guard lifted (slab path) the
+    level sweep gives a valid spanning forest of the same contact graph."""
+    n = 100_500
+    # one big positive label (1) touching n isolated negative labels, plus a negative background in contact with it
+    contacts = np.stack([np.arange(-n - 1, 0), np.ones(n + 1, dtype=np.int64)], 1).astype(np.int32)
+    bridges = np.array([[-(n + 1), -(n + 1), s, 0, 0] for s in (-1, 1)] + [[-(n + 1), -(n + 1), 0, s, 0] for s in (-1, 1)] +
+                       [[-(n + 1), -(n + 1), 0, 0, s] for s in (-1, 1)], dtype=np.int32)
+    uniq = np.concatenate([np.arange(-n - 1, 0), [1]]).astype(np.int32)
+    sol = hg.solve_periodic(uniq, contacts, bridges)
+    assert int(sol.comp_rank.max()) == 3 and int(sol.contained.sum()) == n + 1
+    with pytest.raises(AssertionError, match="iterative death"):
+        sol.containment_dag()
+    dag = sol.containment_dag(max_iterations=None)
+    assert len(dag) == n + 2 and len(dag.edge_src) == n + 1
+    assert len(dag.roots()) == 1
+    kids = dag.children()
+    assert len(kids[dag.roots()[0]]) == 1 and len(kids[1]) == n
