@@ -459,3 +459,16 @@ class AtomCSR:
         out = torch.empty(total, dtype=torch.int64, device=dev_)
         check(lib.mdvc_atom_gather_voxels(*args, _ptr(out), total, _ptr(n_out), _stream()), "mdvc_atom_gather_voxels")
         return to_numpy(out)
+
+
+def tensor_digest(t: torch.Tensor, offset: int = 0, chunk: int = 1 << 26) -> int:
+    """Order-dependent 64-bit checksum of an integer / bool tensor on its own device:
+    sum(value[i] * ((offset + i) mod 1000003 + 1)) in wrapping int64 arithmetic, so partial digests of the slabs of a
+    grid (``offset`` = the slab's first flat index) add up (mod 2^64) to the digest of the whole grid."""
+    flat = t.reshape(-1)
+    acc = torch.zeros((), dtype=torch.int64, device=flat.device)
+    for s in range(0, flat.numel(), chunk):
+        part = flat[s:s + chunk].to(torch.int64)
+        w = torch.arange(offset + s, offset + s + part.numel(), device=flat.device, dtype=torch.int64) % 1000003 + 1
+        acc += (part * w).sum()
+    return int(acc.item())

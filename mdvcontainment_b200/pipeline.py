@@ -87,6 +87,7 @@ class FramePipeline:
     HEAD_VOLUMES = 8192
     MAX_REGROW = 8
     MEMO_SIZE = 32                      # memoised graph-stage solutions (0 switches the memo off)
+    ATOM_QUANTUM = 1 << 16              # host-fed frames are padded to a multiple of this many beads
 
     def __init__(self, dimensions, resolution, closing=True, morph="", periodic=True, max_atoms=0,
                  write_labels=True, device="cuda", use_graph=True):
@@ -107,7 +108,8 @@ class FramePipeline:
         self.plan = dev.FramePlan(self.shape, device=self.device)
         self.labels = torch.empty(self.shape, dtype=torch.int32, device=self.device) if write_labels else None
         self.components = torch.empty(self.shape, dtype=torch.int32, device=self.device)
-        self.pos_dev = torch.empty((max_atoms, 3), dtype=torch.float32, device=self.device) if max_atoms else None
+        cap = -(-int(max_atoms) // self.ATOM_QUANTUM) * self.ATOM_QUANTUM
+        self.pos_dev = torch.empty((cap, 3), dtype=torch.float32, device=self.device) if max_atoms else None
         self.lut_dev = None
         self.lib = _lib.load()
         self._alloc_host()
@@ -211,11 +213,19 @@ class FramePipeline:
             positions_dev.record_stream(self.stream)         # the caching allocator must not recycle it under us
         with torch.cuda.stream(self.stream):
             if host_positions is not None:
-                n = host_positions.shape[0]
-                if self.pos_dev is None or self.pos_dev.shape[0] < n:
-                    self.pos_dev = torch.empty((n, 3), dtype=torch.float32, device=self.device)
+                # Frames of a trajectory differ in their bead count (selections, breathing shells): the count is a launch
+                # parameter of the captured stage-1 graph, so it is rounded up to a multiple of ATOM_QUANTUM and the tail
+                # filled with copies of bead 0 (binning a bead twice sets the same bit) -- a handful of graphs instead
+                # of one capture per frame.
+                n = int(host_positions.shape[0])
+                n_pad = -(-n // self.ATOM_QUANTUM) * self.ATOM_QUANTUM if n else 0
+                if self.pos_dev is None or self.pos_dev.shape[0] < n_pad:
+                    self.pos_dev = torch.empty((n_pad, 3), dtype=torch.float32, device=self.device)
+                    self._graphs.clear()                          # captured against the old buffer
                 self.pos_dev[:n].copy_(host_positions, non_blocking=True)
-                positions_dev = self.pos_dev[:n]
+                if n_pad > n:
+                    self.pos_dev[n:n_pad] = self.pos_dev[0]
+                positions_dev = self.pos_dev[:n_pad]
             if not self._run_graph(positions_dev):
                 self._bits = self.voxelize(positions_dev)
                 self._enqueue_stage1(self._bits, self._rows_counted)

@@ -63,7 +63,7 @@ def dimensions_of_frame(dimensions, f: int) -> np.ndarray:
     return d
 
 
-class _PipelinePool:
+class PipelinePool:
     """``depth`` FramePipelines per grid shape (at most ``max_shapes`` shapes alive: an NPT box that hovers around a
     rounding boundary alternates between two shapes); a box change that keeps the shape only updates the transform."""
 
@@ -71,6 +71,10 @@ class _PipelinePool:
         self.args = (resolution, closing, morph)
         self.depth, self.max_shapes = depth, max_shapes
         self.by_shape = {}                                      # shape -> [pipelines]
+
+    def memo_counters(self):
+        pipes = [p for ps in self.by_shape.values() for p in ps if p is not None]
+        return sum(p.memo_lookups for p in pipes), sum(p.memo_hits for p in pipes)
 
     def get(self, slot: int, dims: np.ndarray):
         from .atomgroup_to_voxels import voxel_transform
@@ -93,13 +97,17 @@ class _PipelinePool:
 
 
 def run_trajectory(frames, dimensions, resolution, closing=True, morph="", n_frames=None,
-                   frame_fn: Callable | None = None, in_flight: int = 3):
+                   frame_fn: Callable | None = None, in_flight: int = 3, stats: dict | None = None,
+                   bind_numa: bool = True, pool: "PipelinePool | None" = None):
     """Process every frame of a trajectory, sharded over the ranks of the current process group.
 
     Default (CUDA): ``in_flight`` FramePipelines per rank, each with its own streams and a reusable pinned staging
     buffer, so that the copy / device stages of frame f+1.. overlap the host graph stage of frame f.
+    A frame that already is a pinned float32 torch tensor is copied to the device straight from where it lies.
     ``frame_fn(positions) -> summary dict`` replaces all of that; tests inject a CPU function to exercise the
-    sharding/gathering logic without a GPU."""
+    sharding/gathering logic without a GPU.  ``stats`` (a dict) receives this rank's frame count and the hit rate of
+    the memoised host graph stage.  ``pool`` (a ``PipelinePool`` made with the same resolution / closing / morph) keeps
+    the pipelines -- device buffers, captured CUDA graphs, memoised graph stages -- alive across calls."""
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if n_frames is None:
@@ -111,9 +119,20 @@ def run_trajectory(frames, dimensions, resolution, closing=True, morph="", n_fra
         return gather_results(local, n_frames, rank, world)
 
     import torch
-    torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
-    depth = max(1, min(int(in_flight), len(mine) or 1))
-    pool = _PipelinePool(resolution, closing, morph, depth)
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    if bind_numa:                                       # before the pinned staging buffers are allocated
+        from .topology import bind_to_gpu
+        placement = bind_to_gpu(local_rank)
+        if stats is not None:
+            stats["placement"] = placement
+    if pool is None:
+        depth = max(1, min(int(in_flight), len(mine) or 1))
+        pool = PipelinePool(resolution, closing, morph, depth)
+    elif pool.args != (resolution, closing, morph):
+        raise ValueError("the pipeline pool was made for another resolution / closing / morph")
+    depth = pool.depth
+    memo0 = pool.memo_counters()
     pins = [None] * depth
     local, pending = {}, []
     for k, f in enumerate(mine):
@@ -121,11 +140,16 @@ def run_trajectory(frames, dimensions, resolution, closing=True, morph="", n_fra
         if len(pending) == depth:                       # the oldest frame in flight is the one that used slot i
             f0, p0 = pending.pop(0)
             local[f0] = summarise(p0.finish())
-        pos = torch.from_numpy(np.ascontiguousarray(get(f), dtype=np.float32).reshape(-1, 3))
-        n = pos.shape[0]
-        if pins[i] is None or pins[i].shape[0] < n:
-            pins[i] = torch.empty((max(n, 1), 3), dtype=torch.float32, pin_memory=True)
-        pins[i][:n].copy_(pos)
+        raw = get(f)
+        if isinstance(raw, torch.Tensor) and raw.is_pinned() and raw.dtype == torch.float32 and raw.is_contiguous():
+            staged = raw.reshape(-1, 3)
+        else:
+            pos = torch.from_numpy(np.ascontiguousarray(raw, dtype=np.float32).reshape(-1, 3))
+            n = pos.shape[0]
+            if pins[i] is None or pins[i].shape[0] < n:
+                pins[i] = torch.empty((max(n, 1), 3), dtype=torch.float32, pin_memory=True)
+            pins[i][:n].copy_(pos)
+            staged = pins[i][:n]
         dims = dimensions_of_frame(dimensions, f)
         # a pipeline of a shape that is about to be evicted may still have a frame in flight: drain first
         if _shape_of(dims, resolution) not in pool.by_shape and len(pool.by_shape) >= pool.max_shapes:
@@ -133,10 +157,13 @@ def run_trajectory(frames, dimensions, resolution, closing=True, morph="", n_fra
                 local[f0] = summarise(p0.finish())
             pending = []
         pipe = pool.get(i, dims)
-        pipe.begin(None, host_positions=pins[i][:n])
+        pipe.begin(None, host_positions=staged)
         pending.append((f, pipe))
     for f0, p0 in pending:
         local[f0] = summarise(p0.finish())
+    if stats is not None:
+        lookups, hits = (b - a for a, b in zip(memo0, pool.memo_counters()))
+        stats.update(frames=len(mine), memo_lookups=lookups, memo_hits=hits, memo_hit_rate=(hits / lookups) if lookups else None)
     return gather_results(local, n_frames, rank, world)
 
 

@@ -1,4 +1,4 @@
-"""Plain-Python model of the host graph stage (test infrastructure, like tests/run_model.py).
+"""Plain-Python model of the host graph stage -- TEST INFRASTRUCTURE (oracle), never imported by the product.
 
 This is round 1's dict-based restatement of the reference's ``graph_logic.py`` / ``rank_logic.py`` (citations
 relative to ``/root/reference/mdvcontainment/``).  It was checked against the live reference on random grids and is

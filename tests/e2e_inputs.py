@@ -25,6 +25,13 @@ def bicelle():
     return u, u.select_atoms("name C")
 
 
+def npt_dimensions(f, box_nm=32.0):
+    """Box of frame f of the NPT trajectory set: isotropic breathing of +-1.2 % (A, float32).  Shared by
+    tests/golden/make_config_golden.py and the GPU test, so both sides bin with the same float32 box."""
+    scale = 1.0 + 0.012 * np.sin(2 * np.pi * f / 7.0)
+    return np.array([box_nm * 10 * scale] * 3 + [90, 90, 90], dtype=np.float32)
+
+
 RUNS = {
     "complex3D": [dict(resolution=1, closing=False), dict(resolution=1, closing=True),
                   dict(resolution=0.5, closing=True), dict(resolution=1, morph="dde"),

@@ -113,7 +113,7 @@ def test_view_order_is_what_networkx_iterates():
 
 
 def _compare_with_model(grid):
-    import host_graph_model as model
+    import graph_model as model
     labels = vo.label_3d_grid(grid).astype(np.int32)
     uniq = np.unique(labels)
     contacts, bridges = vo.find_label_contacts_c(labels), vo.find_bridges_c(labels)
@@ -172,3 +172,38 @@ def test_orientation_guard_and_level_sweep():
     assert len(dag.roots()) == 1
     kids = dag.children()
     assert len(kids[dag.roots()[0]]) == 1 and len(kids[1]) == n
+
+
+def test_many_label_case_matches_the_reference_recorded_graph_stage():
+    """128^3 Bernoulli(0.05), 48 k labels: numbering, ranks, component contact graph and DAG
+    as recorded from the unmodified reference (tests/golden/make_config_golden.py: 23.8 s there)."""
+    import json
+    import os
+    import time
+    from golden_util import GOLD, sha
+    with open(os.path.join(GOLD, "config_cases.json")) as fh:
+        rec = json.load(fh)["many_labels_128"]
+    rng = np.random.default_rng(rec["seed"])
+    grid = rng.random((rec["n"],) * 3) < rec["p"]
+    assert sha(grid, np.uint8) == rec["sha_grid"]
+    labels = vo.label_3d_grid(grid).astype(np.int32)
+    contacts, bridges = vo.find_label_contacts_c(labels), vo.find_bridges_c(labels)
+    assert sha(contacts) == rec["sha_contacts"] and sha(bridges) == rec["sha_bridges"]
+    nf, nt = int(-labels.min()), int(labels.max())
+    uniq = np.concatenate([np.arange(-nf, 0), np.arange(1, nt + 1)]).astype(np.int32)
+    t0 = time.perf_counter()
+    sol = hg.solve_periodic(uniq, contacts, bridges)
+    lut = sol.lut(nf, nt)
+    dag = sol.containment_dag()
+    dt = time.perf_counter() - t0
+    assert len(sol.comp_ids) == rec["n_components"]
+    assert sha(lut) == rec["sha_lut"]
+    assert sha(sol.comp_ids) == rec["sha_component_order"]
+    assert sha(sol.comp_rank) == rec["sha_ranks"] and sha(sol.compl_rank) == rec["sha_complement_ranks"]
+    assert sha(sol.contained.astype(np.uint8)) == rec["sha_contained"]
+    ccg = sol["component_contact_graph"]
+    assert sha(np.array([int(x) for x in ccg.nodes], dtype=np.int64)) == rec["sha_ccg_nodes"]
+    assert sha(np.array([int(v) for x in ccg.nodes for v in ccg.neighbors(x)], dtype=np.int64)) == rec["sha_ccg_adjacency"]
+    assert sha(dag.nodes.astype(np.int64)) == rec["dag"]["sha_nodes"]
+    assert sha(np.array(dag.edges(), dtype=np.int64).reshape(-1, 2)) == rec["dag"]["sha_edges"]
+    assert dt < 0.1 * rec["reference_graph_stage_seconds"]
