@@ -1982,6 +1982,85 @@ extern "C" int mdvc_frame_relabel_runs(int X, int Y, int Z, void *ws, size_t ws_
     return MDVC_OK;
 }
 
+// ------------------------------------------------------------------------------------------
+// N2: per-voxel values straight from the run tables (no dense grid)
+// ------------------------------------------------------------------------------------------
+// value (label or component) of the run that contains linear voxel index `lin` of row `row`
+__device__ __forceinline__ int32_t run_value_at(const uint32_t *__restrict__ rowoff, const uint32_t *__restrict__ runstart,
+                                                const int32_t *__restrict__ table, uint32_t row, uint32_t lin) {
+    uint32_t lo = rowoff[row], hi = rowoff[row + 1];
+    while (hi - lo > 1) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (runstart[mid] <= lin) lo = mid; else hi = mid;
+    }
+    return table[lo];
+}
+
+__global__ void __launch_bounds__(256)
+k_atom_run_values(const int32_t *__restrict__ vox, long long n, Dims D, const Hdr *__restrict__ h,
+                  const uint32_t *__restrict__ rowoff, const uint32_t *__restrict__ runstart,
+                  const int32_t *__restrict__ table, double *__restrict__ out) {
+    const bool ok = h->run_eff != 0;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const int x = vox[3 * i], y = vox[3 * i + 1], z = vox[3 * i + 2];
+        int32_t v = 0;
+        if (ok && (unsigned)x < (unsigned)D.X && (unsigned)y < (unsigned)D.Y && (unsigned)z < (unsigned)D.Z) {
+            const uint32_t row = (uint32_t)x * (uint32_t)D.Y + (uint32_t)y;
+            v = run_value_at(rowoff, runstart, table, row, row * (uint32_t)D.Z + (uint32_t)z);
+        }
+        out[i] = (double)v;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+k_key_run_values(const unsigned long long *__restrict__ keys, long long n, Dims D, const Hdr *__restrict__ h,
+                 const uint32_t *__restrict__ rowoff, const uint32_t *__restrict__ runstart,
+                 const int32_t *__restrict__ table, int32_t *__restrict__ out) {
+    const bool ok = h->run_eff != 0;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const unsigned long long key = keys[i];
+        int32_t v = 0;
+        if (ok && key < D.N) v = run_value_at(rowoff, runstart, table, (uint32_t)key / (uint32_t)D.Z, (uint32_t)key);
+        out[i] = v;
+    }
+}
+
+static int run_value_args(int X, int Y, int Z, void *ws, size_t ws_bytes, const mdvc_frame_caps *caps, int which, Dims &D,
+                          Layout &L, const int32_t *&table) {
+    if (which != 0 && which != 1) return MDVC_ERR_BADARG;
+    if (!make_dims(X, Y, Z, mdvc_words(Z), D)) return MDVC_ERR_BADARG;
+    int rc = check_ws(ws, ws_bytes, caps, D.rows, L);
+    if (rc) return rc;
+    table = at<int32_t>(ws, which ? L.runcomp : L.lab);
+    return MDVC_OK;
+}
+
+extern "C" int mdvc_frame_atom_values(const int32_t *vox, long long n, int X, int Y, int Z, void *ws, size_t ws_bytes,
+                                      const mdvc_frame_caps *caps, int which, double *out, void *stream) {
+    if (n < 0 || (n > 0 && (!vox || !out))) return MDVC_ERR_BADARG;
+    Dims D; Layout L; const int32_t *table;
+    int rc = run_value_args(X, Y, Z, ws, ws_bytes, caps, which, D, L, table);
+    if (rc || n == 0) return rc;
+    k_atom_run_values<<<mdvc_grid(n, 256, 8), 256, 0, (cudaStream_t)stream>>>(vox, n, D, at<Hdr>(ws, L.hdr), at<uint32_t>(ws, L.rowoff),
+                                                                              at<uint32_t>(ws, L.runstart), table, out);
+    MDVC_LAUNCH_CHECK();
+    return MDVC_OK;
+}
+
+extern "C" int mdvc_frame_values_at(const unsigned long long *keys, long long n, int X, int Y, int Z, void *ws, size_t ws_bytes,
+                                    const mdvc_frame_caps *caps, int which, int32_t *out, void *stream) {
+    if (n < 0 || (n > 0 && (!keys || !out))) return MDVC_ERR_BADARG;
+    Dims D; Layout L; const int32_t *table;
+    int rc = run_value_args(X, Y, Z, ws, ws_bytes, caps, which, D, L, table);
+    if (rc || n == 0) return rc;
+    k_key_run_values<<<mdvc_grid(n, 256, 8), 256, 0, (cudaStream_t)stream>>>(keys, n, D, at<Hdr>(ws, L.hdr), at<uint32_t>(ws, L.rowoff),
+                                                                             at<uint32_t>(ws, L.runstart), table, out);
+    MDVC_LAUNCH_CHECK();
+    return MDVC_OK;
+}
+
 extern "C" int mdvc_frame_read_header(const void *ws, mdvc_frame_header *header_host, void *stream) {
     if (!ws || !header_host) return MDVC_ERR_BADARG;
     cudaStream_t st = (cudaStream_t)stream;

@@ -548,7 +548,7 @@ k_asel_count(const unsigned long long *__restrict__ keys, long long n, const int
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
         long long i = base + k;
-        if (i < n) c += is_member(grid[keys[i]], member, lo, n_member);
+        if (i < n) c += is_member(keys ? grid[keys[i]] : grid[i], member, lo, n_member);
     }
     c = mdvc_block_reduce_sum<uint32_t>(c, sm);
     if (threadIdx.x == 0) tile_counts[blockIdx.x] = c;
@@ -565,7 +565,7 @@ k_asel_scatter(const uint32_t *__restrict__ order, const unsigned long long *__r
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
         long long i = base + k;
-        m[k] = i < n && is_member(grid[keys[i]], member, lo, n_member);
+        m[k] = i < n && is_member(keys ? grid[keys[i]] : grid[i], member, lo, n_member);
         c += m[k];
     }
     uint32_t total;
@@ -579,7 +579,7 @@ extern "C" int mdvc_atom_select(const uint32_t *order, const unsigned long long 
                                 const uint8_t *member, int lo, int n_member, const long long *atom_ix, uint32_t *scratch,
                                 long long *out, unsigned long long *n_out_dev, void *stream) {
     if (n < 0 || n >= (1ll << 31) || !grid || !member || !scratch || !n_out_dev || n_member <= 0 ||
-        (n > 0 && (!order || !keys || !out)))
+        (n > 0 && (!order || !out)))                       // keys == NULL: grid holds one value per CSR position
         return MDVC_ERR_BADARG;
     cudaStream_t st = (cudaStream_t)stream;
     if (n == 0) { MDVC_CUDA_CHECK(cudaMemsetAsync(n_out_dev, 0, 8, st)); return MDVC_OK; }
