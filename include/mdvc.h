@@ -157,6 +157,17 @@ int mdvc_frame_expand_planes(const uint32_t *bits, int X, int Y, int Z, int pitc
 int mdvc_frame_relabel_runs(int X, int Y, int Z, void *workspace, size_t workspace_bytes,
                             const mdvc_frame_caps *caps, const int32_t *lut_dev, uint32_t n_entries, void *stream);
 
+/* N2: per-atom / per-voxel-key values straight from the run tables, no dense grid needed
+ * (replaces the full-grid passes of set_betafactors / get_atomgroup_from_nodes, mda_containment.py:139-220).
+ * which = 0: non-periodic label, 1: component (after mdvc_frame_set_lut / mdvc_frame_components).
+ * mdvc_frame_atom_values: vox int32[n][3] (wrapped voxel of every atom) -> out double[n] (the tempfactor dtype);
+ * atoms outside the grid get 0.  mdvc_frame_values_at: keys uint64[n] linear voxel indices (e.g. the sorted keys of
+ * mdvc_atom_sort_by_voxel) -> out int32[n]. */
+int mdvc_frame_atom_values(const int32_t *vox, long long n, int X, int Y, int Z, void *workspace, size_t workspace_bytes,
+                           const mdvc_frame_caps *caps, int which, double *out, void *stream);
+int mdvc_frame_values_at(const unsigned long long *keys, long long n, int X, int Y, int Z, void *workspace,
+                         size_t workspace_bytes, const mdvc_frame_caps *caps, int which, int32_t *out, void *stream);
+
 /* Synchronises the stream and copies the header to the host. Returns flags as MDVC_OVERFLOW_*. */
 int mdvc_frame_read_header(const void *workspace, mdvc_frame_header *header_host, void *stream);
 /* Device pointers into the workspace (valid after the producing stage; sizes from the header):
@@ -224,7 +235,9 @@ size_t mdvc_atom_sort_scratch_bytes(long long n);
 int mdvc_atom_sort_by_voxel(const int32_t *vox, long long n, int X, int Y, int Z, uint32_t *order_out,
                             unsigned long long *keys_out, void *scratch, void *stream);
 /* gather: atoms (in CSR order) whose voxel value is selected by member[] -> atom_ix[order] int64.
- * out capacity n. *n_out_dev device uint64. scratch as for mdvc_grid_select on n items. */
+ * out capacity n. *n_out_dev device uint64. scratch as for mdvc_grid_select on n items.
+ * keys == NULL: `grid` holds one value per CSR position (int32[n], e.g. from mdvc_frame_values_at) instead of a
+ * dense grid indexed by keys. */
 int mdvc_atom_select(const uint32_t *order, const unsigned long long *keys, long long n,
                      const int32_t *grid, const uint8_t *member, int lo, int n_member,
                      const long long *atom_ix, uint32_t *scratch, long long *out,

@@ -61,6 +61,8 @@ SIGNATURES = {
     "mdvc_frame_expand": (_I, [_P, _I, _I, _I, _I, _P, _SZ, _CAPS, _P, _P, _P]),
     "mdvc_frame_expand_planes": (_I, [_P, _I, _I, _I, _I, _P, _SZ, _CAPS, _I, _I, _P, _P, _P]),
     "mdvc_frame_relabel_runs": (_I, [_I, _I, _I, _P, _SZ, _CAPS, _P, _U32, _P]),
+    "mdvc_frame_atom_values": (_I, [_P, _LL, _I, _I, _I, _P, _SZ, _CAPS, _I, _P, _P]),
+    "mdvc_frame_values_at": (_I, [_P, _LL, _I, _I, _I, _P, _SZ, _CAPS, _I, _P, _P]),
     "mdvc_frame_read_header": (_I, [_P, ctypes.POINTER(FrameHeader), _P]),
     "mdvc_frame_contacts_ptr": (_P, [_P, _I, _I, _I, _CAPS]),
     "mdvc_frame_bridges_ptr": (_P, [_P, _I, _I, _I, _CAPS]),

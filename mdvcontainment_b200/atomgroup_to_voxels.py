@@ -104,6 +104,35 @@ class DeviceMapping:
         return key in self._as_dict()
 
 
+def _pinned_view(atomgroup, name):
+    """(numpy view, torch view) of the group's coordinates / tempfactors when they can be moved by DMA in place: the
+    group exposes a contiguous writable view (this package's AtomGroup on an index range) in page-locked memory."""
+    getter = getattr(atomgroup, name, None)
+    view = getter() if getter is not None else None
+    if view is None or not view.flags.c_contiguous or not view.flags.writeable or view.size == 0:
+        return None
+    t = torch.from_numpy(view)
+    return t if t.is_pinned() else None
+
+
+def positions_to_device(atomgroup) -> torch.Tensor:
+    """float32 [n,3] CUDA tensor of the group's coordinates (stream-ordered DMA from pinned memory where possible)."""
+    t = _pinned_view(atomgroup, "_positions_view")
+    if t is not None:
+        return t.to("cuda", non_blocking=True)
+    return dev.to_device(np.ascontiguousarray(atomgroup.positions, dtype=np.float32))
+
+
+def positions_from_device(atomgroup, newpos: torch.Tensor):
+    """``atomgroup.positions = newpos`` (atomgroup_to_voxels.py:142) without host-side staging copies where possible."""
+    t = _pinned_view(atomgroup, "_positions_view")
+    if t is not None:
+        t.copy_(newpos, non_blocking=True)
+        torch.cuda.current_stream().synchronize()      # the caller may read the coordinates as soon as we return
+    else:
+        atomgroup.positions = dev.to_numpy(newpos)
+
+
 def voxelize_on_device(atomgroup, resolution, max_offset=0.05, want_mapping=True, positions_dev=None):
     """One ``create_voxels`` call with every array kept on the device.
 
@@ -114,10 +143,10 @@ def voxelize_on_device(atomgroup, resolution, max_offset=0.05, want_mapping=True
     _check_resolution(atomgroup, resolution, max_offset, box, nbox)
     shape = tuple(int(v) for v in np.diagonal(nbox))
     if positions_dev is None:
-        positions_dev = dev.to_device(np.ascontiguousarray(atomgroup.positions, dtype=np.float32))
+        positions_dev = positions_to_device(atomgroup)
     bits = dev.BitGrid(shape)
     vox, newpos = dev.bin_atoms(positions_dev, T, invT, nbox, bits, want_voxels=want_mapping, want_positions=True)
-    atomgroup.positions = dev.to_numpy(newpos)
+    positions_from_device(atomgroup, newpos)
     return bits, vox, newpos
 
 

@@ -23,13 +23,24 @@ class FrameResult:
     """Device-side state and small host-side results of one labelled frame."""
 
     __slots__ = ("bits", "plan", "header", "contacts", "bridges", "unique_labels", "label_volumes",
-                 "components_dev", "labels_dev", "lut", "timings")
+                 "components_dev", "labels_dev", "lut", "timings", "value_table")
 
     def labels(self) -> torch.Tensor:
         if self.labels_dev is None:
             self.labels_dev = torch.empty(self.bits.shape, dtype=torch.int32, device=self.bits.words.device)
             self.plan.expand(self.bits, self.labels_dev, None)
         return self.labels_dev
+
+    def components(self) -> torch.Tensor:
+        """Dense int32 components grid, written (one ``k_expand`` pass from the run tables) when first asked for:
+        the DAG, ranks, counts and the per-atom queries do not need it (lazy materialisation)."""
+        if self.components_dev is None:
+            if self.value_table == 0:                   # slab=True: labels are the components
+                self.components_dev = self.labels()
+            else:
+                self.components_dev = torch.empty(self.bits.shape, dtype=torch.int32, device=self.bits.words.device)
+                self.plan.expand(self.bits, None, self.components_dev)
+        return self.components_dev
 
 
 def label_frame(bits: dev.BitGrid, periodic=True, plan: dev.FramePlan | None = None) -> FrameResult:
@@ -49,6 +60,7 @@ def label_frame(bits: dev.BitGrid, periodic=True, plan: dev.FramePlan | None = N
     fr.components_dev = None
     fr.labels_dev = None
     fr.lut = None
+    fr.value_table = 1              # which run table holds the components: 1 = runcomp, 0 = labels (slab=True)
     fr.timings = {"device_label_pairs_s": time.perf_counter() - t0}
     return fr
 
@@ -65,13 +77,10 @@ def apply_component_lut(fr: FrameResult, lut, also_labels=False):
             table[np.asarray(labs, dtype=np.int64) + nf] = comp
         lut = table
     fr.lut = lut
-    fr.plan.set_lut(torch.from_numpy(lut).to(fr.bits.words.device))
-    fr.components_dev = torch.empty(fr.bits.shape, dtype=torch.int32, device=fr.bits.words.device)
-    if also_labels and fr.labels_dev is None:
-        fr.labels_dev = torch.empty(fr.bits.shape, dtype=torch.int32, device=fr.bits.words.device)
-        fr.plan.expand(fr.bits, fr.labels_dev, fr.components_dev)
-    else:
-        fr.plan.expand(fr.bits, None, fr.components_dev)
+    fr.plan.set_lut(torch.from_numpy(lut).to(fr.bits.words.device))     # per-run component table; no dense pass yet
+    fr.components_dev = None
+    if also_labels:
+        fr.labels()
 
 
 def _outer_face_labels(labels_dev: torch.Tensor):
@@ -137,6 +146,7 @@ def calc_containment_graph(boolean_grid, verbose=False, write_structures=False, 
     else:
         labels_dev = fr.labels()
         fr.components_dev = labels_dev
+        fr.value_table = 0
         fr.lut = np.arange(-int(fr.header.n_false), int(fr.header.n_true) + 1, dtype=np.int32)
         sol = hg.solve_slab(nonp_unique_labels, fr.contacts, _outer_face_labels(labels_dev))
         if write_structures:
@@ -145,7 +155,7 @@ def calc_containment_graph(boolean_grid, verbose=False, write_structures=False, 
         component_contact_graph = nx.Graph(sol["label_graph"].to_networkx())
         containment_graph = hg.containment_graph(is_contained, nonp_unique_labels, component_contact_graph)
     if write_structures:
-        _write_grid('components.gro', dev.to_numpy(fr.components_dev))
+        _write_grid('components.gro', dev.to_numpy(fr.components()))
     if draw_graphs:
         print('=== NON PERIODIC LABEL CONTACT GRAPH ===')
         _draw_graph(sol["label_graph"].to_networkx())
@@ -157,7 +167,7 @@ def calc_containment_graph(boolean_grid, verbose=False, write_structures=False, 
         return containment_graph, (component_contact_graph if slab else sol), fr, component_ranks, sol["label_graph"]
     if not slab:
         containment_graph, component_contact_graph = containment_graph.to_networkx(), sol["component_contact_graph"]
-    return (containment_graph, component_contact_graph, dev.to_numpy(fr.components_dev), component_ranks,
+    return (containment_graph, component_contact_graph, dev.to_numpy(fr.components()), component_ranks,
             sol["label_graph"].to_networkx())
 
 
@@ -218,7 +228,7 @@ class VoxelContainmentBase:
     @property
     def components_grid_device(self):
         """int32 CUDA tensor [X,Y,Z] (no host copy)."""
-        return self._base._frame.components_dev
+        return self._base._frame.components()
 
     @property
     def nonp_label_contact_graph(self):
@@ -330,14 +340,14 @@ class VoxelContainmentBase:
     def get_voxel_mask(self, nodes):
         """np.isin(components_grid, nodes) (containment_main.py:360-368) -> NumPy bool array."""
         lo, n = self._member_span()
-        _, mask = dev.grid_select(self._base._frame.components_dev, self._resolve_nodes_to_original(nodes), lo, n,
+        _, mask = dev.grid_select(self._base._frame.components(), self._resolve_nodes_to_original(nodes), lo, n,
                                   want_mask=True, want_positions=False)
         return dev.to_numpy(mask)
 
     def get_voxel_positions(self, nodes):
         """np.where of the mask as an (M,3) int64 array in C-order (containment_main.py:370-378)."""
         lo, n = self._member_span()
-        pos, _ = dev.grid_select(self._base._frame.components_dev, self._resolve_nodes_to_original(nodes), lo, n)
+        pos, _ = dev.grid_select(self._base._frame.components(), self._resolve_nodes_to_original(nodes), lo, n)
         return pos
 
     def format_containment(self, nodes=False):
@@ -404,7 +414,7 @@ class VoxelContainment(VoxelContainmentBase):
 
     def _get_components_grid(self):
         if self._components_grid is None:
-            self._components_grid = dev.to_numpy(self._frame.components_dev)
+            self._components_grid = dev.to_numpy(self._frame.components())
         return self._components_grid
 
     def _get_label_graph(self):

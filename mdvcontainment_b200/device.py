@@ -259,6 +259,22 @@ class FramePlan:
         check(self.lib.mdvc_frame_expand(_ptr(bits.words), X, Y, Z, bits.pitch, *self._args(), _ptr(labels),
                                          _ptr(components), _stream()), "mdvc_frame_expand")
 
+    def atom_values(self, vox: torch.Tensor, which: int) -> torch.Tensor:
+        """float64 [n]: label (which=0) or component (which=1) of the voxel of every atom, from the run tables."""
+        X, Y, Z = self.shape
+        out = torch.empty(vox.shape[0], dtype=torch.float64, device=vox.device)
+        check(self.lib.mdvc_frame_atom_values(_ptr(vox), int(vox.shape[0]), X, Y, Z, *self._args(), int(which), _ptr(out),
+                                              _stream()), "mdvc_frame_atom_values")
+        return out
+
+    def values_at(self, keys: torch.Tensor, which: int) -> torch.Tensor:
+        """int32 [n]: label / component at the linear voxel indices ``keys`` (int64/uint64), from the run tables."""
+        X, Y, Z = self.shape
+        out = torch.empty(keys.shape[0], dtype=torch.int32, device=keys.device)
+        check(self.lib.mdvc_frame_values_at(_ptr(keys), int(keys.shape[0]), X, Y, Z, *self._args(), int(which), _ptr(out),
+                                            _stream()), "mdvc_frame_values_at")
+        return out
+
     def read_header(self) -> FrameHeader:
         """Synchronises the current stream."""
         h = FrameHeader()
@@ -426,7 +442,10 @@ class AtomCSR:
             check(lib.mdvc_atom_sort_by_voxel(_ptr(vox), n, X, Y, Z, _ptr(self.order), _ptr(self.keys), _ptr(scratch),
                                               _stream()), "mdvc_atom_sort_by_voxel")
 
-    def select(self, grid: torch.Tensor, values, lo: int, n_values: int, atom_ix: torch.Tensor | None) -> np.ndarray:
+    def select(self, grid: torch.Tensor, values, lo: int, n_values: int, atom_ix: torch.Tensor | None,
+               per_position: bool = False) -> np.ndarray:
+        """Atoms (voxel C-order, then atom order) whose voxel value is one of ``values``.  ``grid`` is the dense int32
+        grid, or -- ``per_position`` -- one value per entry of this CSR (``FramePlan.values_at(self.keys, ...)``)."""
         n = int(self.order.shape[0])
         if n == 0:
             return np.array([], dtype=np.int64)
@@ -435,8 +454,9 @@ class AtomCSR:
         scratch = torch.empty(lib.mdvc_grid_select_scratch_words(n), dtype=torch.int32, device=grid.device)
         out = torch.empty(n, dtype=torch.int64, device=grid.device)
         n_out = torch.zeros(1, dtype=torch.int64, device=grid.device)
-        check(lib.mdvc_atom_select(_ptr(self.order), _ptr(self.keys), n, _ptr(grid), _ptr(member), int(lo), int(n_values),
-                                   _ptr(atom_ix), _ptr(scratch), _ptr(out), _ptr(n_out), _stream()), "mdvc_atom_select")
+        check(lib.mdvc_atom_select(_ptr(self.order), None if per_position else _ptr(self.keys), n, _ptr(grid), _ptr(member),
+                                   int(lo), int(n_values), _ptr(atom_ix), _ptr(scratch), _ptr(out), _ptr(n_out), _stream()),
+              "mdvc_atom_select")
         return to_numpy(out[: int(n_out.item())])
 
     def gather_voxels(self, query_voxels, atom_ix: torch.Tensor | None) -> np.ndarray:

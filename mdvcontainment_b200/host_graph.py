@@ -12,7 +12,7 @@ labels; this takes tens of milliseconds and still scales
 Three places where Python ``set`` iteration order leaks into the reference's results are reproduced with real
 ``set`` objects of the running interpreter (never emulated): the numbering of the components of the minority
 polarity (``_view_order``), the neighbour order of the component contact graph and the pop order that orients the
-containment graph.  ``oracle/graph_model.py`` is a plain-Python model of the same logic; both are checked
+containment graph.  A plain-Python model of the same logic lives with the test oracle (graph_model.py); both are checked
 against the unmodified reference where it is available.
 """
 from __future__ import annotations

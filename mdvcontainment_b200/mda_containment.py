@@ -111,8 +111,9 @@ class ContainmentBase:
         vc = self.voxel_containment
         lo, n = vc._member_span()
         mapping: DeviceMapping = self.voxel2atom
-        idx = mapping.csr.select(vc.components_grid_device, vc._resolve_nodes_to_original(nodes), lo, n,
-                                 mapping.atom_ix_dev)
+        # component of every voxel-sorted atom straight from the run tables (no dense components grid)
+        idx = mapping.csr.select(self._base._csr_components(), vc._resolve_nodes_to_original(nodes), lo, n,
+                                 mapping.atom_ix_dev, per_position=True)
         if len(idx) == 0:
             return self.universe.atoms[[]]
         return self.universe.atoms[idx]
@@ -124,7 +125,9 @@ class ContainmentBase:
             raise ValueError("set_betafactors requires no_mapping='False'.")
         vc = self.voxel_containment
         mapping: DeviceMapping = self.voxel2atom
-        comp = dev.to_numpy(dev.atom_components(mapping.voxels_dev, vc.components_grid_device))
+        fr = self._base.voxel_containment._frame
+        comp_dev = fr.plan.atom_values(mapping.voxels_dev, fr.value_table)      # run-table lookup per atom
+        comp = dev.to_numpy(comp_dev)
         betafactors = np.zeros(len(self.universe.atoms))
         is_view = isinstance(self, ContainmentView)
         if is_view:
@@ -134,7 +137,10 @@ class ContainmentBase:
                     node_of[int(orig)] = node
             values = np.array([node_of.get(int(c), 0) for c in np.unique(comp)], dtype=np.float64)
             comp = values[np.searchsorted(np.unique(comp), comp)]
-        betafactors[mapping.atom_indices] = comp
+        if len(comp) == len(betafactors) and _is_arange(mapping.atom_indices):
+            betafactors = comp if comp.dtype == np.float64 else comp.astype(np.float64)
+        else:
+            betafactors[mapping.atom_indices] = comp
         try:
             self.universe.atoms.tempfactors = betafactors
             if is_view:
@@ -142,7 +148,11 @@ class ContainmentBase:
             else:
                 print('NOTE: tempfactors already set in the universe, and will be overwritten with the component ids.')
         except AttributeError:
-            self.universe.add_TopologyAttr(_tempfactors_attr(betafactors))
+            adopt = getattr(self.universe, "_adopt_tempfactors", None)
+            if adopt is not None:
+                adopt(betafactors)                    # this package's Universe: takes the fresh array as it is
+            else:
+                self.universe.add_TopologyAttr(_tempfactors_attr(betafactors))
             if is_view:
                 print('Writing VIEW component ids in the tempfactors of universe.')
             else:
@@ -156,6 +166,14 @@ class ContainmentBase:
         if min_size > 0:
             keep_nodes = self.voxel_containment.filter_nodes_on_size(min_size)
         return ContainmentView(self._base, keep_nodes)
+
+
+def _is_arange(ix) -> bool:
+    """``universe.atoms.ix`` is sorted and unique, so first == 0 and last == n - 1 make it arange(n) (checking every
+    element of a 10 M atom index array would cost more than the gather it saves)."""
+    ix = np.asarray(ix)
+    n = len(ix)
+    return n == 0 or (int(ix[0]) == 0 and int(ix[-1]) == n - 1)
 
 
 def _tempfactors_attr(values):
@@ -213,6 +231,7 @@ class Containment(ContainmentBase):
         self._betafactors = betafactors
         self._universe = atomgroup.universe
         self._negative_cache = None          # universe.atoms - atomgroup, built on first access
+        self._csr_comp = None                # component of every entry of the voxel-sorted atom list
 
         self._bits, self._voxel2atom = self._voxelize_atomgroup()
         self._grid_shape = self._bits.shape
@@ -223,6 +242,12 @@ class Containment(ContainmentBase):
         self._base = self
         if self._betafactors:
             self.set_betafactors()
+
+    def _csr_components(self):
+        if self._csr_comp is None:
+            fr = self.voxel_containment._frame
+            self._csr_comp = fr.plan.values_at(self._voxel2atom.csr.keys, fr.value_table)
+        return self._csr_comp
 
     def _voxelize_atomgroup(self):
         """mda_containment.py:378-400.  With a mapping, the whole universe is binned first (its

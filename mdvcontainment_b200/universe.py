@@ -20,6 +20,25 @@ import types
 import numpy as np
 
 
+PIN_THRESHOLD_BYTES = 4 << 20      # coordinate arrays from this size on are kept in page-locked host memory
+
+
+def _host_array(shape, dtype):
+    """NumPy array for per-atom data.  Large ones are backed by page-locked (pinned) host memory when a CUDA device is
+    present, so that the voxel path moves them over PCIe by DMA from / to where they lie -- a pageable 122 MB
+    coordinate array costs ~15 ms per host-side staging copy, three to four of them per ``Containment`` call."""
+    nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
+    if nbytes >= PIN_THRESHOLD_BYTES:
+        try:
+            import torch
+            if torch.cuda.is_available():
+                t = torch.empty(tuple(int(v) for v in shape), dtype=getattr(torch, np.dtype(dtype).name), pin_memory=True)
+                return t.numpy()                    # the array keeps the tensor (and its pinned block) alive
+        except Exception:                           # noqa: BLE001 - pinning is an optimisation only
+            pass
+    return np.empty(shape, dtype=dtype)
+
+
 class Tempfactors:
     """Stand-in for ``MDAnalysis.core.topologyattrs.Tempfactors`` (values holder)."""
 
@@ -78,6 +97,13 @@ class AtomGroup:
             return self._u._positions[self._range[0]:self._range[1]].copy()
         return self._u._positions[self._ix]
 
+    def _positions_view(self):
+        """Writable float32 [n,3] view of this group's coordinates inside the universe's array when the group is a
+        contiguous index range (no copy); None otherwise.  The voxel path copies from / to it by DMA."""
+        if self._range is None:
+            return None
+        return self._u._positions[self._range[0]:self._range[1]]
+
     @positions.setter
     def positions(self, value):
         # MDAnalysis stores coordinates as float32; assignment casts.
@@ -107,13 +133,18 @@ class AtomGroup:
     def tempfactors(self):
         if self._u._tempfactors is None:
             raise AttributeError("This Universe does not contain tempfactors information")
+        if self._range is not None:
+            return self._u._tempfactors[self._range[0]:self._range[1]].copy()
         return self._u._tempfactors[self._ix]
 
     @tempfactors.setter
     def tempfactors(self, values):
         if self._u._tempfactors is None:
             raise AttributeError("This Universe does not contain tempfactors information")
-        self._u._tempfactors[self._ix] = values
+        if self._range is not None:
+            self._u._tempfactors[self._range[0]:self._range[1]] = values
+        else:
+            self._u._tempfactors[self._ix] = values
 
     # --- set algebra / indexing ----------------------------------------
     def __getitem__(self, item):
@@ -152,7 +183,9 @@ class Universe:
     """Positions (A, float32), box (float32[6]) and per-atom names."""
 
     def __init__(self, positions, dimensions, names=None, resnames=None, resids=None):
-        self._positions = np.ascontiguousarray(positions, dtype=np.float32).reshape(-1, 3).copy()
+        src = np.asarray(positions, dtype=np.float32).reshape(-1, 3)
+        self._positions = _host_array(src.shape, np.float32)
+        self._positions[...] = src
         n = len(self._positions)
         dims = np.asarray(dimensions, dtype=np.float32).reshape(-1)
         if dims.size == 3:
@@ -173,6 +206,13 @@ class Universe:
         else:
             vals = attr.values
         self._tempfactors = np.array(vals, dtype=np.float64)
+
+    def _adopt_tempfactors(self, values):
+        """``add_TopologyAttr(Tempfactors(values))`` for a float64 array the caller hands over (no copy)."""
+        values = np.asarray(values, dtype=np.float64)
+        if values.shape != (len(self.atoms),):
+            raise ValueError("one tempfactor per atom")
+        self._tempfactors = values
 
     def select_atoms(self, selection: str):
         return self._select(selection, self.atoms.ix)
