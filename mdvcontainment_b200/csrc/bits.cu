@@ -185,35 +185,62 @@ __device__ __forceinline__ bool bin_one_atom(const float *sp3, long long i, cons
     return v[0] >= 0 && v[0] < P.nbox[0] && v[1] >= 0 && v[1] < P.nbox[4] && v[2] >= 0 && v[2] < P.nbox[8];
 }
 
-// One thread per atom.  Positions are AoS (x,y,z per atom = 12 B): a tile of 256 atoms is fetched as 192 coalesced
-// float4 loads into shared memory and read back with stride 3 (conflict-free), instead of three strided 4-byte
-// loads per atom that each touch every sector of the tile (ncu: 2.5x the compulsory DRAM reads).
+// Four consecutive atoms per thread.  Positions are AoS (x,y,z per atom = 12 B), so four atoms are exactly three
+// 16-byte words: each thread fetches them with three streaming float4 loads (the three loads of a warp cover one
+// contiguous 1536-byte span, every sector of it used), runs the four independent FMA chains -- that instruction-level
+// parallelism is what hides the load latency -- and fires its REDs.  No shared memory and no barriers: the previous
+// one-atom-per-thread kernel staged tiles through shared memory and spent 11.6 stall cycles per issued instruction
+// at its two barriers and 12.8 on the tile loads (ncu, profiles/r1_bin_atoms_ncu_summary.txt: 31 % issue-active).
+// The optional outputs leave as 16-byte stores as well.  pos_out may alias pos: a thread reads its four atoms
+// completely before it writes them.
 __global__ void __launch_bounds__(256)
-k_bin_atoms(const float *__restrict__ pos, long long n, BinParams P, uint32_t *__restrict__ occ, int pitch,
-            int32_t *__restrict__ vox_out, float *pos_out) {
-    __shared__ float sp[256 * 3];
-    const bool vec_ok = (reinterpret_cast<uintptr_t>(pos) & 15) == 0;
-    const long long n_tiles = (n + 255) / 256;
-    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const long long base = tile * 256;
-        const int cnt = (int)min(256ll, n - base);
-        __syncthreads();
-        if (vec_ok && cnt == 256) {
-            if (threadIdx.x < 192)
-                reinterpret_cast<float4 *>(sp)[threadIdx.x] = __ldcs(reinterpret_cast<const float4 *>(pos + 3 * base) + threadIdx.x);
-        } else {
-            for (int k = threadIdx.x; k < 3 * cnt; k += 256) sp[k] = pos[3 * base + k];
+k_bin_atoms4(const float *__restrict__ pos, long long n, BinParams P, uint32_t *__restrict__ occ, int pitch,
+             int32_t *__restrict__ vox_out, float *pos_out) {
+    const long long n4 = n >> 2;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < n4; g += stride) {
+        const float4 *src = reinterpret_cast<const float4 *>(pos) + 3 * g;
+        const float4 q0 = __ldcs(src), q1 = __ldcs(src + 1), q2 = __ldcs(src + 2);
+        const float f[12] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w};
+        int32_t v[12];
+        float w[12];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            int vx, vy, vz;
+            const bool inside = bin_one_atom(f + 3 * k, 0, P, vox_out ? v + 3 * k : nullptr, pos_out ? w + 3 * k : nullptr,
+                                             vx, vy, vz);
+            if (occ && inside) {
+                // fire-and-forget RED.OR; inside the grid => the row index fits 32 bits (fewer than 2^31 voxels)
+                const uint32_t row = (uint32_t)vx * (uint32_t)P.nbox[4] + (uint32_t)vy;
+                atomicOr(&occ[(size_t)row * pitch + ((uint32_t)vz >> 5)], 1u << (vz & 31));
+            }
         }
-        __syncthreads();
-        if ((int)threadIdx.x >= cnt) continue;
+        if (vox_out) {
+            int4 *dst = reinterpret_cast<int4 *>(vox_out) + 3 * g;
+            dst[0] = make_int4(v[0], v[1], v[2], v[3]);
+            dst[1] = make_int4(v[4], v[5], v[6], v[7]);
+            dst[2] = make_int4(v[8], v[9], v[10], v[11]);
+        }
+        if (pos_out) {
+            float4 *dst = reinterpret_cast<float4 *>(pos_out) + 3 * g;
+            dst[0] = make_float4(w[0], w[1], w[2], w[3]);
+            dst[1] = make_float4(w[4], w[5], w[6], w[7]);
+            dst[2] = make_float4(w[8], w[9], w[10], w[11]);
+        }
+    }
+}
+
+// One atom per thread with plain loads and stores: the last n % 4 atoms, and whole arrays whose pointers are not
+// 16-byte aligned (views into the middle of a coordinate array).
+__global__ void __launch_bounds__(256)
+k_bin_atoms1(const float *pos, long long first, long long n, BinParams P, uint32_t *__restrict__ occ, int pitch,
+             int32_t *__restrict__ vox_out, float *pos_out) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = first + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const float f[3] = {pos[3 * i], pos[3 * i + 1], pos[3 * i + 2]};
         int vx, vy, vz;
-        const bool inside = bin_one_atom(sp + 3 * threadIdx.x, base + threadIdx.x, P, vox_out, pos_out, vx, vy, vz);
+        const bool inside = bin_one_atom(f, i, P, vox_out, pos_out, vx, vy, vz);
         if (occ && inside) {
-            // Fire-and-forget RED.OR.  A __match_any_sync aggregation of lanes hitting the same word was
-            // measured on B200 (ncu: 20 of 27 stall cycles per issue on the MIO/short-scoreboard path,
-            // 255 us for 10.2 M atoms): atom order is spatially uncorrelated with the voxel grid, so
-            // there is almost nothing to merge and the match itself was the bottleneck.
-            // inside the grid => the row index fits 32 bits (the grid holds fewer than 2^31 voxels)
             const uint32_t row = (uint32_t)vx * (uint32_t)P.nbox[4] + (uint32_t)vy;
             atomicOr(&occ[(size_t)row * pitch + ((uint32_t)vz >> 5)], 1u << (vz & 31));
         }
@@ -236,8 +263,18 @@ extern "C" int mdvc_bin_atoms(const float *pos, long long n, const double *T_hos
         if (nbox_host[k] <= -(1ll << 28) || nbox_host[k] >= (1ll << 28)) P.fits32 = 0;
         P.nbox32[k] = (int)nbox_host[k];
     }
-    k_bin_atoms<<<mdvc_grid(n, 256, 64), 256, 0, (cudaStream_t)stream>>>(pos, n, P, occ_bits, pitch, vox_out, pos_out);
-    MDVC_LAUNCH_CHECK();
+    cudaStream_t st = (cudaStream_t)stream;
+    const uintptr_t ptrs = (uintptr_t)pos | (uintptr_t)vox_out | (uintptr_t)pos_out;
+    long long done = 0;
+    if ((ptrs & 15) == 0 && n >= 4) {
+        k_bin_atoms4<<<mdvc_grid(n >> 2, 256, 32), 256, 0, st>>>(pos, n, P, occ_bits, pitch, vox_out, pos_out);
+        MDVC_LAUNCH_CHECK();
+        done = n & ~3ll;
+    }
+    if (done < n) {
+        k_bin_atoms1<<<mdvc_grid(n - done, 256, 32), 256, 0, st>>>(pos, done, n, P, occ_bits, pitch, vox_out, pos_out);
+        MDVC_LAUNCH_CHECK();
+    }
     return MDVC_OK;
 }
 
