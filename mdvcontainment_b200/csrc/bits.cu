@@ -127,10 +127,10 @@ __device__ __forceinline__ long long floordiv_ll(long long a, long long b) {
 // from contracting differently -- floor, triclinic wrap (z, y, x; Python floor division), optional outputs.
 // Fast path: when the floors and the box matrix fit 28 bits (any realistic box) everything after the floor is
 // 32-bit integer work; the general path keeps 64-bit integers like the reference's int64 arrays.
-// Returns true and the wrapped voxel when it lies inside the grid.
-__device__ __forceinline__ bool bin_one_atom(const float *sp3, long long i, const BinParams &P,
-                                             int32_t *__restrict__ vox_out, float *pos_out, int &ox, int &oy, int &oz) {
-    const double p0 = (double)sp3[0], p1 = (double)sp3[1], p2 = (double)sp3[2];
+// Returns true when the wrapped voxel (vox) lies inside the grid; newpos = the rewritten position when want_pos.
+__device__ __forceinline__ bool bin_one_atom(float x, float y, float z, const BinParams &P, bool want_pos, int (&vox)[3],
+                                             float (&newpos)[3]) {
+    const double p0 = (double)x, p1 = (double)y, p2 = (double)z;
     double fj[3], fl[3];
 #pragma unroll
     for (int j = 0; j < 3; ++j) {
@@ -150,17 +150,16 @@ __device__ __forceinline__ bool bin_one_atom(const float *sp3, long long i, cons
 #pragma unroll
             for (int j = 0; j < 3; ++j) w3[j] -= sh * P.nbox32[3 * dim + j];
         }
-        if (vox_out) { vox_out[3 * i] = w3[0]; vox_out[3 * i + 1] = w3[1]; vox_out[3 * i + 2] = w3[2]; }
-        if (pos_out) {
+        if (want_pos) {
             // (voxel + fractional part) back through inv(T): atomgroup_to_voxels.py:142
             const double g0 = __dadd_rn((double)w3[0], __dsub_rn(fj[0], (double)u0)),
                          g1 = __dadd_rn((double)w3[1], __dsub_rn(fj[1], (double)u1)),
                          g2 = __dadd_rn((double)w3[2], __dsub_rn(fj[2], (double)u2));
 #pragma unroll
             for (int j = 0; j < 3; ++j)
-                pos_out[3 * i + j] = (float)__fma_rn(g2, P.invT[6 + j], __fma_rn(g1, P.invT[3 + j], __dmul_rn(g0, P.invT[j])));
+                newpos[j] = (float)__fma_rn(g2, P.invT[6 + j], __fma_rn(g1, P.invT[3 + j], __dmul_rn(g0, P.invT[j])));
         }
-        ox = w3[0]; oy = w3[1]; oz = w3[2];
+        vox[0] = w3[0]; vox[1] = w3[1]; vox[2] = w3[2];
         return (unsigned)w3[0] < (unsigned)P.nbox32[0] && (unsigned)w3[1] < (unsigned)P.nbox32[4] &&
                (unsigned)w3[2] < (unsigned)P.nbox32[8];
     }
@@ -174,14 +173,13 @@ __device__ __forceinline__ bool bin_one_atom(const float *sp3, long long i, cons
 #pragma unroll
         for (int j = 0; j < 3; ++j) v[j] -= sft * P.nbox[3 * dim + j];
     }
-    if (vox_out) { vox_out[3 * i] = (int32_t)v[0]; vox_out[3 * i + 1] = (int32_t)v[1]; vox_out[3 * i + 2] = (int32_t)v[2]; }
-    if (pos_out) {
+    if (want_pos) {
         const double g0 = __dadd_rn((double)v[0], f[0]), g1 = __dadd_rn((double)v[1], f[1]), g2 = __dadd_rn((double)v[2], f[2]);
 #pragma unroll
         for (int j = 0; j < 3; ++j)
-            pos_out[3 * i + j] = (float)__fma_rn(g2, P.invT[6 + j], __fma_rn(g1, P.invT[3 + j], __dmul_rn(g0, P.invT[j])));
+            newpos[j] = (float)__fma_rn(g2, P.invT[6 + j], __fma_rn(g1, P.invT[3 + j], __dmul_rn(g0, P.invT[j])));
     }
-    ox = (int)v[0]; oy = (int)v[1]; oz = (int)v[2];
+    vox[0] = (int)v[0]; vox[1] = (int)v[1]; vox[2] = (int)v[2];
     return v[0] >= 0 && v[0] < P.nbox[0] && v[1] >= 0 && v[1] < P.nbox[4] && v[2] >= 0 && v[2] < P.nbox[8];
 }
 
@@ -193,7 +191,7 @@ __device__ __forceinline__ bool bin_one_atom(const float *sp3, long long i, cons
 // at its two barriers and 12.8 on the tile loads (ncu, profiles/r1_bin_atoms_ncu_summary.txt: 31 % issue-active).
 // The optional outputs leave as 16-byte stores as well.  pos_out may alias pos: a thread reads its four atoms
 // completely before it writes them.
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 4)
 k_bin_atoms4(const float *__restrict__ pos, long long n, BinParams P, uint32_t *__restrict__ occ, int pitch,
              int32_t *__restrict__ vox_out, float *pos_out) {
     const long long n4 = n >> 2;
@@ -206,13 +204,15 @@ k_bin_atoms4(const float *__restrict__ pos, long long n, BinParams P, uint32_t *
         float w[12];
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-            int vx, vy, vz;
-            const bool inside = bin_one_atom(f + 3 * k, 0, P, vox_out ? v + 3 * k : nullptr, pos_out ? w + 3 * k : nullptr,
-                                             vx, vy, vz);
+            int vk[3];
+            float wk[3];
+            const bool inside = bin_one_atom(f[3 * k], f[3 * k + 1], f[3 * k + 2], P, pos_out != nullptr, vk, wk);
+#pragma unroll
+            for (int j = 0; j < 3; ++j) { v[3 * k + j] = vk[j]; w[3 * k + j] = wk[j]; }
             if (occ && inside) {
                 // fire-and-forget RED.OR; inside the grid => the row index fits 32 bits (fewer than 2^31 voxels)
-                const uint32_t row = (uint32_t)vx * (uint32_t)P.nbox[4] + (uint32_t)vy;
-                atomicOr(&occ[(size_t)row * pitch + ((uint32_t)vz >> 5)], 1u << (vz & 31));
+                const uint32_t row = (uint32_t)vk[0] * (uint32_t)P.nbox[4] + (uint32_t)vk[1];
+                atomicOr(&occ[(size_t)row * pitch + ((uint32_t)vk[2] >> 5)], 1u << (vk[2] & 31));
             }
         }
         if (vox_out) {
@@ -237,12 +237,14 @@ k_bin_atoms1(const float *pos, long long first, long long n, BinParams P, uint32
              int32_t *__restrict__ vox_out, float *pos_out) {
     const long long stride = (long long)gridDim.x * blockDim.x;
     for (long long i = first + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-        const float f[3] = {pos[3 * i], pos[3 * i + 1], pos[3 * i + 2]};
-        int vx, vy, vz;
-        const bool inside = bin_one_atom(f, i, P, vox_out, pos_out, vx, vy, vz);
+        int vk[3];
+        float wk[3] = {0.f, 0.f, 0.f};
+        const bool inside = bin_one_atom(pos[3 * i], pos[3 * i + 1], pos[3 * i + 2], P, pos_out != nullptr, vk, wk);
+        if (vox_out) { vox_out[3 * i] = vk[0]; vox_out[3 * i + 1] = vk[1]; vox_out[3 * i + 2] = vk[2]; }
+        if (pos_out) { pos_out[3 * i] = wk[0]; pos_out[3 * i + 1] = wk[1]; pos_out[3 * i + 2] = wk[2]; }
         if (occ && inside) {
-            const uint32_t row = (uint32_t)vx * (uint32_t)P.nbox[4] + (uint32_t)vy;
-            atomicOr(&occ[(size_t)row * pitch + ((uint32_t)vz >> 5)], 1u << (vz & 31));
+            const uint32_t row = (uint32_t)vk[0] * (uint32_t)P.nbox[4] + (uint32_t)vk[1];
+            atomicOr(&occ[(size_t)row * pitch + ((uint32_t)vk[2] >> 5)], 1u << (vk[2] & 31));
         }
     }
 }
