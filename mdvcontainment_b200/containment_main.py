@@ -386,13 +386,19 @@ class VoxelContainment(VoxelContainmentBase):
         self._write_structures = write_structures
         self._draw_graphs = draw_graphs
         self._slab = slab
-        self._base = self
         (self._containment_graph, self._component_contact_graph, self._frame, self._component_ranks,
          self._label_graph) = self._calc_containment()
         self._components_grid = None
         self._nonp_label_contact_graph = None
         self._inv_containment_graph = False
         self._voxel_counts = self._compute_counts() if counts else False
+
+    @property
+    def _base(self):
+        """The data owner is this object itself.  A property rather than the reference's ``self._base = self``
+        (containment_main.py:478): the attribute would be a reference cycle, and a cycle keeps gigabytes of device
+        buffers alive until the garbage collector happens to run."""
+        return self
 
     def _calc_containment(self):
         return calc_containment_graph(self._grid, verbose=self._verbose, write_structures=self._write_structures,

@@ -239,9 +239,14 @@ class Containment(ContainmentBase):
         self.voxel_containment = VoxelContainment(
             self._bits, verbose=self._verbose, write_structures=self._write_structures,
             slab=self._slab, counts=self._return_counts)
-        self._base = self
         if self._betafactors:
             self.set_betafactors()
+
+    @property
+    def _base(self):
+        """This object owns the data (a property instead of ``self._base = self``: no reference cycle, so the device
+        buffers are released as soon as the object is dropped)."""
+        return self
 
     def _csr_components(self):
         if self._csr_comp is None:

@@ -51,10 +51,11 @@ class Tempfactors:
 class AtomGroup:
     """An ordered set of atom indices into a :class:`Universe`."""
 
-    def __init__(self, universe: "Universe", ix):
+    def __init__(self, universe: "Universe", ix, _sorted_unique: bool = False):
         self._u = universe
         self._ix = np.asarray(ix, dtype=np.int64).reshape(-1)
         self._range_cache = False         # decided on first use: creating a 10 M atom group should not scan it
+        self._sorted_unique = _sorted_unique      # indices known to ascend strictly (selections of universe.atoms)
 
     @property
     def _range(self):
@@ -63,7 +64,7 @@ class AtomGroup:
         if self._range_cache is False:
             ix, n = self._ix, len(self._ix)
             self._range_cache = (int(ix[0]), int(ix[0]) + n) if n and int(ix[-1]) - int(ix[0]) == n - 1 \
-                and bool(np.all(ix[1:] - ix[:-1] == 1)) else None
+                and (self._sorted_unique or bool(np.all(ix[1:] - ix[:-1] == 1))) else None
         return self._range_cache
 
     # --- identity -------------------------------------------------------
@@ -176,7 +177,7 @@ class AtomGroup:
         return f"<AtomGroup with {len(self)} atoms>"
 
     def select_atoms(self, selection: str):
-        return self._u._select(selection, self._ix)
+        return self._u._select(selection, self._ix, self._sorted_unique)
 
 
 class Universe:
@@ -196,7 +197,7 @@ class Universe:
         self._resids = np.asarray(resids if resids is not None else np.ones(n), dtype=np.int64)
         self._tempfactors = None
         self.trajectory = types.SimpleNamespace(frame=0)
-        self.atoms = AtomGroup(self, np.arange(n, dtype=np.int64))
+        self.atoms = AtomGroup(self, np.arange(n, dtype=np.int64), _sorted_unique=True)
 
     def add_TopologyAttr(self, attr, values=None):
         if isinstance(attr, str):
@@ -215,15 +216,15 @@ class Universe:
         self._tempfactors = values
 
     def select_atoms(self, selection: str):
-        return self._select(selection, self.atoms.ix)
+        return self._select(selection, self.atoms.ix, True)
 
-    def _select(self, selection: str, ix):
+    def _select(self, selection: str, ix, sorted_unique: bool = False):
         """Tiny selection language: ``all`` | ``[not] name A B ..`` | ``[not] resname A B ..``."""
         tokens = selection.split()
         if not tokens:
             raise ValueError("empty selection")
         if tokens == ["all"]:
-            return AtomGroup(self, ix)
+            return AtomGroup(self, ix, _sorted_unique=sorted_unique)
         negate = tokens[0] == "not"
         if negate:
             tokens = tokens[1:]
@@ -233,7 +234,7 @@ class Universe:
         mask = np.isin(field[ix].astype(str), tokens[1:])
         if negate:
             mask = ~mask
-        return AtomGroup(self, ix[mask])
+        return AtomGroup(self, ix[mask], _sorted_unique=sorted_unique)
 
 
 def is_atomgroup(obj) -> bool:

@@ -14,7 +14,7 @@ from mdvcontainment_b200.slab import DistGather, LocalGather, analyse_slabs, sla
 ap = argparse.ArgumentParser()
 ap.add_argument("--size", type=int, default=2048)
 ap.add_argument("--x", type=int, default=0, help="number of planes (default: size)")
-ap.add_argument("--salt", type=float, default=1e-4)
+ap.add_argument("--salt", type=float, default=1e-3)
 ap.add_argument("--reps", type=int, default=2)
 args = ap.parse_args()
 rank, world, local = (int(os.environ.get(k, d)) for k, d in (("RANK", 0), ("WORLD_SIZE", 1), ("LOCAL_RANK", 0)))
@@ -41,7 +41,7 @@ for _ in range(args.reps):
     times.append(time.perf_counter() - t0)
     labels, comps = res.labels[rank], res.components[rank]
 n_vox = float(shape[0]) * shape[1] * shape[2]
-total_counts = int(sum(int(v) for v in res.voxel_counts.values()))
+total_counts = int(res.count_values.sum())
 local_hist_ok = int(torch.count_nonzero(comps == 0).item()) == 0
 if rank == 0:
     print(json.dumps({
@@ -50,7 +50,10 @@ if rank == 0:
         "beyond_reference_limit": bool(n_vox >= 2 ** 31 - 2),
         "seconds_per_grid": min(times), "gvoxel_per_s": n_vox / min(times) / 1e9, "generate_s": t_gen,
         "labels": [res.n_true, res.n_false], "contacts": int(len(res.contacts)), "bridges": int(len(np.asarray(res.bridges).reshape(-1, 5))),
-        "components": len(res.voxel_counts), "counts_sum_equals_voxels": total_counts == int(n_vox),
-        "no_unlabelled_voxels_rank0": local_hist_ok, "dag_head": str(res).splitlines()[:6]}))
+        "components": int(len(res.dag)), "dag_edges": int(len(res.dag.edge_src)), "roots": len(res.dag.roots()),
+        "largest_components": sorted(((int(v), int(k)) for k, v in zip(res.count_ids[np.argsort(res.count_values)[-4:]],
+                                                                       np.sort(res.count_values)[-4:])), reverse=True),
+        "counts_sum_equals_voxels": total_counts == int(n_vox), "no_unlabelled_voxels_rank0": local_hist_ok,
+        "all_times_s": times, "timings_s": getattr(res, "timings", None)}))
 if world > 1:
     dist.destroy_process_group()
