@@ -191,6 +191,7 @@ class SlabResult:
         self.contacts = self.bridges = None
         self.n_true = self.n_false = 0
         self.labels = self.components = self.extents = self.merge = None
+        self.timings = {}
         self._graph = self._ranks = self._counts = None
 
     @property
@@ -246,8 +247,10 @@ def analyse_slabs(slab_bits: dict, shape, gather=None, morph_ops: str = "", want
     morph_ops   'd'/'e' string applied to the whole periodic grid first (halo planes exchanged)
 
     Returns a SlabResult; ``labels`` / ``components`` are {slab index: int32 CUDA tensor of the slab}."""
+    import time
     import torch
     from . import _lib, device as dev, host_graph as hg
+    t_start = time.perf_counter()
     X, Y, Z = (int(v) for v in shape)
     gather = gather or LocalGather(len(slab_bits))
     G = gather.n_slabs
@@ -302,17 +305,20 @@ def analyse_slabs(slab_bits: dict, shape, gather=None, morph_ops: str = "", want
                     "bridges": plan.bridges(), "volumes": plan.label_volumes()}
 
     # --- boundary pairs: last plane of slab g against the first plane of slab g+1 (ring) --------
+    t_local = time.perf_counter()
     firsts = gather.gather_tensors(first_planes)
     for g in own:
         local[g]["boundary"] = _plane_pairs(dev, last_planes[g], firsts[(g + 1) % G], 1 if g == G - 1 else 0)
     everything = gather.gather_objects(local)
 
     # --- global solve, identical on every rank ----------------------------------------------------
+    t_exchange = time.perf_counter()
     merged = merge_slabs([e["n_true"] for e in everything], [e["n_false"] for e in everything],
                          [e["boundary"] for e in everything], [e["contacts"] for e in everything],
                          [e["bridges"] for e in everything], [e["volumes"] for e in everything])
     NT, NF = merged["n_true"], merged["n_false"]
     uniq = np.concatenate([np.arange(-NF, 0, dtype=np.int32), np.arange(1, NT + 1, dtype=np.int32)])
+    t_merge = time.perf_counter()
     sol = hg.solve_periodic(uniq, merged["contacts"], merged["bridges"])
     comp_lut = sol.lut(NF, NT)
 
@@ -323,6 +329,7 @@ def analyse_slabs(slab_bits: dict, shape, gather=None, morph_ops: str = "", want
     res.dag, res.solution = sol.containment_dag(max_iterations=None), sol
     res.contacts, res.bridges, res.n_true, res.n_false = merged["contacts"], merged["bridges"], NT, NF
     res.extents, res.merge = ext, merged
+    t_graph = time.perf_counter()
 
     # --- dense grids of the owned slabs: one expand pass each ----------------------------------------
     res.labels, res.components = {}, {}
@@ -342,4 +349,7 @@ def analyse_slabs(slab_bits: dict, shape, gather=None, morph_ops: str = "", want
         comps = torch.empty(bits.shape, dtype=torch.int32, device=bits.words.device)
         plan.expand(bits, labels, comps)
         res.labels[g], res.components[g] = labels, comps
+    res.timings = {"morph_label_pairs_readback_s": t_local - t_start, "exchange_boundary_pairs_s": t_exchange - t_local,
+                   "merge_slabs_s": t_merge - t_exchange, "host_graph_s": t_graph - t_merge,
+                   "enqueue_dense_write_s": time.perf_counter() - t_graph}
     return res
