@@ -493,7 +493,10 @@ __device__ __forceinline__ uint4 not4(uint4 a) { return make_uint4(~a.x, ~a.y, ~
 // exchange tile is read for j0-1 and j0+2 only, the edge bits of both rows travel in one pair of shuffles, and the
 // per-plane overhead (mbarrier wait, barrier, pointers) is paid once per two rows.
 // E1 / E2: the first / second operation is an erosion (dilation of the complement); 'de' is <false, true>.
-template <int S, bool FULLZ, bool E1, bool E2>
+// ONE: a single operation (E1; E2 must be false): the first half of the pipeline only -- no exchange tile, one
+// z-dilation per plane -- for the odd operation of a morph string ('d', 'e', the last of 'dde'), which used to take
+// the word-per-thread kernel (114 us at 1024^3 against 69 us for two fused operations).
+template <int S, bool FULLZ, bool E1, bool E2, bool ONE>
 __global__ void __launch_bounds__(256)
 k_close_sweep2(const uint32_t *__restrict__ in, uint32_t *__restrict__ out, int X, int Y, int Z, int pitch, int nw,
                int lq_log2, int JR, int TX, uint32_t *__restrict__ row_counts) {
@@ -504,7 +507,7 @@ k_close_sweep2(const uint32_t *__restrict__ in, uint32_t *__restrict__ out, int 
     const int tile4 = JT * nq;
     uint4 *raw = (uint4 *)close_smem;                             // [S][JT][nq]
     uint4 *cmp = raw + S * tile4;                                 // [2][JT][nq]
-    uint64_t *full = (uint64_t *)(cmp + 2 * tile4);               // [S]
+    uint64_t *full = (uint64_t *)(cmp + (ONE ? 0 : 2) * tile4);   // [S]  (a single operation has no exchange tile)
     const int t = threadIdx.x;
     const int jr = t >> lq_log2, l = t & (LQ - 1);
     const int j0 = 2 * jr;
@@ -610,6 +613,27 @@ k_close_sweep2(const uint32_t *__restrict__ in, uint32_t *__restrict__ out, int 
         uint4 n0 = or4(or4(P0m2, P0m1), P0), n1 = or4(or4(P1m2, P1m1), P1);
         if (E1 != E2) { n0 = and4(not4(n0), vm); n1 = and4(not4(n1), vm); }
         P0m2 = P0m1; P0m1 = P0; P1m2 = P1m1; P1m1 = P1;
+        if (ONE) {
+            __syncthreads();                                      // every thread is done with this stage of the ring
+            if (t == 0 && s + S < n_in) issue(s + S, stage);
+            if (s >= 3 && s < n_in - 1) {                         // n0 / n1 = finished plane xs + s - 3
+                if (out0) op[0] = n0;
+                if (out1) op[nq] = n1;
+                op += plane4;
+                if (row_counts) {
+                    const QuadStarts s0 = mdvc_quad_starts(n0, vm, l, LQ), s1 = mdvc_quad_starts(n1, vm, l, LQ);
+                    uint32_t c0 = __popc(s0.s0) + __popc(s0.s1) + __popc(s0.s2) + __popc(s0.s3);
+                    uint32_t c1 = __popc(s1.s0) + __popc(s1.s1) + __popc(s1.s2) + __popc(s1.s3);
+                    uint32_t cc = c0 | (c1 << 16);
+                    for (int o = LQ >> 1; o > 0; o >>= 1) cc += __shfl_xor_sync(MDVC_FULL, cc, o, LQ);
+                    const size_t row0 = (size_t)(xs + s - 3) * Y + yout0;
+                    if (out0 && l == 0) row_counts[row0] = cc & 0xffffu;
+                    if (out1 && l == 0) row_counts[row0 + 1] = cc >> 16;
+                }
+            }
+            if (++stage == S) { stage = 0; phase ^= 1u; }
+            continue;
+        }
         uint4 *ex = cmp + (s & 1) * tile4 + me;
         if (lane_ok) { ex[0] = n0; ex[nq] = n1; }
         __syncthreads();
@@ -642,10 +666,11 @@ k_close_sweep2(const uint32_t *__restrict__ in, uint32_t *__restrict__ out, int 
     }
 }
 
-// 'd' immediately followed by 'e' on rows of at most 32 words.  Returns MDVC_OK with *done = 1 when the fused
-// kernel was launched, *done = 0 when the shape does not qualify (the caller then runs the two single steps).
-static int launch_close(const uint32_t *src, uint32_t *dst, int X, int Y, int Z, int pitch, bool e1, bool e2, cudaStream_t st,
-                        int *done, uint32_t *row_counts = nullptr, int *counted = nullptr) {
+// Two consecutive operations (e1 then e2) -- or, with `one`, the single operation e1 -- on rows of at most 32 words.
+// Returns MDVC_OK with *done = 1 when the TMA-staged kernel was launched, *done = 0 when the shape does not qualify
+// (the caller then runs the word-per-thread steps).
+static int launch_close(const uint32_t *src, uint32_t *dst, int X, int Y, int Z, int pitch, bool e1, bool e2, bool one,
+                        cudaStream_t st, int *done, uint32_t *row_counts = nullptr, int *counted = nullptr) {
     *done = 0;
     constexpr int S = 3;
     int nw = mdvc_words(Z);
@@ -655,7 +680,7 @@ static int launch_close(const uint32_t *src, uint32_t *dst, int X, int Y, int Z,
     int LQ = 1 << lq_log2;
     int JT = 2 * (256 / LQ);
     if (JT > Y + 4) JT = Y + 4;                                   // one tile covers all of y
-    size_t row_bytes = (size_t)(S + 2) * pitch * 4;
+    size_t row_bytes = (size_t)(S + (one ? 0 : 2)) * pitch * 4;
     int fit = (int)((48 * 1024 - S * 8) / row_bytes);
     if (JT > fit) JT = fit;
     if (JT < 5) JT = 5;
@@ -672,9 +697,14 @@ static int launch_close(const uint32_t *src, uint32_t *dst, int X, int Y, int Z,
     size_t smem = (size_t)JT * row_bytes + S * 8;
     dim3 grid(ny, xchunks);
     int threads = (((JT / 2) * LQ + 31) / 32) * 32;
-#define MDVC_CLOSE2(FZ, A, B) k_close_sweep2<S, FZ, A, B><<<grid, threads, smem, st>>>(src, dst, X, Y, Z, pitch, nw, lq_log2, JT / 2, TX, row_counts)
-    const int variant = (Z % 128 == 0 ? 4 : 0) | (e1 ? 2 : 0) | (e2 ? 1 : 0);
+#define MDVC_CLOSE2(FZ, A, B) k_close_sweep2<S, FZ, A, B, false><<<grid, threads, smem, st>>>(src, dst, X, Y, Z, pitch, nw, lq_log2, JT / 2, TX, row_counts)
+#define MDVC_CLOSE1(FZ, A) k_close_sweep2<S, FZ, A, false, true><<<grid, threads, smem, st>>>(src, dst, X, Y, Z, pitch, nw, lq_log2, JT / 2, TX, row_counts)
+    const int variant = one ? 8 + (Z % 128 == 0 ? 2 : 0) + (e1 ? 1 : 0) : (Z % 128 == 0 ? 4 : 0) | (e1 ? 2 : 0) | (e2 ? 1 : 0);
     switch (variant) {
+        case 8: MDVC_CLOSE1(false, false); break;
+        case 9: MDVC_CLOSE1(false, true); break;
+        case 10: MDVC_CLOSE1(true, false); break;
+        case 11: MDVC_CLOSE1(true, true); break;
         case 0: MDVC_CLOSE2(false, false, false); break;
         case 1: MDVC_CLOSE2(false, false, true); break;
         case 2: MDVC_CLOSE2(false, true, false); break;
@@ -685,6 +715,7 @@ static int launch_close(const uint32_t *src, uint32_t *dst, int X, int Y, int Z,
         default: MDVC_CLOSE2(true, true, true); break;
     }
 #undef MDVC_CLOSE2
+#undef MDVC_CLOSE1
     if (counted) *counted = row_counts != nullptr;
     MDVC_LAUNCH_CHECK();
     *done = 1;
@@ -757,12 +788,19 @@ static int morph_impl(const uint32_t *bits_in, uint32_t *bits_out, uint32_t *tmp
         int fused = 0;
         if (pair_at(i)) {
             const bool last = i + 2 == n_ops;                     // only the final grid's rows are worth counting
-            int rc = launch_close(src, dst, X, Y, Z, pitch, ops[i] == 'e', ops[i + 1] == 'e', st, &fused,
+            int rc = launch_close(src, dst, X, Y, Z, pitch, ops[i] == 'e', ops[i + 1] == 'e', false, st, &fused,
                                   last ? row_counts : nullptr, last ? counted : nullptr);
             if (rc) return rc;
         }
         if (fused) { ++i; src = dst; continue; }
         if (pair_at(i)) { mdvc_set_error_msg("fused morph pair declined after planning"); return MDVC_ERR_BADARG; }
+        if (can_fuse) {                                           // the odd operation on the same TMA-staged layout
+            const bool last = i + 1 == n_ops;
+            int rc = launch_close(src, dst, X, Y, Z, pitch, ops[i] == 'e', false, true, st, &fused,
+                                  last ? row_counts : nullptr, last ? counted : nullptr);
+            if (rc) return rc;
+            if (fused) { src = dst; continue; }
+        }
         int rc = launch_morph(src, dst, X, Y, Z, pitch, ops[i] == 'e', st);
         if (rc) return rc;
         src = dst;

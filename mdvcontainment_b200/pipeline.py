@@ -68,6 +68,20 @@ class FrameOutput:
         return self
 
 
+class _Range:
+    """NVTX range (visible in Nsight Systems / ncu --nvtx); a few hundred nanoseconds when no tool is attached."""
+
+    def __init__(self, name):
+        self.name = name
+
+    def __enter__(self):
+        torch.cuda.nvtx.range_push(self.name)
+
+    def __exit__(self, *exc):
+        torch.cuda.nvtx.range_pop()
+        return False
+
+
 def _check_positions(positions_dev):
     if positions_dev.dtype != torch.float32 or positions_dev.dim() != 2 or positions_dev.shape[1] != 3:
         raise ValueError(f"positions must be float32 [n,3], got {positions_dev.dtype} {tuple(positions_dev.shape)}")
@@ -173,30 +187,36 @@ class FramePipeline:
     # ---------------------------------------------------------------------------------------
     def voxelize(self, positions_dev: torch.Tensor) -> dev.BitGrid:
         """bin + morph; returns the final bit grid (device)."""
-        self.bits_a.words.zero_()
-        dev.bin_atoms(positions_dev, self.T, self.invT, self.nbox, self.bits_a)
+        with _Range("mdvc.bin"):
+            self.bits_a.words.zero_()
+            dev.bin_atoms(positions_dev, self.T, self.invT, self.nbox, self.bits_a)
         self._rows_counted = False
         if not self.ops:
             return self.bits_a
         X, Y, Z = self.shape
         counted = ctypes.c_int(0)                  # the fused closing also counts the runs per row of its result
+        torch.cuda.nvtx.range_push("mdvc.morph")
         rc = self.lib.mdvc_morph_counted(self.bits_a.words.data_ptr(), self.bits_b.words.data_ptr(),
                                          self.bits_tmp.words.data_ptr() if self.bits_tmp is not None else None,
                                          X, Y, Z, self.bits_a.pitch, self.ops.encode(),
                                          ctypes.c_void_p(self.plan.row_counts_ptr()), ctypes.byref(counted),
                                          ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+        torch.cuda.nvtx.range_pop()
         _lib.check(rc, "mdvc_morph_counted")
         self._rows_counted = bool(counted.value)
         return self.bits_b
 
     def _enqueue_stage1(self, bits: dev.BitGrid, rows_counted: bool = False, record: bool = True):
-        self.plan.label(bits, rows_counted)
-        self.plan.pairs(bits, self.periodic)
+        with _Range("mdvc.label"):
+            self.plan.label(bits, rows_counted)
+        with _Range("mdvc.pairs"):
+            self.plan.pairs(bits, self.periodic)
         # small results: four async copies into pinned memory, waited for in finish()
-        self.h_header.copy_(self.d_header, non_blocking=True)
-        self.h_contacts.copy_(self.d_contacts, non_blocking=True)
-        self.h_bridges.copy_(self.d_bridges, non_blocking=True)
-        self.h_volumes.copy_(self.d_volumes, non_blocking=True)
+        with _Range("mdvc.readback"):
+            self.h_header.copy_(self.d_header, non_blocking=True)
+            self.h_contacts.copy_(self.d_contacts, non_blocking=True)
+            self.h_bridges.copy_(self.d_bridges, non_blocking=True)
+            self.h_volumes.copy_(self.d_volumes, non_blocking=True)
         if record:
             self.ev_stage1.record()
 
@@ -222,7 +242,8 @@ class FramePipeline:
                 if self.pos_dev is None or self.pos_dev.shape[0] < n_pad:
                     self.pos_dev = torch.empty((n_pad, 3), dtype=torch.float32, device=self.device)
                     self._graphs.clear()                          # captured against the old buffer
-                self.pos_dev[:n].copy_(host_positions, non_blocking=True)
+                with _Range("mdvc.h2d_positions"):
+                    self.pos_dev[:n].copy_(host_positions, non_blocking=True)
                 if n_pad > n:
                     self.pos_dev[n:n_pad] = self.pos_dev[0]
                 positions_dev = self.pos_dev[:n_pad]
@@ -270,7 +291,8 @@ class FramePipeline:
                 torch.cuda.synchronize()
                 return False
         self._graph, self._graph_bits, _, n_launch = self._graphs[key]
-        self._graph.replay()
+        with _Range("mdvc.stage1(graph replay: bin, morph, label, pairs, readback)"):
+            self._graph.replay()
         self.replayed_launches += n_launch                        # kernels of this library launched by the replay
         self._bits = self._graph_bits
         self.ev_stage1.record()
@@ -324,9 +346,10 @@ class FramePipeline:
         hit = self._solved.get(key)
         self.memo_lookups += 1
         if hit is None:
-            sol = hg.solve_periodic(uniq, contacts, bridges)
-            lut = sol.lut(n_false, n_true)
-            dag = sol.containment_dag(max_iterations=None)         # no 100 000-component guard on this path
+            with _Range("mdvc.graph_stage(host)"):
+                sol = hg.solve_periodic(uniq, contacts, bridges)
+                lut = sol.lut(n_false, n_true)
+                dag = sol.containment_dag(max_iterations=None)     # no 100 000-component guard on this path
             if self.MEMO_SIZE:
                 if len(self._solved) >= self.MEMO_SIZE:
                     self._solved.pop(next(iter(self._solved)))
@@ -350,7 +373,8 @@ class FramePipeline:
             self.plan.set_lut(lut_dev)
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-            self.plan.expand(bits, self.labels, self.components)
+            with _Range("mdvc.expand"):
+                self.plan.expand(bits, self.labels, self.components)
             e1.record()
         self.expand_events.append((e0, e1))
         t2 = time.perf_counter()

@@ -190,7 +190,7 @@ class SlabResult:
         self.dag = self.solution = self.count_ids = self.count_values = None
         self.contacts = self.bridges = None
         self.n_true = self.n_false = 0
-        self.labels = self.components = self.extents = self.merge = None
+        self.labels = self.components = self.extents = self.merge = self.plans = None
         self.timings = {}
         self._graph = self._ranks = self._counts = None
 
@@ -217,7 +217,7 @@ class SlabResult:
         return hg.format_dag_structure(self.dag, self.component_ranks, self.voxel_counts)
 
 
-def _plane_pairs(dev, plane_a, plane_b, sx_boundary, n_slots=1 << 12):
+def _plane_pairs(dev, plane_a, plane_b, sx_boundary, n_slots=1 << 16):
     import torch
     from . import _lib
     lib = _lib.load()
@@ -238,13 +238,15 @@ def _plane_pairs(dev, plane_a, plane_b, sx_boundary, n_slots=1 << 12):
         n_slots *= 8
 
 
-def analyse_slabs(slab_bits: dict, shape, gather=None, morph_ops: str = "", want_labels=True):
+def analyse_slabs(slab_bits: dict, shape, gather=None, morph_ops: str = "", want_labels=True, plans: dict | None = None):
     """Containment analysis of a periodic grid given as x-slabs of bit grids.
 
     slab_bits   {slab index: BitGrid of that slab's own planes} for the slabs this process owns
     shape       (X, Y, Z) of the whole grid
     gather      LocalGather(G) (default, all slabs here) or DistGather() (one slab per rank)
     morph_ops   'd'/'e' string applied to the whole periodic grid first (halo planes exchanged)
+    plans       {slab index: FramePlan} of an earlier call on slabs of the same shape (``result.plans``): workspaces
+                and the capacities they grew to are reused instead of being rediscovered
 
     Returns a SlabResult; ``labels`` / ``components`` are {slab index: int32 CUDA tensor of the slab}."""
     import time
@@ -276,11 +278,14 @@ def analyse_slabs(slab_bits: dict, shape, gather=None, morph_ops: str = "", want
         slab_bits = new_bits
 
     # --- per-slab labelling, y/z-periodic pairs, boundary planes -------------------------------
-    plans, headers, first_planes, last_planes = {}, {}, {}, {}
+    plans_in, plans = plans, {}
+    headers, first_planes, last_planes = {}, {}, {}
     local = {}
     for g in own:
         bits = slab_bits[g]
-        plan = dev.FramePlan(bits.shape, device=bits.words.device)
+        plan = plans_in.get(g) if plans_in else None
+        if plan is None or plan.shape != tuple(bits.shape):
+            plan = dev.FramePlan(bits.shape, device=bits.words.device)
         for _ in range(6):
             plan.label(bits)
             plan.pairs(bits, periodic=2)
@@ -328,7 +333,7 @@ def analyse_slabs(slab_bits: dict, shape, gather=None, morph_ops: str = "", want
     # components): no guard here
     res.dag, res.solution = sol.containment_dag(max_iterations=None), sol
     res.contacts, res.bridges, res.n_true, res.n_false = merged["contacts"], merged["bridges"], NT, NF
-    res.extents, res.merge = ext, merged
+    res.extents, res.merge, res.plans = ext, merged, plans
     t_graph = time.perf_counter()
 
     # --- dense grids of the owned slabs: one expand pass each ----------------------------------------

@@ -104,15 +104,16 @@ def test_fused_closing_equals_two_steps(dev):
 
 @pytest.mark.parametrize("shape", FUSED_CLOSE_SHAPES)
 def test_counted_morph_leaves_the_runs_per_row(dev, shape):
-    """mdvc_morph_counted: the fused kernel also counts the z-runs of every row of its result (stage 1a of the
-    labelling); mdvc_frame_label_counted on those counts gives the same labels as the plain call."""
+    """mdvc_morph_counted: the TMA-staged kernel (two fused operations, or the odd single one) also counts the z-runs
+    of every row of its result (stage 1a of the labelling); mdvc_frame_label_counted on those counts gives the same
+    labels as the plain call."""
     import ctypes
     from mdvcontainment_b200 import _lib
     lib = _lib.load()
     rng = np.random.default_rng(7 + sum(shape))
     g = rng.random(shape) < 0.3
     X, Y, Z = shape
-    for ops in ("de", "edde", "d"):
+    for ops in ("de", "edde", "d", "e", "dde"):
         want = vo.morph(g, ops)
         src = dev.BitGrid.from_bool(g)
         out, tmp = dev.BitGrid(shape), dev.BitGrid(shape)
@@ -121,7 +122,7 @@ def test_counted_morph_leaves_the_runs_per_row(dev, shape):
         rc = lib.mdvc_morph_counted(src.words.data_ptr(), out.words.data_ptr(), tmp.words.data_ptr(), X, Y, Z, src.pitch,
                                     ops.encode(), ctypes.c_void_p(plan.row_counts_ptr()), ctypes.byref(counted),
                                     ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
-        assert rc == 0 and counted.value == (1 if len(ops) % 2 == 0 else 0)
+        assert rc == 0 and counted.value == 1            # pairs and the odd single operation both count (rows <= 32 words)
         assert np.array_equal(out.to_bool().cpu().numpy(), want)
         if counted.value:
             runs = 1 + (want[:, :, 1:] != want[:, :, :-1]).sum(axis=2)

@@ -19,17 +19,29 @@ def main():
     _, nbox, T, invT = voxel_transform(dims, 0.5)
     bits0 = dev.BitGrid((n, n, n))
     dev.bin_atoms(torch.from_numpy(pos).cuda(), T, invT, nbox, bits0)
-    for _ in range(3):
-        dev.morph(bits0, "de")
-    torch.cuda.synchronize()
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
-    ev[0].record()
-    for _ in range(reps):
-        dev.morph(bits0, "de")
-    ev[1].record()
-    torch.cuda.synchronize()
-    t = ev[0].elapsed_time(ev[1]) / reps
-    print(f"close {n}^3: {t * 1e3:8.1f} us   {n ** 3 / 4 / t / 1e6:8.1f} GB/s algorithmic (read+write of the bit grid)")
+    import ctypes
+    from mdvcontainment_b200 import _lib
+    lib = _lib.load()
+    out, tmp = dev.BitGrid((n, n, n)), dev.BitGrid((n, n, n))
+    st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    for ops in ("de", "d", "e", "dde"):
+        def run():
+            rc = lib.mdvc_morph(bits0.words.data_ptr(), out.words.data_ptr(), tmp.words.data_ptr(), n, n, n, bits0.pitch,
+                                ops.encode(), st)
+            assert rc == 0
+        for _ in range(3):
+            run()
+        torch.cuda.synchronize()
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+        ev[0].record()
+        for _ in range(reps):
+            run()
+        ev[1].record()
+        torch.cuda.synchronize()
+        t = ev[0].elapsed_time(ev[1]) / reps
+        launches = (len(ops) + 1) // 2
+        print(f"morph '{ops}' {n}^3: {t * 1e3:8.1f} us   {launches * n ** 3 / 4 / t / 1e6:8.1f} GB/s algorithmic "
+              f"({launches} launch(es), each reads + writes the bit grid once; preallocated buffers)")
 
 
 if __name__ == "__main__":
