@@ -87,12 +87,17 @@ __device__ __forceinline__ unsigned long long mdvc_mix64(unsigned long long k) {
     return k;
 }
 
-// returns false when the table is full (caller raises an overflow flag)
+// Returns false when no free slot turns up within MDVC_SET_MAX_PROBES probes: the table is full or so crowded that
+// it has to grow anyway (the caller raises an overflow flag and the host retries with more slots).  The bound matters:
+// probing a FULL table to the end costs n_slots loads per key, and a many-label grid pushed a million keys through
+// undersized tables that way (15 s for one 1024^3 noise grid before the bound, milliseconds after).
+#define MDVC_SET_MAX_PROBES 128u
 __device__ __forceinline__ bool mdvc_set_insert(unsigned long long *slots, uint32_t n_slots,
                                                 unsigned long long key) {
     uint32_t mask = n_slots - 1;
     uint32_t h = (uint32_t)mdvc_mix64(key) & mask;
-    for (uint32_t probe = 0; probe < n_slots; ++probe) {
+    const uint32_t limit = n_slots < MDVC_SET_MAX_PROBES ? n_slots : MDVC_SET_MAX_PROBES;
+    for (uint32_t probe = 0; probe < limit; ++probe) {
         unsigned long long cur = __ldcg(&slots[h]);
         if (cur == key) return true;
         if (cur == MDVC_KEY_EMPTY) {

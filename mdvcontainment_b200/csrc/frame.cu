@@ -1084,6 +1084,7 @@ struct PairSink {
         last2 = last;
         last = key;
         if (!cache->add(key)) return;
+        if (*(volatile uint32_t *)flags & overflow_bit) return;       // already overflowed: this attempt is void anyway
         if (!mdvc_set_insert(slots, n_slots, key)) atomicOr(flags, overflow_bit);
     }
 };
