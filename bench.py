@@ -356,8 +356,17 @@ def run_ours(args):
     set_memo(True)
     run_frames(n_flight * n_scenes, False)
 
-    # plain pinned-host -> device copy ceiling with all ranks copying at once (what bounds the e2e leg)
+    # plain pinned-host -> device copy ceiling with all ranks copying at once (what bounds the e2e leg), from ordinary
+    # page-locked memory and from write-combined page-locked memory
     h2d = h2d_ceiling(torch, dist, world, pos_pinned[0], pipe.pos_dev)
+    try:
+        from mdvcontainment_b200 import device as dev
+        wc = dev.staging_empty(pos_pinned[0].shape, torch.float32, write_combined=True)
+        wc.copy_(pos_pinned[0])
+        h2d["write_combined"] = h2d_ceiling(torch, dist, world, wc, pipe.pos_dev)
+        del wc
+    except Exception as exc:                            # noqa: BLE001 - informational measurement
+        h2d["write_combined"] = {"error": repr(exc)}
 
     # the dominant kernel alone (one frame at a time, nothing else on the GPU), for the roofline's context
     iso = []

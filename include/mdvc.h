@@ -46,6 +46,12 @@ int mdvc_row_pitch_words(int Z);
 /* number of CUDA kernels this library has launched so far in the calling process (for benchmarks) */
 unsigned long long mdvc_launch_count(void);
 
+/* Page-locked HOST staging memory for the coordinate copies (N1: the trajectory driver's buffers; the reference
+ * reads atomgroup.positions from pageable NumPy memory, mda_containment.py:385-388).  write_combined != 0: memory the
+ * CPU only writes sequentially and the GPU only reads by DMA.  The caller frees with mdvc_host_free. */
+int mdvc_host_alloc(size_t bytes, int write_combined, void **ptr_out_host);
+int mdvc_host_free(void *ptr_host);
+
 /* ---------------------------------------------------------------------------------------
  * T1  bool grid <-> bit grid        (reference type: dense bool ndarray,
  *     atomgroup_to_voxels.py:195-197; containment_main.py:460)

@@ -45,6 +45,8 @@ SIGNATURES = {
     "mdvc_last_error": (ctypes.c_char_p, []),
     "mdvc_row_pitch_words": (_I, [_I]),
     "mdvc_launch_count": (_U64, []),
+    "mdvc_host_alloc": (_I, [_SZ, _I, _P]),
+    "mdvc_host_free": (_I, [_P]),
     "mdvc_pack_bool": (_I, [_P, _I, _I, _I, _P, _I, _P]),
     "mdvc_unpack_bool": (_I, [_P, _I, _I, _I, _I, _P, _P]),
     "mdvc_popcount": (_I, [_P, _I, _I, _I, _I, _P, _P]),

@@ -24,6 +24,24 @@ extern "C" const char *mdvc_last_error(void) { return g_err; }
 extern "C" int mdvc_row_pitch_words(int Z) { return ((mdvc_words(Z) + 3) / 4) * 4; }
 
 // ------------------------------------------------------------------------------------------
+// host staging memory
+// ------------------------------------------------------------------------------------------
+// Page-locked host memory for coordinate staging buffers.  write_combined: uncached on the CPU side -- right for
+// buffers the host only ever fills front to back and the GPU reads by DMA (no cache snooping on the PCIe reads);
+// never read such a buffer from the CPU.
+extern "C" int mdvc_host_alloc(size_t bytes, int write_combined, void **ptr_out_host) {
+    if (!ptr_out_host || bytes == 0) return MDVC_ERR_BADARG;
+    *ptr_out_host = nullptr;
+    MDVC_CUDA_CHECK(cudaHostAlloc(ptr_out_host, bytes, cudaHostAllocPortable | (write_combined ? cudaHostAllocWriteCombined : 0)));
+    return MDVC_OK;
+}
+extern "C" int mdvc_host_free(void *ptr_host) {
+    if (!ptr_host) return MDVC_OK;
+    MDVC_CUDA_CHECK(cudaFreeHost(ptr_host));
+    return MDVC_OK;
+}
+
+// ------------------------------------------------------------------------------------------
 // T1  pack / unpack
 // ------------------------------------------------------------------------------------------
 // One warp packs 32 voxels per ballot; lanes walk z so byte loads are contiguous.

@@ -110,6 +110,39 @@ def bin_atoms(pos: torch.Tensor, T, invT, nbox, bits: BitGrid | None, want_voxel
 
 
 # ---------------------------------------------------------------------------------------------
+# host staging memory
+# ---------------------------------------------------------------------------------------------
+class _HostBlock:
+    """Owner of one mdvc_host_alloc block (freed with the last tensor that views it)."""
+
+    def __init__(self, nbytes, write_combined):
+        self.ptr = ctypes.c_void_p()
+        check(_lib.load().mdvc_host_alloc(int(nbytes), int(bool(write_combined)), ctypes.byref(self.ptr)), "mdvc_host_alloc")
+        self.nbytes = int(nbytes)
+
+    def __del__(self):
+        try:
+            if self.ptr:
+                _lib.load().mdvc_host_free(self.ptr)
+                self.ptr = ctypes.c_void_p()
+        except Exception:                               # noqa: BLE001 - interpreter shutdown
+            pass
+
+
+def staging_empty(shape, dtype=torch.float32, write_combined=True) -> torch.Tensor:
+    """Page-locked host tensor for H2D staging.  ``write_combined``: fill it front to back, never read it on the CPU."""
+    _require_cuda()
+    shape = tuple(int(v) for v in shape)
+    n = int(np.prod(shape)) if shape else 1
+    item = torch.empty((), dtype=dtype).element_size()
+    block = _HostBlock(max(n * item, 1), write_combined)
+    buf = (ctypes.c_uint8 * block.nbytes).from_address(block.ptr.value)
+    buf._mdvc_block = block                            # tensor storage -> NumPy array -> ctypes buffer -> allocation
+    arr = np.frombuffer(buf, dtype=np.uint8)
+    return torch.from_numpy(arr)[: n * item].view(dtype).reshape(shape)
+
+
+# ---------------------------------------------------------------------------------------------
 # device tensor -> NumPy array
 # ---------------------------------------------------------------------------------------------
 _PINNED = []          # two reusable pinned staging buffers (uint8)

@@ -131,8 +131,25 @@ def merge_slabs(n_true, n_false, boundary_rows, local_contacts, local_bridges, l
             if (~inbox).any():
                 bridges.append(_normalise_bridges(ga[~inbox], gb[~inbox], rows[~inbox][:, 2:]))
     volumes[NF] = 0
-    contacts = np.unique(np.concatenate(contacts), axis=0).astype(np.int32) if contacts else np.empty((0, 2), np.int32)
-    bridges = np.unique(np.concatenate(bridges), axis=0).astype(np.int32) if bridges else np.array([], dtype=np.int32)
+    # sorted unique rows through one packed int64 key per row (lexicographic order of the key == of the row);
+    # np.unique(axis=0) sorts rows as structured records and takes most of a second per million rows
+    R = np.int64(NF + NT + 1)
+    if contacts:
+        c = np.concatenate(contacts)
+        key = np.unique((c[:, 0] + NF) * R + (c[:, 1] + NF))
+        contacts = np.stack([key // R - NF, key % R - NF], 1).astype(np.int32)
+    else:
+        contacts = np.empty((0, 2), np.int32)
+    if bridges and int(R) * int(R) * 27 < 2 ** 63:
+        b = np.concatenate(bridges)
+        code = (b[:, 2] + 1) * 9 + (b[:, 3] + 1) * 3 + (b[:, 4] + 1)
+        key = np.unique(((b[:, 0] + NF) * R + (b[:, 1] + NF)) * 27 + code)
+        code, pair = key % 27, key // 27
+        bridges = np.stack([pair // R - NF, pair % R - NF, code // 9 - 1, code // 3 % 3 - 1, code % 3 - 1], 1).astype(np.int32)
+    elif bridges:
+        bridges = np.unique(np.concatenate(bridges), axis=0).astype(np.int32)
+    else:
+        bridges = np.array([], dtype=np.int32)
     return {"luts": luts, "n_true": NT, "n_false": NF, "contacts": contacts, "bridges": bridges, "volumes": volumes}
 
 

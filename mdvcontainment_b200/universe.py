@@ -157,7 +157,14 @@ class AtomGroup:
         if item.size == 0:
             return AtomGroup(self._u, np.empty(0, dtype=np.int64))
         if item.dtype == bool:
-            return AtomGroup(self._u, self._ix[item])
+            return AtomGroup(self._u, self._ix[item], _sorted_unique=self._sorted_unique)
+        if self._range is not None and self._range[0] == 0:
+            # indexing the whole-universe group: ix[item] == item (a gather over 10^7 indices otherwise)
+            item = item.astype(np.int64, copy=False)
+            n = len(self._ix)
+            if item.size and (int(item.min()) < -n or int(item.max()) >= n):
+                raise IndexError("atom index out of range")
+            return AtomGroup(self._u, np.where(item < 0, item + n, item) if item.size and int(item.min()) < 0 else item)
         return AtomGroup(self._u, self._ix[item.astype(np.int64)])
 
     def __sub__(self, other):
