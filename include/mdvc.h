@@ -74,6 +74,17 @@ int mdvc_bin_atoms(const float *pos, long long n, const double *T_host, const do
                    const long long *nbox_host, uint32_t *occ_bits, int pitch,
                    int32_t *vox_out, float *pos_out, void *stream);
 
+/* A1 into a grid that this call also CLEARS (the usual case: one occupancy grid per frame).  Same arguments as
+ * mdvc_bin_atoms plus a scratch buffer of mdvc_bin_scratch_bytes(n) bytes (16-byte aligned device memory; NULL or
+ * too small = clear + mdvc_bin_atoms).  Beads are first bucketed by x-plane range, then the grid is cleared and
+ * filled range by range so that the clearing stores and the atomics of a range meet in the L2: the coordinates are
+ * read once and the grid is written once, instead of one DRAM read-modify-write per bead.  Result identical to
+ * clear + mdvc_bin_atoms (the OR of the same bits). */
+size_t mdvc_bin_scratch_bytes(long long n);
+int mdvc_bin_grid(const float *pos, long long n, const double *T_host, const double *invT_host,
+                  const long long *nbox_host, uint32_t *occ_bits, int pitch, int32_t *vox_out, float *pos_out,
+                  void *scratch, size_t scratch_bytes, void *stream);
+
 /* ---------------------------------------------------------------------------------------
  * A3/A4  morphology  replaces dilate_voxels / erode_voxels / morph_voxels / close_voxels
  *     (atomgroup_to_voxels.py:242-308): periodic 3x3x3 dilation 'd' / erosion 'e', applied left

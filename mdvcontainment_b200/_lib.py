@@ -51,6 +51,8 @@ SIGNATURES = {
     "mdvc_unpack_bool": (_I, [_P, _I, _I, _I, _I, _P, _P]),
     "mdvc_popcount": (_I, [_P, _I, _I, _I, _I, _P, _P]),
     "mdvc_bin_atoms": (_I, [_P, _LL, _P, _P, _P, _P, _I, _P, _P, _P]),
+    "mdvc_bin_scratch_bytes": (_SZ, [_LL]),
+    "mdvc_bin_grid": (_I, [_P, _LL, _P, _P, _P, _P, _I, _P, _P, _P, _SZ, _P]),
     "mdvc_morph": (_I, [_P, _P, _P, _I, _I, _I, _I, ctypes.c_char_p, _P]),
     "mdvc_morph_counted": (_I, [_P, _P, _P, _I, _I, _I, _I, ctypes.c_char_p, _P, _P, _P]),
     "mdvc_frame_workspace_bytes": (_SZ, [_I, _I, _I, _CAPS]),

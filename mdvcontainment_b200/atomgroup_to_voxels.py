@@ -144,8 +144,9 @@ def voxelize_on_device(atomgroup, resolution, max_offset=0.05, want_mapping=True
     shape = tuple(int(v) for v in np.diagonal(nbox))
     if positions_dev is None:
         positions_dev = positions_to_device(atomgroup)
-    bits = dev.BitGrid(shape)
-    vox, newpos = dev.bin_atoms(positions_dev, T, invT, nbox, bits, want_voxels=want_mapping, want_positions=True)
+    bits = dev.BitGrid(shape, words=torch.empty((shape[0], shape[1], dev.pitch_words(shape[2])), dtype=torch.int32,
+                                                device=positions_dev.device))
+    vox, newpos = dev.bin_grid(positions_dev, T, invT, nbox, bits, want_voxels=want_mapping, want_positions=True)
     positions_from_device(atomgroup, newpos)
     return bits, vox, newpos
 

@@ -299,6 +299,165 @@ extern "C" int mdvc_bin_atoms(const float *pos, long long n, const double *T_hos
 }
 
 // ------------------------------------------------------------------------------------------
+// A1  binning into a freshly cleared grid, x-chunk by x-chunk
+// ------------------------------------------------------------------------------------------
+// The plain kernels above fire one RED.OR per bead at a grid that does not fit the L2 (128 MiB at 1024^3) in an
+// order that has nothing to do with the grid: every RED is a read-modify-write of a random 32-byte DRAM sector
+// (ncu: 475 MB of DRAM traffic + the 128 MB memset for 122 MB of coordinates, and the kernel's whole duration
+// comes straight off the frame time because that scattered traffic shares the DRAM with the dense write).
+// Here the beads are first dropped into at most BIN_CHUNKS buckets by x-plane range (a per-CTA count in shared
+// memory, one global atomicAdd per CTA and bucket to reserve a contiguous stretch, keys written next to each other),
+// then the grid is cleared and filled one plane range at a time: a range is 16 MiB at 1024^3, so its clearing stores
+// and its REDs meet in the L2 and every line goes to DRAM once.  DRAM traffic: coordinates read once, 4 B/bead of keys
+// (L2-resident), grid written once.
+#define BIN_CHUNKS 8
+#define BIN_TILE_ATOMS 2048                  // 256 threads x 8 beads per iteration
+
+struct BinBuckets {
+    uint32_t *cursor;        // [BIN_CHUNKS] beads offered to each bucket (may exceed cap), [BIN_CHUNKS] = spill count
+    uint32_t *keys;          // [BIN_CHUNKS][cap] then the spill list [n]
+    uint32_t cap;
+    int px_shift;            // bucket = x >> px_shift
+    uint32_t row_bits;       // pitch * 32: key = row * row_bits + z  (word = key >> 5, bit = key & 31)
+};
+
+__global__ void __launch_bounds__(256, 3)
+k_bin_bucket(const float *__restrict__ pos, long long n, BinParams P, BinBuckets B, int32_t *__restrict__ vox_out, float *pos_out) {
+    __shared__ uint32_t s_cnt[BIN_CHUNKS], s_base[BIN_CHUNKS];
+    const long long n4 = n >> 2;                                  // groups of four beads (three float4)
+    const long long tile_groups = BIN_TILE_ATOMS / 4;
+    const long long n_tiles = (n4 + tile_groups - 1) / tile_groups;
+    const uint32_t Y = (uint32_t)P.nbox[4];
+    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        if (threadIdx.x < BIN_CHUNKS) s_cnt[threadIdx.x] = 0;
+        __syncthreads();
+        uint32_t key[8], slot[8];
+        int bucket[8];
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            const long long g = tile * tile_groups + half * 256 + threadIdx.x;
+            if (g < n4) {
+                const float4 *src = reinterpret_cast<const float4 *>(pos) + 3 * g;
+                const float4 q0 = __ldcs(src), q1 = __ldcs(src + 1), q2 = __ldcs(src + 2);
+                const float f[12] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w};
+                int32_t v[12];
+                float w[12];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    int vk[3];
+                    float wk[3];
+                    const bool inside = bin_one_atom(f[3 * k], f[3 * k + 1], f[3 * k + 2], P, pos_out != nullptr, vk, wk);
+#pragma unroll
+                    for (int j = 0; j < 3; ++j) { v[3 * k + j] = vk[j]; w[3 * k + j] = wk[j]; }
+                    bucket[4 * half + k] = inside ? (vk[0] >> B.px_shift) : -1;
+                    key[4 * half + k] = ((uint32_t)vk[0] * Y + (uint32_t)vk[1]) * B.row_bits + (uint32_t)vk[2];
+                }
+                if (vox_out) {
+                    int4 *dst = reinterpret_cast<int4 *>(vox_out) + 3 * g;
+                    dst[0] = make_int4(v[0], v[1], v[2], v[3]);
+                    dst[1] = make_int4(v[4], v[5], v[6], v[7]);
+                    dst[2] = make_int4(v[8], v[9], v[10], v[11]);
+                }
+                if (pos_out) {
+                    float4 *dst = reinterpret_cast<float4 *>(pos_out) + 3 * g;
+                    dst[0] = make_float4(w[0], w[1], w[2], w[3]);
+                    dst[1] = make_float4(w[4], w[5], w[6], w[7]);
+                    dst[2] = make_float4(w[8], w[9], w[10], w[11]);
+                }
+            } else {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) bucket[4 * half + k] = -1;
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+            if (bucket[k] >= 0) slot[k] = atomicAdd(&s_cnt[bucket[k]], 1u);
+        __syncthreads();
+        if (threadIdx.x < BIN_CHUNKS) s_base[threadIdx.x] = s_cnt[threadIdx.x] ? atomicAdd(&B.cursor[threadIdx.x], s_cnt[threadIdx.x]) : 0u;
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            if (bucket[k] < 0) continue;
+            const uint32_t at = s_base[bucket[k]] + slot[k];
+            if (at < B.cap) B.keys[(size_t)bucket[k] * B.cap + at] = key[k];
+            else B.keys[(size_t)BIN_CHUNKS * B.cap + atomicAdd(&B.cursor[BIN_CHUNKS], 1u)] = key[k];   // bucket full: spill list
+        }
+        __syncthreads();                                          // s_base is reused by the next tile
+    }
+}
+
+// the REDs of one key list (a bucket, or the spill list): count read from device memory
+__global__ void __launch_bounds__(256)
+k_bin_keys(const uint32_t *__restrict__ keys, const uint32_t *__restrict__ count_ptr, uint32_t cap, uint32_t *__restrict__ occ) {
+    const uint32_t n = min(*count_ptr, cap);
+    const uint32_t stride = gridDim.x * blockDim.x;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const uint32_t k = __ldcs(keys + i);
+        atomicOr(&occ[k >> 5], 1u << (k & 31));
+    }
+}
+
+extern "C" size_t mdvc_bin_scratch_bytes(long long n) {
+    if (n < 0) return 0;
+    const size_t cap = (((size_t)n * 2 / BIN_CHUNKS + 3) & ~(size_t)3) + 1024;
+    return (64 + BIN_CHUNKS * cap + (size_t)n) * sizeof(uint32_t);
+}
+
+extern "C" int mdvc_bin_grid(const float *pos, long long n, const double *T_host, const double *invT_host,
+                             const long long *nbox_host, uint32_t *occ_bits, int pitch, int32_t *vox_out, float *pos_out,
+                             void *scratch, size_t scratch_bytes, void *stream) {
+    if (n < 0 || !T_host || !invT_host || !nbox_host || !occ_bits || (n > 0 && !pos)) return MDVC_ERR_BADARG;
+    const long long X = nbox_host[0], Y = nbox_host[4], Z = nbox_host[8];
+    if (X <= 0 || Y <= 0 || Z <= 0 || pitch < mdvc_words((int)Z) || X * Y * Z >= (1ll << 31)) return MDVC_ERR_BADARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t plane_words = (size_t)Y * pitch, grid_bytes = (size_t)X * plane_words * sizeof(uint32_t);
+    const unsigned long long grid_bits = (unsigned long long)X * plane_words * 32ull;
+    const uintptr_t ptrs = (uintptr_t)pos | (uintptr_t)vox_out | (uintptr_t)pos_out;
+    // small inputs, unaligned arrays, grids whose padded bit count does not fit 32 bits or a missing / short scratch:
+    // clear everything and take the plain kernels
+    if (n < 4 * BIN_TILE_ATOMS || (ptrs & 15) != 0 || grid_bits >= (1ull << 32) || !scratch ||
+        scratch_bytes < mdvc_bin_scratch_bytes(n) || ((uintptr_t)scratch & 15) != 0) {
+        MDVC_CUDA_CHECK(cudaMemsetAsync(occ_bits, 0, grid_bytes, st));
+        return mdvc_bin_atoms(pos, n, T_host, invT_host, nbox_host, occ_bits, pitch, vox_out, pos_out, stream);
+    }
+    BinParams P;
+    memcpy(P.T, T_host, sizeof(P.T));
+    memcpy(P.invT, invT_host, sizeof(P.invT));
+    memcpy(P.nbox, nbox_host, sizeof(P.nbox));
+    P.fits32 = 1;
+    for (int k = 0; k < 9; ++k) {
+        if (nbox_host[k] <= -(1ll << 28) || nbox_host[k] >= (1ll << 28)) P.fits32 = 0;
+        P.nbox32[k] = (int)nbox_host[k];
+    }
+    BinBuckets B;
+    B.cursor = reinterpret_cast<uint32_t *>(scratch);
+    B.keys = B.cursor + 64;
+    B.cap = (uint32_t)((((size_t)n * 2 / BIN_CHUNKS + 3) & ~(size_t)3) + 1024);
+    B.px_shift = 0;
+    while (((X + (1ll << B.px_shift) - 1) >> B.px_shift) > BIN_CHUNKS) ++B.px_shift;
+    B.row_bits = (uint32_t)pitch * 32u;
+    const int n_chunks = (int)((X + (1ll << B.px_shift) - 1) >> B.px_shift);
+    MDVC_CUDA_CHECK(cudaMemsetAsync(B.cursor, 0, 64 * sizeof(uint32_t), st));
+    const long long n_tiles = ((n >> 2) + BIN_TILE_ATOMS / 4 - 1) / (BIN_TILE_ATOMS / 4);
+    k_bin_bucket<<<mdvc_grid(n_tiles * 256, 256, 3), 256, 0, st>>>(pos, n, P, B, vox_out, pos_out);
+    MDVC_LAUNCH_CHECK();
+    for (int c = 0; c < n_chunks; ++c) {
+        const long long x0 = (long long)c << B.px_shift, x1 = (x0 + (1ll << B.px_shift)) < X ? x0 + (1ll << B.px_shift) : X;
+        MDVC_CUDA_CHECK(cudaMemsetAsync(occ_bits + (size_t)x0 * plane_words, 0, (size_t)(x1 - x0) * plane_words * sizeof(uint32_t), st));
+        k_bin_keys<<<mdvc_grid((long long)B.cap, 256, 4), 256, 0, st>>>(B.keys + (size_t)c * B.cap, B.cursor + c, B.cap, occ_bits);
+        MDVC_LAUNCH_CHECK();
+    }
+    // beads that found their bucket full (very uneven systems) and the last n % 4 beads
+    k_bin_keys<<<mdvc_grid(n, 256, 4), 256, 0, st>>>(B.keys + (size_t)BIN_CHUNKS * B.cap, B.cursor + BIN_CHUNKS, (uint32_t)n, occ_bits);
+    MDVC_LAUNCH_CHECK();
+    if (n & 3) {
+        k_bin_atoms1<<<1, 256, 0, st>>>(pos, n & ~3ll, n, P, occ_bits, pitch, vox_out, pos_out);
+        MDVC_LAUNCH_CHECK();
+    }
+    return MDVC_OK;
+}
+
+// ------------------------------------------------------------------------------------------
 // A3/A4  morphology (periodic 3x3x3), one output word per thread
 // ------------------------------------------------------------------------------------------
 // z-dilation of word w of one row, periodic in z.  invert: operate on the complement (erosion).

@@ -109,6 +109,31 @@ def bin_atoms(pos: torch.Tensor, T, invT, nbox, bits: BitGrid | None, want_voxel
     return vox, newpos
 
 
+def bin_scratch(n: int, device) -> torch.Tensor:
+    """Scratch for ``bin_grid`` (bucketed bead keys), reusable for any bead count <= n."""
+    return torch.empty(max(int(_lib.load().mdvc_bin_scratch_bytes(int(n))), 16), dtype=torch.uint8, device=device)
+
+
+def bin_grid(pos: torch.Tensor, T, invT, nbox, bits: BitGrid, scratch: torch.Tensor | None = None, want_voxels=False,
+             want_positions=False):
+    """A1 into ``bits``, which this call also clears (no separate memset): beads bucketed by x-plane range, the grid
+    cleared and filled range by range inside the L2 (``mdvc_bin_grid``).  Returns (voxels | None, positions | None)."""
+    n = int(pos.shape[0])
+    Tc = np.ascontiguousarray(T, dtype=np.float64)
+    iTc = np.ascontiguousarray(invT, dtype=np.float64)
+    nb = np.ascontiguousarray(nbox, dtype=np.int64)
+    need = int(_lib.load().mdvc_bin_scratch_bytes(n))
+    if scratch is None or scratch.numel() < need:
+        scratch = bin_scratch(n, pos.device)
+    vox = torch.empty((n, 3), dtype=torch.int32, device=pos.device) if want_voxels else None
+    newpos = torch.empty((n, 3), dtype=torch.float32, device=pos.device) if want_positions else None
+    rc = _lib.load().mdvc_bin_grid(_ptr(pos), n, Tc.ctypes.data_as(ctypes.c_void_p), iTc.ctypes.data_as(ctypes.c_void_p),
+                                   nb.ctypes.data_as(ctypes.c_void_p), _ptr(bits.words), bits.pitch, _ptr(vox), _ptr(newpos),
+                                   _ptr(scratch), int(scratch.numel()), _stream())
+    check(rc, "mdvc_bin_grid")
+    return vox, newpos
+
+
 # ---------------------------------------------------------------------------------------------
 # host staging memory
 # ---------------------------------------------------------------------------------------------

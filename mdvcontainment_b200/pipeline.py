@@ -126,6 +126,7 @@ class FramePipeline:
         self.pos_dev = torch.empty((cap, 3), dtype=torch.float32, device=self.device) if max_atoms else None
         self.lut_dev = None
         self.lib = _lib.load()
+        self.bin_scratch = dev.bin_scratch(cap, self.device) if max_atoms else None
         self._alloc_host()
         # stage 1 (bin .. pairs: latency/issue-bound, small) on a high-priority stream, the dense write (HBM-bound,
         # tens of thousands of short CTAs) on a low-priority one: with several pipelines in flight the block
@@ -185,11 +186,16 @@ class FramePipeline:
         self._alloc_host()
 
     # ---------------------------------------------------------------------------------------
+    def _ensure_bin_scratch(self, n: int):
+        if self.bin_scratch is None or self.bin_scratch.numel() < self.lib.mdvc_bin_scratch_bytes(int(n)):
+            self.bin_scratch = dev.bin_scratch(int(n), self.device)
+            self._graphs.clear()                                  # captured against the old scratch
+
     def voxelize(self, positions_dev: torch.Tensor) -> dev.BitGrid:
         """bin + morph; returns the final bit grid (device)."""
         with _Range("mdvc.bin"):
-            self.bits_a.words.zero_()
-            dev.bin_atoms(positions_dev, self.T, self.invT, self.nbox, self.bits_a)
+            self._ensure_bin_scratch(int(positions_dev.shape[0]))
+            dev.bin_grid(positions_dev, self.T, self.invT, self.nbox, self.bits_a, self.bin_scratch)   # clears + bins
         self._rows_counted = False
         if not self.ops:
             return self.bits_a
@@ -231,6 +237,8 @@ class FramePipeline:
         if positions_dev is not None:
             _check_positions(positions_dev)
             positions_dev.record_stream(self.stream)         # the caching allocator must not recycle it under us
+        n_beads = int((host_positions if host_positions is not None else positions_dev).shape[0])
+        self._ensure_bin_scratch(-(-n_beads // self.ATOM_QUANTUM) * self.ATOM_QUANTUM)    # before any graph capture
         with torch.cuda.stream(self.stream):
             if host_positions is not None:
                 # Frames of a trajectory differ in their bead count (selections, breathing shells): the count is a launch

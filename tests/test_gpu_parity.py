@@ -143,6 +143,50 @@ def test_morph_rejects_unknown_op(dev):
 
 
 # ------------------------------------------------------------------------------------------ A1
+@pytest.mark.parametrize("case", ["uniform", "one_plane_range", "two_blobs", "outside_and_far"])
+@pytest.mark.parametrize("n", [8192, 50001, 262147])
+def test_bin_grid_bucketed_path_equals_plain_binning(dev, case, n):
+    """mdvc_bin_grid (beads bucketed by x-plane range, grid cleared and filled range by range) against clear +
+    mdvc_bin_atoms and the oracle: same occupancy, voxels and rewritten positions -- for even and very uneven bead
+    distributions (a full bucket spills), bead counts that are no multiple of four, beads far outside the box."""
+    rng = np.random.default_rng(n + len(case))
+    dims = np.array([403.0, 251.5, 330.0, 90, 90, 90], dtype=np.float32)
+    res = 0.5
+    _, nbox, T, invT = vo.voxel_transform(dims, res)
+    shape = tuple(int(v) for v in np.diagonal(nbox))
+    box = dims[:3]
+    if case == "uniform":
+        pos = rng.random((n, 3)) * box
+    elif case == "one_plane_range":
+        pos = rng.random((n, 3)) * box * np.array([0.04, 1, 1]) + np.array([0.5 * box[0], 0, 0])
+    elif case == "two_blobs":
+        pos = np.concatenate([rng.normal(0.2, 0.02, (n // 2, 3)), rng.normal(0.8, 0.05, (n - n // 2, 3))]) * box
+    else:
+        pos = (rng.random((n, 3)) * 7 - 3) * box
+    pos = np.round(pos, 2).astype(np.float32)
+    pos_d = torch.from_numpy(pos).cuda()
+    plain = dev.BitGrid(shape)
+    v0, p0 = dev.bin_atoms(pos_d, T, invT, nbox, plain, want_voxels=True, want_positions=True)
+    junk = torch.full((shape[0], shape[1], dev.pitch_words(shape[2])), -1, dtype=torch.int32, device="cuda")
+    fresh = dev.BitGrid(shape, words=junk)                      # must be cleared by the call itself
+    v1, p1 = dev.bin_grid(pos_d, T, invT, nbox, fresh, want_voxels=True, want_positions=True)
+    assert torch.equal(fresh.words, plain.words)
+    assert torch.equal(v0, v1) and torch.equal(p0.view(torch.int32), p1.view(torch.int32))
+    vox, _, newpos = vo.voxelate_fma(pos, dims, res)
+    assert np.array_equal(fresh.to_bool().cpu().numpy(), vo.occupancy(vox, nbox))
+    assert np.array_equal(v1.cpu().numpy(), vox.astype(np.int32))
+    # occupancy only, into a reused scratch, unaligned view (falls back to the plain kernels)
+    scratch = dev.bin_scratch(n, "cuda")
+    again = dev.BitGrid(shape, words=torch.full_like(junk, 7))
+    dev.bin_grid(pos_d, T, invT, nbox, again, scratch)
+    assert torch.equal(again.words, plain.words)
+    odd = dev.BitGrid(shape, words=torch.full_like(junk, 7))
+    dev.bin_grid(pos_d[1:], T, invT, nbox, odd, scratch)
+    want = dev.BitGrid(shape)
+    dev.bin_atoms(pos_d[1:].contiguous(), T, invT, nbox, want)
+    assert torch.equal(odd.words, want.words)
+
+
 @pytest.mark.parametrize("name", sorted(binning_cases()))
 def test_binning_matches_golden(dev, name):
     c = binning_cases()[name]

@@ -3,7 +3,7 @@
     python tools/frame_experiments.py [n=1024]
 
 * frames in flight 1..5
-* the same loop with the binning (memset + RED kernel) removed -- the bit grid of the previous frame is reused --
+* the same loop with the binning (clear + bucket + RED kernels) removed -- the bit grid of the previous frame is reused --
   which bounds what a better binning could buy inside the overlapped loop
 * the same loop without the dense write, which shows the cost of everything else when nothing competes with it
 """
@@ -56,13 +56,12 @@ def main():
     pipes = [FramePipeline(dims, 0.5, closing=True) for _ in range(3)]
     base = timed(pipes, pos)
     # no binning: keep bits_a of the last frame (graphs are re-captured without the memset and the RED kernel)
-    real_bin = dev.bin_atoms
+    real_bin = dev.bin_grid
     for p in pipes:
         p._graphs.clear()
-        p.bits_a.words.zero_ = lambda: None
-    dev.bin_atoms = lambda *a, **k: (None, None)
+    dev.bin_grid = lambda *a, **k: (None, None)
     no_bin = timed(pipes, pos)
-    dev.bin_atoms = real_bin
+    dev.bin_grid = real_bin
     print(f"3 in flight: {base:7.3f} ms/frame; without binning {no_bin:7.3f} ms/frame ({base - no_bin:+.3f})")
     del pipes
     torch.cuda.empty_cache()
