@@ -125,6 +125,7 @@ struct BinParams {
     long long nbox[9];
     int nbox32[9];       // the same matrix when every entry fits (fits32), for the all-32-bit fast path
     int fits32;
+    float Tf[9], Taf[9]; // T and |T| rounded to float32: the certified single-precision floor of bin_floor_f32
 };
 
 // Python floor division a // b for b > 0.  Atoms are almost always inside the box or one image away, so
@@ -201,6 +202,41 @@ __device__ __forceinline__ bool bin_one_atom(float x, float y, float z, const Bi
     return v[0] >= 0 && v[0] < P.nbox[0] && v[1] >= 0 && v[1] < P.nbox[4] && v[2] >= 0 && v[2] < P.nbox[8];
 }
 
+// Certified single-precision floor.  The reference floors the float64 chain above; almost every bead lies nowhere near
+// a voxel face, and for those the same floor follows from float32 arithmetic: with a = |p0 T0j| + |p1 T1j| + |p2 T2j|
+// the float32 chain differs from the exact value by less than 4 * 2^-24 * a (one rounding of T, one per product / sum),
+// and the float64 chain by ~1e-13, so a float32 result whose distance to the nearest integer exceeds 1e-6 * a (4x the
+// bound) has the reference's floor.  Anything closer -- beads ON a face, as coordinates rounded to 0.01 A often are,
+// huge coordinates, NaNs -- returns false and takes the float64 path.  ~20 instructions instead of ~190 per bead.
+__device__ __forceinline__ bool bin_floor_f32(float x, float y, float z, const BinParams &P, int (&u)[3]) {
+    const float ax = fabsf(x), ay = fabsf(y), az = fabsf(z);
+    bool sure = true;
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+        const float f = fmaf(z, P.Tf[6 + j], fmaf(y, P.Tf[3 + j], x * P.Tf[j]));
+        const float a = fmaf(az, P.Taf[6 + j], fmaf(ay, P.Taf[3 + j], ax * P.Taf[j]));
+        const float fl = floorf(f), frac = f - fl, eps = fmaf(a, 1e-6f, 1e-30f);
+        sure = sure && frac >= eps && frac <= 1.0f - eps && a < 1e5f;
+        u[j] = (int)fl;
+    }
+    return sure;
+}
+
+// triclinic-aware wrap of floored voxel coordinates (dims 2, 1, 0; Python floor division), 32-bit
+__device__ __forceinline__ bool bin_wrap32(const BinParams &P, int (&w3)[3]) {
+#pragma unroll
+    for (int dim = 2; dim >= 0; --dim) {
+        const int nn = P.nbox32[4 * dim], a = w3[dim];
+        int sh;
+        if (a >= 0) sh = a < nn ? 0 : (a < 2 * nn ? 1 : a / nn);
+        else sh = a >= -nn ? -1 : -((-a + nn - 1) / nn);
+#pragma unroll
+        for (int j = 0; j < 3; ++j) w3[j] -= sh * P.nbox32[3 * dim + j];
+    }
+    return (unsigned)w3[0] < (unsigned)P.nbox32[0] && (unsigned)w3[1] < (unsigned)P.nbox32[4] &&
+           (unsigned)w3[2] < (unsigned)P.nbox32[8];
+}
+
 // Four consecutive atoms per thread.  Positions are AoS (x,y,z per atom = 12 B), so four atoms are exactly three
 // 16-byte words: each thread fetches them with three streaming float4 loads (the three loads of a warp cover one
 // contiguous 1536-byte span, every sector of it used), runs the four independent FMA chains -- that instruction-level
@@ -267,6 +303,19 @@ k_bin_atoms1(const float *pos, long long first, long long n, BinParams P, uint32
     }
 }
 
+static void bin_params(BinParams &P, const double *T_host, const double *invT_host, const long long *nbox_host) {
+    memcpy(P.T, T_host, sizeof(P.T));
+    memcpy(P.invT, invT_host, sizeof(P.invT));
+    memcpy(P.nbox, nbox_host, sizeof(P.nbox));
+    P.fits32 = 1;
+    for (int k = 0; k < 9; ++k) {
+        if (nbox_host[k] <= -(1ll << 28) || nbox_host[k] >= (1ll << 28)) P.fits32 = 0;
+        P.nbox32[k] = (int)nbox_host[k];
+        P.Tf[k] = (float)T_host[k];
+        P.Taf[k] = fabsf(P.Tf[k]);
+    }
+}
+
 extern "C" int mdvc_bin_atoms(const float *pos, long long n, const double *T_host, const double *invT_host,
                               const long long *nbox_host, uint32_t *occ_bits, int pitch,
                               int32_t *vox_out, float *pos_out, void *stream) {
@@ -275,14 +324,7 @@ extern "C" int mdvc_bin_atoms(const float *pos, long long n, const double *T_hos
     if (occ_bits && pitch < mdvc_words((int)nbox_host[8])) return MDVC_ERR_BADARG;
     if (n == 0) return MDVC_OK;
     BinParams P;
-    memcpy(P.T, T_host, sizeof(P.T));
-    memcpy(P.invT, invT_host, sizeof(P.invT));
-    memcpy(P.nbox, nbox_host, sizeof(P.nbox));
-    P.fits32 = 1;
-    for (int k = 0; k < 9; ++k) {
-        if (nbox_host[k] <= -(1ll << 28) || nbox_host[k] >= (1ll << 28)) P.fits32 = 0;
-        P.nbox32[k] = (int)nbox_host[k];
-    }
+    bin_params(P, T_host, invT_host, nbox_host);
     cudaStream_t st = (cudaStream_t)stream;
     const uintptr_t ptrs = (uintptr_t)pos | (uintptr_t)vox_out | (uintptr_t)pos_out;
     long long done = 0;
@@ -321,15 +363,22 @@ struct BinBuckets {
     uint32_t row_bits;       // pitch * 32: key = row * row_bits + z  (word = key >> 5, bit = key & 31)
 };
 
+// FAST (occupancy only, 32-bit box): the certified float32 floor decides almost every bead; the few it cannot decide
+// (on or next to a voxel face) are queued in shared memory and redone in float64 by the first threads of the CTA --
+// densely, not as a divergent branch that a third of all warps would have to sit through -- and go to the spill list.
+template <bool FAST>
 __global__ void __launch_bounds__(256, 3)
 k_bin_bucket(const float *__restrict__ pos, long long n, BinParams P, BinBuckets B, int32_t *__restrict__ vox_out, float *pos_out) {
     __shared__ uint32_t s_cnt[BIN_CHUNKS], s_base[BIN_CHUNKS];
+    __shared__ uint32_t s_nslow;
+    __shared__ unsigned short s_slow[FAST ? BIN_TILE_ATOMS : 1];
     const long long n4 = n >> 2;                                  // groups of four beads (three float4)
     const long long tile_groups = BIN_TILE_ATOMS / 4;
     const long long n_tiles = (n4 + tile_groups - 1) / tile_groups;
     const uint32_t Y = (uint32_t)P.nbox[4];
     for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         if (threadIdx.x < BIN_CHUNKS) s_cnt[threadIdx.x] = 0;
+        if (threadIdx.x == 0) s_nslow = 0;
         __syncthreads();
         uint32_t key[8], slot[8];
         int bucket[8];
@@ -340,29 +389,45 @@ k_bin_bucket(const float *__restrict__ pos, long long n, BinParams P, BinBuckets
                 const float4 *src = reinterpret_cast<const float4 *>(pos) + 3 * g;
                 const float4 q0 = __ldcs(src), q1 = __ldcs(src + 1), q2 = __ldcs(src + 2);
                 const float f[12] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w};
-                int32_t v[12];
-                float w[12];
+                if (FAST) {
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    int vk[3];
-                    float wk[3];
-                    const bool inside = bin_one_atom(f[3 * k], f[3 * k + 1], f[3 * k + 2], P, pos_out != nullptr, vk, wk);
+                    for (int k = 0; k < 4; ++k) {
+                        int vk[3];
+                        bucket[4 * half + k] = -1;
+                        if (bin_floor_f32(f[3 * k], f[3 * k + 1], f[3 * k + 2], P, vk)) {
+                            if (bin_wrap32(P, vk)) {
+                                bucket[4 * half + k] = vk[0] >> B.px_shift;
+                                key[4 * half + k] = ((uint32_t)vk[0] * Y + (uint32_t)vk[1]) * B.row_bits + (uint32_t)vk[2];
+                            }
+                        } else {
+                            s_slow[atomicAdd(&s_nslow, 1u)] = (unsigned short)((half * 256 + threadIdx.x) * 4 + k);
+                        }
+                    }
+                } else {
+                    int32_t v[12];
+                    float w[12];
 #pragma unroll
-                    for (int j = 0; j < 3; ++j) { v[3 * k + j] = vk[j]; w[3 * k + j] = wk[j]; }
-                    bucket[4 * half + k] = inside ? (vk[0] >> B.px_shift) : -1;
-                    key[4 * half + k] = ((uint32_t)vk[0] * Y + (uint32_t)vk[1]) * B.row_bits + (uint32_t)vk[2];
-                }
-                if (vox_out) {
-                    int4 *dst = reinterpret_cast<int4 *>(vox_out) + 3 * g;
-                    dst[0] = make_int4(v[0], v[1], v[2], v[3]);
-                    dst[1] = make_int4(v[4], v[5], v[6], v[7]);
-                    dst[2] = make_int4(v[8], v[9], v[10], v[11]);
-                }
-                if (pos_out) {
-                    float4 *dst = reinterpret_cast<float4 *>(pos_out) + 3 * g;
-                    dst[0] = make_float4(w[0], w[1], w[2], w[3]);
-                    dst[1] = make_float4(w[4], w[5], w[6], w[7]);
-                    dst[2] = make_float4(w[8], w[9], w[10], w[11]);
+                    for (int k = 0; k < 4; ++k) {
+                        int vk[3];
+                        float wk[3];
+                        const bool inside = bin_one_atom(f[3 * k], f[3 * k + 1], f[3 * k + 2], P, pos_out != nullptr, vk, wk);
+#pragma unroll
+                        for (int j = 0; j < 3; ++j) { v[3 * k + j] = vk[j]; w[3 * k + j] = wk[j]; }
+                        bucket[4 * half + k] = inside ? (vk[0] >> B.px_shift) : -1;
+                        key[4 * half + k] = ((uint32_t)vk[0] * Y + (uint32_t)vk[1]) * B.row_bits + (uint32_t)vk[2];
+                    }
+                    if (vox_out) {
+                        int4 *dst = reinterpret_cast<int4 *>(vox_out) + 3 * g;
+                        dst[0] = make_int4(v[0], v[1], v[2], v[3]);
+                        dst[1] = make_int4(v[4], v[5], v[6], v[7]);
+                        dst[2] = make_int4(v[8], v[9], v[10], v[11]);
+                    }
+                    if (pos_out) {
+                        float4 *dst = reinterpret_cast<float4 *>(pos_out) + 3 * g;
+                        dst[0] = make_float4(w[0], w[1], w[2], w[3]);
+                        dst[1] = make_float4(w[4], w[5], w[6], w[7]);
+                        dst[2] = make_float4(w[8], w[9], w[10], w[11]);
+                    }
                 }
             } else {
 #pragma unroll
@@ -374,6 +439,17 @@ k_bin_bucket(const float *__restrict__ pos, long long n, BinParams P, BinBuckets
             if (bucket[k] >= 0) slot[k] = atomicAdd(&s_cnt[bucket[k]], 1u);
         __syncthreads();
         if (threadIdx.x < BIN_CHUNKS) s_base[threadIdx.x] = s_cnt[threadIdx.x] ? atomicAdd(&B.cursor[threadIdx.x], s_cnt[threadIdx.x]) : 0u;
+        if (FAST) {
+            // the undecided beads again, in float64, one per thread; they join the spill list
+            for (uint32_t i = threadIdx.x; i < s_nslow; i += blockDim.x) {
+                const long long atom = tile * BIN_TILE_ATOMS + s_slow[i];
+                int vk[3];
+                float wk[3];
+                if (bin_one_atom(pos[3 * atom], pos[3 * atom + 1], pos[3 * atom + 2], P, false, vk, wk))
+                    B.keys[(size_t)BIN_CHUNKS * B.cap + atomicAdd(&B.cursor[BIN_CHUNKS], 1u)] =
+                        ((uint32_t)vk[0] * Y + (uint32_t)vk[1]) * B.row_bits + (uint32_t)vk[2];
+            }
+        }
         __syncthreads();
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
@@ -382,7 +458,7 @@ k_bin_bucket(const float *__restrict__ pos, long long n, BinParams P, BinBuckets
             if (at < B.cap) B.keys[(size_t)bucket[k] * B.cap + at] = key[k];
             else B.keys[(size_t)BIN_CHUNKS * B.cap + atomicAdd(&B.cursor[BIN_CHUNKS], 1u)] = key[k];   // bucket full: spill list
         }
-        __syncthreads();                                          // s_base is reused by the next tile
+        __syncthreads();                                          // s_base / s_slow are reused by the next tile
     }
 }
 
@@ -421,14 +497,7 @@ extern "C" int mdvc_bin_grid(const float *pos, long long n, const double *T_host
         return mdvc_bin_atoms(pos, n, T_host, invT_host, nbox_host, occ_bits, pitch, vox_out, pos_out, stream);
     }
     BinParams P;
-    memcpy(P.T, T_host, sizeof(P.T));
-    memcpy(P.invT, invT_host, sizeof(P.invT));
-    memcpy(P.nbox, nbox_host, sizeof(P.nbox));
-    P.fits32 = 1;
-    for (int k = 0; k < 9; ++k) {
-        if (nbox_host[k] <= -(1ll << 28) || nbox_host[k] >= (1ll << 28)) P.fits32 = 0;
-        P.nbox32[k] = (int)nbox_host[k];
-    }
+    bin_params(P, T_host, invT_host, nbox_host);
     BinBuckets B;
     B.cursor = reinterpret_cast<uint32_t *>(scratch);
     B.keys = B.cursor + 64;
@@ -439,7 +508,10 @@ extern "C" int mdvc_bin_grid(const float *pos, long long n, const double *T_host
     const int n_chunks = (int)((X + (1ll << B.px_shift) - 1) >> B.px_shift);
     MDVC_CUDA_CHECK(cudaMemsetAsync(B.cursor, 0, 64 * sizeof(uint32_t), st));
     const long long n_tiles = ((n >> 2) + BIN_TILE_ATOMS / 4 - 1) / (BIN_TILE_ATOMS / 4);
-    k_bin_bucket<<<mdvc_grid(n_tiles * 256, 256, 3), 256, 0, st>>>(pos, n, P, B, vox_out, pos_out);
+    if (P.fits32 && !vox_out && !pos_out)
+        k_bin_bucket<true><<<mdvc_grid(n_tiles * 256, 256, 3), 256, 0, st>>>(pos, n, P, B, vox_out, pos_out);
+    else
+        k_bin_bucket<false><<<mdvc_grid(n_tiles * 256, 256, 3), 256, 0, st>>>(pos, n, P, B, vox_out, pos_out);
     MDVC_LAUNCH_CHECK();
     for (int c = 0; c < n_chunks; ++c) {
         const long long x0 = (long long)c << B.px_shift, x1 = (x0 + (1ll << B.px_shift)) < X ? x0 + (1ll << B.px_shift) : X;

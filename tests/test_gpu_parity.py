@@ -143,7 +143,7 @@ def test_morph_rejects_unknown_op(dev):
 
 
 # ------------------------------------------------------------------------------------------ A1
-@pytest.mark.parametrize("case", ["uniform", "one_plane_range", "two_blobs", "outside_and_far"])
+@pytest.mark.parametrize("case", ["uniform", "one_plane_range", "two_blobs", "outside_and_far", "on_and_next_to_faces"])
 @pytest.mark.parametrize("n", [8192, 50001, 262147])
 def test_bin_grid_bucketed_path_equals_plain_binning(dev, case, n):
     """mdvc_bin_grid (beads bucketed by x-plane range, grid cleared and filled range by range) against clear +
@@ -161,9 +161,22 @@ def test_bin_grid_bucketed_path_equals_plain_binning(dev, case, n):
         pos = rng.random((n, 3)) * box * np.array([0.04, 1, 1]) + np.array([0.5 * box[0], 0, 0])
     elif case == "two_blobs":
         pos = np.concatenate([rng.normal(0.2, 0.02, (n // 2, 3)), rng.normal(0.8, 0.05, (n - n // 2, 3))]) * box
+    elif case == "on_and_next_to_faces":
+        # voxel faces (multiples of the 5 A voxel edge, also outside the box) and their float32 neighbours: the
+        # certified single-precision floor must hand every one of them to the float64 path
+        faces = (rng.integers(-90, 180, (n, 3)) * 5.0).astype(np.float32)
+        step = rng.integers(-3, 4, (n, 3))
+        pos = faces.copy()
+        for k in range(1, 4):
+            pos = np.where(step >= k, np.nextafter(pos, np.float32(np.inf)), pos)
+            pos = np.where(step <= -k, np.nextafter(pos, np.float32(-np.inf)), pos)
+        pos[::7] = (rng.random((len(pos[::7]), 3)) * box).astype(np.float32)
+        pos[5] = [1e7, -3e6, 2.5]
     else:
         pos = (rng.random((n, 3)) * 7 - 3) * box
-    pos = np.round(pos, 2).astype(np.float32)
+    if case != "on_and_next_to_faces":
+        pos = np.round(pos, 2)
+    pos = pos.astype(np.float32)
     pos_d = torch.from_numpy(pos).cuda()
     plain = dev.BitGrid(shape)
     v0, p0 = dev.bin_atoms(pos_d, T, invT, nbox, plain, want_voxels=True, want_positions=True)
