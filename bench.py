@@ -426,7 +426,10 @@ def run_ours(args):
            "timed_regions": f"{reps} regions of {args.steps} frames each; value = median region (min/max in `spread`)",
            "parallelism": f"frames sharded over {world} GPU(s), no collective on the data path"}
     h2d_bytes = int(n_atoms * 12)
-    e2e_bound = h2d["aggregate_gbs"] * 1e9 / h2d_bytes if h2d.get("aggregate_gbs") else None
+    # every rank moves the same number of frames and the region ends with the slowest rank: the copy bound of this loop is
+    # world x the slowest rank's rate; the aggregate rate would need frames to migrate to the ranks with faster links
+    e2e_bound = world * h2d["per_rank_min_gbs"] * 1e9 / h2d_bytes if h2d.get("per_rank_min_gbs") else None
+    e2e_aggregate_bound = h2d["aggregate_gbs"] * 1e9 / h2d_bytes if h2d.get("aggregate_gbs") else None
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": med / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -454,6 +457,10 @@ def run_ours(args):
                                       "label -> component table"},
                 "h2d_ceiling_gbs": h2d, "h2d_bound_frames_per_s": e2e_bound,
                 "frac_of_h2d_bound": (e2e_value / e2e_bound) if e2e_bound else None,
+                "h2d_bound_note": "bound = n_gpus x slowest rank's concurrent pinned-H2D rate / bytes per frame (static sharding: "
+                                  "the region ends with the slowest rank); `h2d_aggregate_bound_frames_per_s` is what the sum of "
+                                  "all ranks' rates would allow",
+                "h2d_aggregate_bound_frames_per_s": e2e_aggregate_bound,
                 "placement": placement},
         "components_only": {"value": world * args.steps / (ms_conly / 1e3), "unit": UNIT, "ms_per_step": ms_conly / args.steps,
                             "note": "informational, not the headline: labels grid not materialised (4 B/voxel written instead "

@@ -470,33 +470,59 @@ k_rs_hist(const unsigned long long *__restrict__ keys, long long n, int shift, u
     hist[(size_t)threadIdx.x * tiles + blockIdx.x] = sh[threadIdx.x];   // digit-major
 }
 
+// Stable scatter of one 8-bit digit.  Items keep their order li = k * RS_THREADS + thread inside the tile, i.e. the 64
+// "rows" (k, warp) in ascending order and the lanes of a row in ascending order.  The rank of an item among the equal
+// digits of its tile = (items with that digit in earlier rows) + (earlier lanes of its row with that digit): the second
+// term comes from one __match_any_sync per item, the first from a per-row digit count in shared memory that 256
+// threads (one per digit) turn into a prefix over the 64 rows.  The first version let every digit's thread walk the
+// whole tile (2048 serial shared-memory reads per thread): 1.3 ms per pass for 20 M atoms, 5 % of the DRAM roofline.
 __global__ void __launch_bounds__(RS_THREADS)
 k_rs_scatter(const unsigned long long *__restrict__ keys_in, const uint32_t *__restrict__ val_in, long long n, int shift,
              uint32_t tiles, const uint32_t *__restrict__ hist_scanned, unsigned long long *__restrict__ keys_out,
              uint32_t *__restrict__ val_out) {
+    constexpr int ROWS = RS_ITEMS * (RS_THREADS / 32);
     __shared__ uint32_t digit_base[256];
-    __shared__ unsigned short sd[RS_TILE];
-    long long base = (long long)blockIdx.x * RS_TILE;
-    digit_base[threadIdx.x] = hist_scanned[(size_t)threadIdx.x * tiles + blockIdx.x];
-    for (int k = 0; k < RS_ITEMS; ++k) {
-        int li = k * RS_THREADS + threadIdx.x;
-        long long i = base + li;
-        sd[li] = i < n ? (unsigned short)((keys_in[i] >> shift) & 255u) : (unsigned short)256;
-    }
-    __syncthreads();
-    // rank of item li among equal digits inside the tile = number of earlier items with that digit.
-    // thread d (one per digit) walks the tile once and writes the destinations of its digit's items.
-    __shared__ uint32_t dest[RS_TILE];
+    __shared__ unsigned short cnt[ROWS][256];                    // items of digit d in row r, then: in the rows before r
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const long long base = (long long)blockIdx.x * RS_TILE;
+    digit_base[tid] = hist_scanned[(size_t)tid * tiles + blockIdx.x];
     {
-        uint32_t d = threadIdx.x, run = digit_base[d];
-        for (int li = 0; li < RS_TILE; ++li)
-            if (sd[li] == d) dest[li] = run++;
+        uint32_t *z = reinterpret_cast<uint32_t *>(&cnt[0][0]);
+        for (int q = tid; q < ROWS * 256 / 2; q += RS_THREADS) z[q] = 0u;
     }
     __syncthreads();
+    unsigned long long key[RS_ITEMS];
+    uint32_t digit[RS_ITEMS], rank[RS_ITEMS];
+#pragma unroll
     for (int k = 0; k < RS_ITEMS; ++k) {
-        int li = k * RS_THREADS + threadIdx.x;
-        long long i = base + li;
-        if (i < n) { uint32_t o = dest[li]; keys_out[o] = keys_in[i]; val_out[o] = val_in[i]; }
+        const long long i = base + (long long)k * RS_THREADS + tid;
+        const bool valid = i < n;
+        key[k] = valid ? keys_in[i] : 0ull;
+        const uint32_t d = valid ? (uint32_t)((key[k] >> shift) & 255u) : 256u;   // the invalid lanes only match each other
+        const unsigned peers = __match_any_sync(MDVC_FULL, d);
+        rank[k] = __popc(peers & ((1u << lane) - 1u));
+        if (valid && rank[k] == 0) cnt[k * (RS_THREADS / 32) + warp][d] = (unsigned short)__popc(peers);
+        digit[k] = d;
+    }
+    __syncthreads();
+    {
+        uint32_t run = 0;
+#pragma unroll 8
+        for (int r = 0; r < ROWS; ++r) {
+            const uint32_t c = cnt[r][tid];
+            cnt[r][tid] = (unsigned short)run;
+            run += c;
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < RS_ITEMS; ++k) {
+        const long long i = base + (long long)k * RS_THREADS + tid;
+        if (i < n) {
+            const uint32_t o = digit_base[digit[k]] + cnt[k * (RS_THREADS / 32) + warp][digit[k]] + rank[k];
+            keys_out[o] = key[k];
+            val_out[o] = val_in[i];
+        }
     }
 }
 

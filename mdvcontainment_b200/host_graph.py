@@ -79,6 +79,7 @@ class LabelGraph:
         self._canonical = bool(self._sorted and n and (self._n_neg == 0 or (v[0] == -self._n_neg and v[self._n_neg - 1] == -1))
                                and (self._n_neg == n or (v[self._n_neg] == 1 and v[-1] == n - self._n_neg)))
         self._half = None
+        self._rows = None
 
     @property
     def nodes(self):
@@ -102,6 +103,11 @@ class LabelGraph:
     def rows(self):
         """(contact rows, bridge rows) with the rows touching label 0 removed (graph_logic.py:38-39, 45-46), as node
         indices: (cu, cv), (bu, bv, shift[.,3])."""
+        if self._rows is None:
+            self._rows = self._compute_rows()
+        return self._rows
+
+    def _compute_rows(self):
         c = self.contacts
         c = c[(c != 0).all(axis=1)] if len(c) else c.reshape(0, 2)
         cu, cv = self.index_of(c[:, 0]), self.index_of(c[:, 1])

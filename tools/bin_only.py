@@ -29,17 +29,32 @@ def main():
     _, nbox, T, invT = voxel_transform(dims, 0.5)
     bits0 = dev.BitGrid((n, n, n))
     p = torch.from_numpy(pos).cuda()
-    for _ in range(3):
+    thrash = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")       # evicts the L2 between repetitions
+    scratch = dev.bin_scratch(len(pos), "cuda")
+
+    def plain():
+        bits0.words.zero_()
         dev.bin_atoms(p, T, invT, nbox, bits0)
-    torch.cuda.synchronize()
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
-    ev[0].record()
-    for _ in range(reps):
-        dev.bin_atoms(p, T, invT, nbox, bits0)
-    ev[1].record()
-    torch.cuda.synchronize()
-    t = ev[0].elapsed_time(ev[1]) / reps
-    print(f"bin {len(pos)} atoms into {n}^3: {t * 1e3:8.1f} us   {len(pos) * 12 / t / 1e6:8.1f} GB/s (12 B/atom)")
+
+    def bucketed():
+        dev.bin_grid(p, T, invT, nbox, bits0, scratch)
+
+    for name, fn in (("clear + mdvc_bin_atoms", plain), ("mdvc_bin_grid", bucketed)):
+        for _ in range(3):
+            fn()
+        ts = []
+        for _ in range(reps):
+            thrash.fill_(1)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn()
+            e1.record()
+            torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        ts.sort()
+        t = ts[len(ts) // 2]
+        print(f"{name:24s} {len(pos)} atoms into {n}^3: {t * 1e3:8.1f} us median (L2 evicted before each), "
+              f"{len(pos) * 12 / t / 1e6:8.1f} GB/s (12 B/atom)")
 
 
 if __name__ == "__main__":
