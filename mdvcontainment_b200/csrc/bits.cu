@@ -367,7 +367,7 @@ struct BinBuckets {
 // (on or next to a voxel face) are queued in shared memory and redone in float64 by the first threads of the CTA --
 // densely, not as a divergent branch that a third of all warps would have to sit through -- and go to the spill list.
 template <bool FAST>
-__global__ void __launch_bounds__(256, 3)
+__global__ void __launch_bounds__(256, FAST ? 5 : 3)
 k_bin_bucket(const float *__restrict__ pos, long long n, BinParams P, BinBuckets B, int32_t *__restrict__ vox_out, float *pos_out) {
     __shared__ uint32_t s_cnt[BIN_CHUNKS], s_base[BIN_CHUNKS];
     __shared__ uint32_t s_nslow;
@@ -509,7 +509,7 @@ extern "C" int mdvc_bin_grid(const float *pos, long long n, const double *T_host
     MDVC_CUDA_CHECK(cudaMemsetAsync(B.cursor, 0, 64 * sizeof(uint32_t), st));
     const long long n_tiles = ((n >> 2) + BIN_TILE_ATOMS / 4 - 1) / (BIN_TILE_ATOMS / 4);
     if (P.fits32 && !vox_out && !pos_out)
-        k_bin_bucket<true><<<mdvc_grid(n_tiles * 256, 256, 3), 256, 0, st>>>(pos, n, P, B, vox_out, pos_out);
+        k_bin_bucket<true><<<mdvc_grid(n_tiles * 256, 256, 5), 256, 0, st>>>(pos, n, P, B, vox_out, pos_out);
     else
         k_bin_bucket<false><<<mdvc_grid(n_tiles * 256, 256, 3), 256, 0, st>>>(pos, n, P, B, vox_out, pos_out);
     MDVC_LAUNCH_CHECK();
