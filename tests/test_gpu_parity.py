@@ -492,3 +492,47 @@ def test_atom_components_and_csr(dev):
             qq = np.asarray(qq).reshape(-1, 3)
             inside = (qq >= 0).all(1) & (qq < np.array(shape)).all(1)
             assert np.array_equal(csr.gather_voxels(qq, torch.from_numpy(ix).cuda()), vo.voxels2atoms(qq[inside], mapping))
+
+
+# ------------------------------------------------------------------------------------------ limits and guards
+def test_rows_longer_than_the_packed_z_field_are_rejected(dev):
+    """Run z-starts are packed into 24 bits in the link / pair kernels: Z >= 2^24 must be refused up front, not
+    labelled wrongly (grids that long would pass the 2^31-voxel check, e.g. 4 x 4 x 2^25)."""
+    import ctypes
+    from mdvcontainment_b200 import _lib
+    with pytest.raises(ValueError, match="2\\^24"):
+        dev.BitGrid((2, 2, 1 << 24))
+    lib = _lib.load()
+    Z = 1 << 24
+    pitch = lib.mdvc_row_pitch_words(Z)
+    words = torch.zeros((1, 1, pitch), dtype=torch.int32, device="cuda")
+    caps = _lib.FrameCaps(4096, 4096, 64, 64)
+    ws = torch.empty(lib.mdvc_frame_workspace_bytes(1, 1, Z, ctypes.byref(caps)), dtype=torch.uint8, device="cuda")
+    rc = lib.mdvc_frame_label(words.data_ptr(), 1, 1, Z, pitch, ws.data_ptr(), ws.numel(), ctypes.byref(caps), None)
+    assert rc == _lib.ERR_BADARG
+    ok = lib.mdvc_frame_label(words.data_ptr(), 1, 1, Z - 1, pitch, ws.data_ptr(), ws.numel(), ctypes.byref(caps), None)
+    assert ok == 0
+
+
+def test_pipeline_guards():
+    """FramePipeline refuses what it cannot do before any device work: non-periodic frames, positions of the wrong
+    dtype / layout; FrameOutput.own() detaches the leased grids from the pipeline's buffers."""
+    from mdvcontainment_b200 import synth
+    from mdvcontainment_b200.pipeline import FramePipeline
+    pos, dims = synth.vesicle_scene(box_nm=16.0, seed=2)
+    with pytest.raises(NotImplementedError):
+        FramePipeline(dims, 0.5, periodic=False)
+    pipe = FramePipeline(dims, 0.5, closing=True)
+    p = torch.from_numpy(pos).cuda()
+    with pytest.raises(ValueError):
+        pipe.run(p.double())
+    with pytest.raises(ValueError):
+        pipe.run(p.t().contiguous().t())
+    with pytest.raises(ValueError):
+        pipe.run(torch.from_numpy(pos))
+    first = pipe.run(p).own()
+    keep = first.components_dev.clone()
+    other = pipe.run(torch.from_numpy(pos[: len(pos) // 3]).cuda())     # overwrites the pipeline's buffers
+    assert torch.equal(first.components_dev, keep)
+    assert first.components_dev.data_ptr() != other.components_dev.data_ptr()
+    assert not torch.equal(other.components_dev, keep)
