@@ -18,6 +18,7 @@ against the unmodified reference where it is available.
 from __future__ import annotations
 
 import ctypes
+import itertools
 
 import networkx as nx
 import numpy as np
@@ -349,7 +350,9 @@ class PeriodicSolution:
             keep = cs != cd
             cs, cd, lab = cs[keep], cd[keep], lg.node_vals[src[keep]]
             # add sequence: components in order, their labels ascending, each label's successors in insertion order
-            order = np.lexsort((np.flatnonzero(keep), lab, cs))
+            # (one stable sort on (component, label): the half-edges already are in insertion order)
+            lab_rank = lab - lab.min() if len(lab) else lab
+            order = np.argsort(cs.astype(np.int64) * (int(lab_rank.max()) + 1 if len(lab) else 1) + lab_rank, kind="stable")
             cs, cd = cs[order].astype(np.int64), cd[order].astype(np.int64)
             first = _first_occurrence(cs * K + cd)
             cs, cd = cs[first], cd[first]
@@ -420,11 +423,14 @@ class PeriodicSolution:
         adj = {ids[k]: flat[off[k]:off[k + 1]] for k in busy.tolist()}
         get, pop = adj.get, stack.pop
         parents, kids = [], []
+        # every component is popped at most once, so the reference's guard (assert before the 100 001st pop) can only
+        # fire when there are more components than that: checked per pop only then
+        guarded = max_iterations is not None and K > max_iterations
         counter = 0
         while stack:
-            if max_iterations is not None:
+            if guarded:
                 assert counter < max_iterations, _ORIENT_MESSAGE
-            counter += 1
+                counter += 1
             q = pop()
             nbs = get(q)
             if nbs is None:
@@ -438,7 +444,7 @@ class PeriodicSolution:
         if not parents:
             return CompactDAG(nodes, [], [])
         eu = np.repeat(np.asarray(parents, dtype=np.int64), [len(k) for k in kids])
-        ev = np.fromiter((c for k in kids for c in k), dtype=np.int64, count=len(eu))
+        ev = np.fromiter(itertools.chain.from_iterable(kids), dtype=np.int64, count=len(eu))
         return CompactDAG(nodes, eu, ev)
 
     def _orient_by_levels(self, offsets, nbrs):
