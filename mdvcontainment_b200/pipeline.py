@@ -104,7 +104,7 @@ class FramePipeline:
     ATOM_QUANTUM = 1 << 16              # host-fed frames are padded to a multiple of this many beads
 
     def __init__(self, dimensions, resolution, closing=True, morph="", periodic=True, max_atoms=0,
-                 write_labels=True, device="cuda", use_graph=True):
+                 write_labels=True, device="cuda", use_graph=True, streams=None):
         if not periodic:
             raise NotImplementedError("FramePipeline handles periodic frames; slab frames go through "
                                       "VoxelContainment(slab=True)")
@@ -131,8 +131,13 @@ class FramePipeline:
         # stage 1 (bin .. pairs: latency/issue-bound, small) on a high-priority stream, the dense write (HBM-bound,
         # tens of thousands of short CTAs) on a low-priority one: with several pipelines in flight the block
         # scheduler then slots the next frame's stage-1 CTAs in between the current frame's write CTAs
-        self.stream = torch.cuda.Stream(device=self.device, priority=-1)
-        self.stream_x = torch.cuda.Stream(device=self.device, priority=0)
+        # ``streams=(stage1_stream, write_stream)`` lets several pipelines share streams (both may be the same one: the
+        # device then runs the frames' kernels strictly one after the other)
+        if streams is not None:
+            self.stream, self.stream_x = streams
+        else:
+            self.stream = torch.cuda.Stream(device=self.device, priority=-1)
+            self.stream_x = torch.cuda.Stream(device=self.device, priority=0)
         self.ev_stage1 = torch.cuda.Event()
         self.expand_events = []                                   # (start, end) of every dense write
         self._bits = None

@@ -53,8 +53,25 @@ def main():
         del pipes
         torch.cuda.empty_cache()
 
+    one = torch.cuda.Stream()
+    for depth in (2, 3, 4):
+        pipes = [FramePipeline(dims, 0.5, closing=True, streams=(one, one)) for _ in range(depth)]
+        t = timed(pipes, pos)
+        ex = sum(p.expand_elapsed_ms() for p in pipes) / depth
+        print(f"{depth} in flight on ONE shared stream: {t:7.3f} ms/frame (dense write inside the loop {ex:6.3f} ms)")
+        del pipes
+        torch.cuda.empty_cache()
+    two = (torch.cuda.Stream(priority=-1), torch.cuda.Stream(priority=0))
+    pipes = [FramePipeline(dims, 0.5, closing=True, streams=two) for _ in range(3)]
+    t = timed(pipes, pos)
+    ex = sum(p.expand_elapsed_ms() for p in pipes) / 3
+    print(f"3 in flight on TWO shared streams (stage 1 / dense write): {t:7.3f} ms/frame (dense write {ex:6.3f} ms)")
+    del pipes
+    torch.cuda.empty_cache()
+
     pipes = [FramePipeline(dims, 0.5, closing=True) for _ in range(3)]
     base = timed(pipes, pos)
+    print(f"(own streams: dense write inside the loop {sum(p.expand_elapsed_ms() for p in pipes) / 3:6.3f} ms)")
     # no binning: keep bits_a of the last frame (graphs are re-captured without the memset and the RED kernel)
     real_bin = dev.bin_grid
     for p in pipes:
