@@ -284,6 +284,18 @@ int mdvc_host_shift_graph_ranks(long long n_nodes, const int32_t *edge_u_host, c
                                 const int32_t *edge_shift_host, long long n_edges, const uint8_t *skip_node_host,
                                 int32_t *root_out_host, int8_t *rank_out_host, int32_t *max_rank_out_host);
 
+/* create_component_contact_graph (graph_logic.py:164-198) for large label graphs, HOST functions.
+ * mdvc_host_component_neighbours: the sequence in which the reference meets neighbouring components -- components in
+ * order, their nodes in ascending index (= label) order, each node's successors in the insertion order of the
+ * half-edges (src, dst)[n_edges] -- every (component, neighbour) pair at its first occurrence only.  Outputs hold up to
+ * n_edges pairs.  mdvc_host_adjacency: adjacency lists in networkx's order (a neighbour appears where the first edge
+ * joining two nodes was added, from either side) from an edge sequence; offsets int64[n_comps + 1], neighbours int32[2 n]. */
+int mdvc_host_component_neighbours(long long n_nodes, const int32_t *comp_of_node_host, int32_t n_comps,
+                                   const int32_t *src_host, const int32_t *dst_host, long long n_edges,
+                                   int32_t *out_cs_host, int32_t *out_cd_host, long long *n_out_host);
+int mdvc_host_adjacency(int32_t n_comps, const int32_t *eu_host, const int32_t *ev_host, long long n,
+                        long long *offsets_out_host, int32_t *nbrs_out_host);
+
 #ifdef __cplusplus
 }
 #endif

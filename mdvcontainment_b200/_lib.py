@@ -88,6 +88,8 @@ SIGNATURES = {
     "mdvc_atom_gather_voxels": (_I, [_P, _LL, _I, _I, _I, _P, _P, _LL, _P, _P, _P, _U64, _P, _P]),
     "mdvc_atom_select": (_I, [_P, _P, _LL, _P, _P, _I, _I, _P, _P, _P, _P, _P]),
     "mdvc_host_shift_graph_ranks": (_I, [_LL, _P, _P, _P, _LL, _P, _P, _P, _P]),
+    "mdvc_host_component_neighbours": (_I, [_LL, _P, _I, _P, _P, _LL, _P, _P, _P]),
+    "mdvc_host_adjacency": (_I, [_I, _P, _P, _LL, _P, _P]),
 }
 
 _lib = None

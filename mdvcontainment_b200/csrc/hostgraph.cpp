@@ -159,3 +159,98 @@ extern "C" int mdvc_host_shift_graph_ranks(long long n_nodes, const int32_t *edg
     if (max_rank_out_host) *max_rank_out_host = best;
     return MDVC_OK;
 }
+
+// ------------------------------------------------------------------------------------------
+// component-level bookkeeping of create_component_contact_graph (graph_logic.py:164-198) for large label graphs
+// ------------------------------------------------------------------------------------------
+// The reference walks the components in order, each component's labels in ascending order, each label's successors in
+// the insertion order of the label graph's edges, and collects the neighbouring components.  This returns that
+// sequence with every (component, neighbour) pair kept at its first occurrence -- O(nodes + edges) with two counting
+// sorts and a stamp array, where NumPy needs a stable sort and a unique over all half-edges.  Nodes must be numbered by
+// ascending label value (node index order == label order inside a component).
+extern "C" int mdvc_host_component_neighbours(long long n_nodes, const int32_t *comp_of_node_host, int32_t n_comps,
+                                              const int32_t *src_host, const int32_t *dst_host, long long n_edges,
+                                              int32_t *out_cs_host, int32_t *out_cd_host, long long *n_out_host) {
+    if (n_nodes < 0 || n_edges < 0 || n_comps < 0 || !n_out_host || (n_nodes > 0 && !comp_of_node_host) ||
+        (n_edges > 0 && (!src_host || !dst_host || !out_cs_host || !out_cd_host)))
+        return MDVC_ERR_BADARG;
+    *n_out_host = 0;
+    for (long long i = 0; i < n_nodes; ++i)
+        if (comp_of_node_host[i] < 0 || comp_of_node_host[i] >= n_comps) return MDVC_ERR_BADARG;
+    // half-edges by source node, insertion order kept (stable counting sort)
+    std::vector<long long> estart((size_t)n_nodes + 1, 0);
+    for (long long e = 0; e < n_edges; ++e) {
+        if (src_host[e] < 0 || src_host[e] >= n_nodes || dst_host[e] < 0 || dst_host[e] >= n_nodes) return MDVC_ERR_BADARG;
+        ++estart[(size_t)src_host[e] + 1];
+    }
+    for (long long i = 0; i < n_nodes; ++i) estart[(size_t)i + 1] += estart[(size_t)i];
+    std::vector<int32_t> edst((size_t)n_edges);
+    {
+        std::vector<long long> fill(estart.begin(), estart.end() - 1);
+        for (long long e = 0; e < n_edges; ++e) edst[(size_t)fill[(size_t)src_host[e]]++] = dst_host[e];
+    }
+    // nodes by component, ascending node index inside a component
+    std::vector<long long> nstart((size_t)n_comps + 1, 0);
+    for (long long i = 0; i < n_nodes; ++i) ++nstart[(size_t)comp_of_node_host[i] + 1];
+    for (int32_t c = 0; c < n_comps; ++c) nstart[(size_t)c + 1] += nstart[(size_t)c];
+    std::vector<int32_t> nodes((size_t)n_nodes);
+    {
+        std::vector<long long> fill(nstart.begin(), nstart.end() - 1);
+        for (long long i = 0; i < n_nodes; ++i) nodes[(size_t)fill[(size_t)comp_of_node_host[i]]++] = (int32_t)i;
+    }
+    std::vector<int32_t> stamp((size_t)n_comps, -1);
+    long long n_out = 0;
+    for (int32_t c = 0; c < n_comps; ++c) {
+        for (long long k = nstart[(size_t)c]; k < nstart[(size_t)c + 1]; ++k) {
+            const int32_t node = nodes[(size_t)k];
+            for (long long e = estart[(size_t)node]; e < estart[(size_t)node + 1]; ++e) {
+                const int32_t other = comp_of_node_host[edst[(size_t)e]];
+                if (other == c || stamp[(size_t)other] == c) continue;
+                stamp[(size_t)other] = c;
+                out_cs_host[n_out] = c;
+                out_cd_host[n_out] = other;
+                ++n_out;
+            }
+        }
+    }
+    *n_out_host = n_out;
+    return MDVC_OK;
+}
+
+// Adjacency lists of an undirected graph in networkx's order -- a neighbour appears where the first edge joining the two
+// nodes was added, from either side (nx.Graph.add_edge) -- from the edge sequence (u, v)[n].  offsets int64[n_comps + 1],
+// neighbours int32[2 n] (only offsets[n_comps] entries are used).
+extern "C" int mdvc_host_adjacency(int32_t n_comps, const int32_t *eu_host, const int32_t *ev_host, long long n,
+                                   long long *offsets_out_host, int32_t *nbrs_out_host) {
+    if (n_comps < 0 || n < 0 || !offsets_out_host || (n > 0 && (!eu_host || !ev_host || !nbrs_out_host))) return MDVC_ERR_BADARG;
+    size_t cap = 64;
+    while (cap < (size_t)n * 2 + 2) cap <<= 1;
+    const unsigned long long EMPTY = ~0ull;
+    std::vector<unsigned long long> table(cap, EMPTY);
+    std::vector<uint8_t> fresh((size_t)n, 0);
+    for (int32_t c = 0; c <= n_comps; ++c) offsets_out_host[c] = 0;
+    for (long long k = 0; k < n; ++k) {
+        const int32_t u = eu_host[k], v = ev_host[k];
+        if (u < 0 || v < 0 || u >= n_comps || v >= n_comps) return MDVC_ERR_BADARG;
+        const unsigned long long a = (unsigned long long)(u < v ? u : v), b = (unsigned long long)(u < v ? v : u);
+        const unsigned long long key = (a << 32) | b;
+        unsigned long long h = key;                              // splitmix64 finaliser: both key halves reach every bit
+        h ^= h >> 30; h *= 0xbf58476d1ce4e5b9ull; h ^= h >> 27; h *= 0x94d049bb133111ebull; h ^= h >> 31;
+        size_t slot = (size_t)h & (cap - 1);
+        while (table[slot] != EMPTY && table[slot] != key) slot = (slot + 1) & (cap - 1);
+        if (table[slot] == key) continue;
+        table[slot] = key;
+        fresh[(size_t)k] = 1;
+        ++offsets_out_host[(size_t)u + 1];
+        if (u != v) ++offsets_out_host[(size_t)v + 1];
+    }
+    for (int32_t c = 0; c < n_comps; ++c) offsets_out_host[(size_t)c + 1] += offsets_out_host[(size_t)c];
+    std::vector<long long> fill(offsets_out_host, offsets_out_host + n_comps);
+    for (long long k = 0; k < n; ++k) {
+        if (!fresh[(size_t)k]) continue;
+        const int32_t u = eu_host[k], v = ev_host[k];
+        nbrs_out_host[fill[(size_t)u]++] = v;
+        if (u != v) nbrs_out_host[fill[(size_t)v]++] = u;
+    }
+    return MDVC_OK;
+}

@@ -56,6 +56,38 @@ def shift_graph_ranks(n_nodes, edge_u, edge_v, edge_shift=None, skip=None, want_
     return root, rank, int(best.value)
 
 
+def component_neighbours(comp_of_node, n_comps, src, dst):
+    """(cs, cd): ordered distinct neighbour components per component (``mdvc_host_component_neighbours``)."""
+    lib = _lib.load()
+    comp = np.ascontiguousarray(comp_of_node, dtype=np.int32)
+    s = np.ascontiguousarray(src, dtype=np.int32)
+    d = np.ascontiguousarray(dst, dtype=np.int32)
+    cs = np.empty(len(s), dtype=np.int32)
+    cd = np.empty(len(s), dtype=np.int32)
+    n_out = ctypes.c_longlong(0)
+
+    def ptr(a):
+        return None if a.size == 0 else a.ctypes.data
+
+    rc = lib.mdvc_host_component_neighbours(len(comp), ptr(comp), int(n_comps), ptr(s), ptr(d), len(s), ptr(cs), ptr(cd),
+                                            ctypes.addressof(n_out))
+    _lib.check(rc, "mdvc_host_component_neighbours")
+    return cs[:n_out.value], cd[:n_out.value]
+
+
+def adjacency(n_comps, eu, ev):
+    """(offsets int64[n_comps + 1], neighbours int64) in networkx's adjacency order (``mdvc_host_adjacency``)."""
+    lib = _lib.load()
+    u = np.ascontiguousarray(eu, dtype=np.int32)
+    v = np.ascontiguousarray(ev, dtype=np.int32)
+    offsets = np.zeros(int(n_comps) + 1, dtype=np.int64)
+    nbrs = np.empty(2 * len(u), dtype=np.int32)
+    rc = lib.mdvc_host_adjacency(int(n_comps), u.ctypes.data if u.size else None, v.ctypes.data if v.size else None, len(u),
+                                 offsets.ctypes.data, nbrs.ctypes.data if nbrs.size else None)
+    _lib.check(rc, "mdvc_host_adjacency")
+    return offsets, nbrs[: int(offsets[-1])].astype(np.int64)
+
+
 # ------------------------------------------------------------------------------------------------
 # label graph
 # ------------------------------------------------------------------------------------------------
@@ -346,17 +378,23 @@ class PeriodicSolution:
             lg = self.label_graph
             K = len(self.comp_ids)
             src, dst = lg.half_edges()
-            cs, cd = self.comp_of_node[src], self.comp_of_node[dst]
-            keep = cs != cd
-            cs, cd, lab = cs[keep], cd[keep], lg.node_vals[src[keep]]
-            # add sequence: components in order, their labels ascending, each label's successors in insertion order
-            # (one stable sort on (component, label): the half-edges already are in insertion order)
-            lab_rank = lab - lab.min() if len(lab) else lab
-            order = np.argsort(cs.astype(np.int64) * (int(lab_rank.max()) + 1 if len(lab) else 1) + lab_rank, kind="stable")
-            cs, cd = cs[order].astype(np.int64), cd[order].astype(np.int64)
-            first = _first_occurrence(cs * K + cd)
-            cs, cd = cs[first], cd[first]
-            if len(cs):
+            if lg._sorted:
+                # add sequence -- components in order, their labels ascending, each label's successors in insertion
+                # order -- with every (component, neighbour) pair at its first occurrence: compiled, O(labels + edges)
+                cs, cd = component_neighbours(self.comp_of_node, K, src, dst)
+            else:
+                cs, cd = self.comp_of_node[src], self.comp_of_node[dst]
+                keep = cs != cd
+                cs, cd, lab = cs[keep], cd[keep], lg.node_vals[src[keep]]
+                lab_rank = lab - lab.min() if len(lab) else lab
+                order = np.argsort(cs.astype(np.int64) * (int(lab_rank.max()) + 1 if len(lab) else 1) + lab_rank, kind="stable")
+                cs, cd = cs[order].astype(np.int64), cd[order].astype(np.int64)
+                first = _first_occurrence(cs * K + cd)
+                cs, cd = cs[first], cd[first]
+            # The reference collects a component's neighbours in a Python set and adds the edges in that set's iteration
+            # order.  More than 100 000 components it cannot orient at all (its guard fires), so beyond that there is
+            # no order to reproduce and the first-occurrence order stays.
+            if len(cs) and K <= MAX_ORIENT_ITERATIONS:
                 brk = np.flatnonzero(cs[1:] != cs[:-1]) + 1
                 starts = np.concatenate([[0], brk]); ends = np.concatenate([brk, [len(cs)]])
                 multi = np.flatnonzero(ends - starts > 1)
@@ -365,22 +403,15 @@ class PeriodicSolution:
                     for s, e in zip(starts[multi].tolist(), ends[multi].tolist()):
                         ids[s:e] = set(ids[s:e])
                     cd = self.component_index(np.asarray(ids, dtype=np.int64))
-            self._ccg = (cs, cd)
+            self._ccg = (np.asarray(cs, dtype=np.int64), np.asarray(cd, dtype=np.int64))
         return self._ccg
 
     def contact_adjacency(self):
         """CSR (offsets, neighbours) of the component contact graph with networkx's adjacency order: a neighbour
         appears where the first edge joining the two components was added, from either side."""
         if "adj" not in self._cache:
-            K = len(self.comp_ids)
             cs, cd = self.contact_edges()
-            u = np.stack([cs, cd], 1).ravel()
-            v = np.stack([cd, cs], 1).ravel()
-            first = _first_occurrence(u * K + v)
-            u, v = u[first], v[first]
-            order = np.argsort(u, kind="stable")
-            offsets = np.concatenate([[0], np.cumsum(np.bincount(u, minlength=K))]).astype(np.int64)
-            self._cache["adj"] = (offsets, v[order])
+            self._cache["adj"] = adjacency(len(self.comp_ids), cs, cd)
         return self._cache["adj"]
 
     def component_contact_graph(self):
