@@ -8,7 +8,8 @@ import ctypes
 import os
 
 PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(PKG, "libmdvc.so")
+# MDVC_LIB=<path> loads another build of the same ABI (A/B timing of kernel variants; development only)
+LIB_PATH = os.environ.get("MDVC_LIB") or os.path.join(PKG, "libmdvc.so")
 
 OK = 0
 ERR_BADARG, ERR_CUDA, ERR_WORKSPACE = -1, -2, -3

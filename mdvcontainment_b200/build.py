@@ -32,24 +32,26 @@ def needs_build() -> bool:
     return any(os.path.getmtime(d) > t for d in deps if os.path.exists(d))
 
 
-def build_library(force: bool = False, verbose: bool = False) -> str:
-    if not force and not needs_build():
+def build_library(force: bool = False, verbose: bool = False, out: str | None = None) -> str:
+    """``out``: build a variant (with MDVC_NVCC_EXTRA defines) into another file instead of libmdvc.so."""
+    if out is None and not force and not needs_build():
         return LIB
     objs = []
     flags = [f for f in NVCC_FLAGS if not f.startswith("--use_fast_math")]
     flags += os.environ.get("MDVC_NVCC_EXTRA", "").split()          # e.g. -DSTRIP_TY=128 for tuning experiments
     for src in SOURCES:
-        obj = os.path.join(CSRC, os.path.splitext(src)[0] + ".o")
+        obj = os.path.join(CSRC, os.path.splitext(src)[0] + (".o" if out is None else ".variant.o"))
         cmd = [_nvcc(), *flags, "-c", os.path.join(CSRC, src), "-o", obj]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
             print(" ".join(cmd), file=sys.stderr)
         subprocess.check_call(cmd)
         objs.append(obj)
-    cmd = [_nvcc(), "-shared", "-gencode", "arch=compute_100a,code=sm_100a", *objs, "-o", LIB, "-lcudart"]
+    cmd = [_nvcc(), "-shared", "-gencode", "arch=compute_100a,code=sm_100a", *objs, "-o", out or LIB, "-lcudart"]
     subprocess.check_call(cmd)
-    return LIB
+    return out or LIB
 
 
 if __name__ == "__main__":
-    print(build_library(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    out = sys.argv[sys.argv.index("--out") + 1] if "--out" in sys.argv else None
+    print(build_library(force="--force" in sys.argv, verbose="-v" in sys.argv, out=out))

@@ -1168,11 +1168,18 @@ __device__ __noinline__ void pairs_one_run_global(const uint32_t *__restrict__ b
 // z-face bridges use both directions so that only planes x and x-1 are needed: the last run of a row
 // steps +z into the first runs of the 6 rows with dx in {0,-1}; the first run steps -z into the last
 // runs of the 3 rows with dx = -1 (the reverse of the dx = +1, +z steps).
-#define PT_TY 128
+#ifndef PT_TY
+#define PT_TY 64                    // 64 rows x 2 threads per tile: 189-193 us at 1024^3 against 202 (128 rows) and 214-222 (32 rows)
+#endif
 #define PT_ROWS (PT_TY + 2)
 #define PT_SLOTS (2 * PT_ROWS)
-#define PT_CAP 3072
-__global__ void __launch_bounds__(2 * PT_TY, 4)
+#ifndef PT_CAP
+#define PT_CAP (24 * PT_TY)
+#endif
+#ifndef PT_MIN_CTAS
+#define PT_MIN_CTAS (512 / PT_TY)
+#endif
+__global__ void __launch_bounds__(2 * PT_TY, PT_MIN_CTAS)
 k_tile_pairs(const uint32_t *__restrict__ bits, Dims D, Hdr *h, const uint32_t *__restrict__ rowoff,
              const uint8_t *__restrict__ rowpol, const uint32_t *__restrict__ runstart, const int32_t *__restrict__ lab,
              unsigned long long *cset, uint32_t c_slots, unsigned long long *bset, uint32_t b_slots, int periodic) {
