@@ -352,7 +352,9 @@ extern "C" int mdvc_bin_atoms(const float *pos, long long n, const double *T_hos
 // then the grid is cleared and filled one plane range at a time: a range is 16 MiB at 1024^3, so its clearing stores
 // and its REDs meet in the L2 and every line goes to DRAM once.  DRAM traffic: coordinates read once, 4 B/bead of keys
 // (L2-resident), grid written once.
+#ifndef BIN_CHUNKS
 #define BIN_CHUNKS 8
+#endif
 #define BIN_TILE_ATOMS 2048                  // 256 threads x 8 beads per iteration
 
 struct BinBuckets {

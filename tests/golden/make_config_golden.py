@@ -163,6 +163,9 @@ def main():
     if only in (None, "cylinder"):
         rec["cylinder_512"] = cylinder_512()
         print("cylinder 512:", rec["cylinder_512"]["str"])
+    if only == "cylinder1024":                         # ~10 min and ~25 GB of host memory: run on request only
+        rec["cylinder_1024"] = cylinder_512(1024)
+        print("cylinder 1024:", rec["cylinder_1024"]["str"])
     with open(out_path, "w") as fh:
         json.dump(rec, fh, indent=1, sort_keys=True)
 

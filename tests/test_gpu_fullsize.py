@@ -156,5 +156,23 @@ def test_hollow_cylinder_1024_known_answer():
     assert [sorted(len(list(v.containment_graph.successors(n))) for n in v.containment_graph.nodes) for v in (vc, small)][0] == \
         sorted(len(list(small.containment_graph.successors(n))) for n in small.containment_graph.nodes)
     assert str(vc).count("\n") == str(small).count("\n")
+    # the same grid through the unmodified reference (tests/golden/make_config_golden.py --only cylinder1024): DAG text,
+    # contacts, bridges and digests of the label and component grids
+    import json
+    import os
+    from golden_util import GOLD
+    with open(os.path.join(GOLD, "config_cases.json")) as fh:
+        rec = json.load(fh).get("cylinder_1024")
+    if rec is not None:
+        closed = dev.morph(bits, "de")
+        assert tensor_digest(closed.to_bool()) == rec["digest_closed"]
+        ref_vc = VoxelContainment(closed)
+        assert str(ref_vc) == rec["str"]
+        assert {str(int(k)): int(v) for k, v in ref_vc.voxel_counts.items()} == rec["counts"]
+        assert np.asarray(ref_vc._frame.contacts).reshape(-1, 2).tolist() == rec["contacts"]
+        assert np.asarray(ref_vc._frame.bridges).reshape(-1, 5).tolist() == rec["bridges"]
+        assert tensor_digest(ref_vc.nonp_labeled_grid_device) == rec["digest_labels"]
+        assert tensor_digest(ref_vc.components_grid_device) == rec["digest_components"]
+        del ref_vc, closed
     del vc, bits
     torch.cuda.empty_cache()
