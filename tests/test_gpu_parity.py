@@ -536,3 +536,22 @@ def test_pipeline_guards():
     assert torch.equal(first.components_dev, keep)
     assert first.components_dev.data_ptr() != other.components_dev.data_ptr()
     assert not torch.equal(other.components_dev, keep)
+
+
+def test_staging_memory_is_page_locked_and_outlives_its_views(dev):
+    """mdvc_host_alloc through device.staging_empty: pinned (ordinary and write-combined) host tensors usable as H2D
+    sources; a slice keeps the allocation alive after the parent tensor is gone."""
+    import gc
+    for wc in (False, True):
+        t = dev.staging_empty((1000, 3), torch.float32, write_combined=wc)
+        assert t.shape == (1000, 3) and t.dtype == torch.float32 and t.is_pinned()
+        src = torch.arange(3000, dtype=torch.float32).reshape(1000, 3)
+        t.copy_(src)
+        part = t[10:20]
+        del t
+        gc.collect()
+        d = part.to("cuda", non_blocking=True)
+        torch.cuda.synchronize()
+        assert torch.equal(d.cpu(), src[10:20])
+        del part, d
+        gc.collect()
