@@ -25,8 +25,9 @@ def main():
     path = sys.argv[1]
     last_frames = int(sys.argv[2]) if len(sys.argv) > 2 else 0
     seq = load(path)
-    if last_frames:      # keep only the launches from the last `last_frames` k_bin_atoms on
-        idx = [i for i, (n, _) in enumerate(seq) if n.startswith("k_bin_atoms")]
+    if last_frames:      # keep only the launches from the last `last_frames` frames on (a frame starts with its binning)
+        first = "k_bin_bucket" if any(n.startswith("k_bin_bucket") for n, _ in seq) else "k_bin_atoms"
+        idx = [i for i, (n, _) in enumerate(seq) if n.startswith(first)]
         seq = seq[idx[-last_frames]:]
     agg = collections.OrderedDict()
     for n, v in seq:
