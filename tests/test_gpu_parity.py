@@ -555,3 +555,30 @@ def test_staging_memory_is_page_locked_and_outlives_its_views(dev):
         assert torch.equal(d.cpu(), src[10:20])
         del part, d
         gc.collect()
+
+
+@pytest.mark.parametrize("shape,p", [((5, 7, 1000), 0.5), ((5, 7, 1024), 0.016), ((3, 4, 800), 0.004), ((6, 3, 552), 0.03),
+                                     ((2, 9, 1016), 0.9), ((4, 4, 1024), 0.0), ((1, 5, 640), 1.0)])
+def test_one_warp_per_row_dense_write(dev, shape, p):
+    """Rows of 17..32 words take k_expand_row32 (next row prefetched, run values looked up by warp shuffle when a row has
+    at most 32 runs, by loads otherwise): rows with 1, a few, about 32 and hundreds of runs, labels and components,
+    each grid alone and both together, against the oracle."""
+    from mdvcontainment_b200 import VoxelContainment
+    rng = np.random.default_rng(int(1000 * p) + shape[2])
+    g = rng.random(shape) < p
+    want = vo.label_3d_grid(g).astype(np.int32)
+    vc = VoxelContainment(g)
+    fr = vc._frame
+    both_l = torch.empty(shape, dtype=torch.int32, device="cuda")
+    both_c = torch.empty(shape, dtype=torch.int32, device="cuda")
+    fr.plan.expand(fr.bits, both_l, both_c)
+    only_l = torch.full(shape, 7, dtype=torch.int32, device="cuda")
+    fr.plan.expand(fr.bits, only_l, None)
+    only_c = torch.full(shape, 7, dtype=torch.int32, device="cuda")
+    fr.plan.expand(fr.bits, None, only_c)
+    assert np.array_equal(both_l.cpu().numpy(), want)
+    assert torch.equal(only_l, both_l) and torch.equal(only_c, both_c)
+    lut = torch.as_tensor(fr.lut, device="cuda")
+    assert torch.equal(both_c, lut[(both_l + int(fr.header.n_false)).long()])
+    runs = 1 + int((g[:, :, 1:] != g[:, :, :-1]).sum(axis=2).max())
+    assert (runs > 32) == (p in (0.5, 0.03))                  # both look-up paths are exercised across the cases

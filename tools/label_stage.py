@@ -30,6 +30,22 @@ def main():
         h = plan.read_header()
         print(f"[{r}] label {ev[0].elapsed_time(ev[1]) * 1e3:7.1f} us  pairs {ev[1].elapsed_time(ev[2]) * 1e3:7.1f} us  "
               f"runs {h.total_runs} labels +{h.n_true}/-{h.n_false} contacts {h.n_contacts} bridges {h.n_bridges} flags {h.flags}")
+    # the dense write alone (components from the device-side periodic merge), labels + components and components only
+    plan.components(True)
+    labels = torch.empty((n, n, n), dtype=torch.int32, device="cuda")
+    comps = torch.empty((n, n, n), dtype=torch.int32, device="cuda")
+    for name, args in (("labels + components", (labels, comps)), ("components only", (None, comps))):
+        ts = []
+        for _ in range(6):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            plan.expand(closed, *args)
+            e1.record()
+            torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        t = sorted(ts)[len(ts) // 2]
+        nbytes = n ** 3 * (4.0 * sum(a is not None for a in args) + 0.125)
+        print(f"expand {name:20s} {t * 1e3:8.1f} us  {nbytes / t / 1e6:7.0f} GB/s   digest {int(comps[::97, ::89, ::83].sum())}")
 
 
 if __name__ == "__main__":
