@@ -29,7 +29,7 @@ struct Hdr {                       // overlays mdvc_frame_header (64 x uint32)
     uint32_t run_eff;              // runs actually stored (0 when the capacity overflowed)
     uint32_t n_labels;             // n_false + n_true + 1, 0 when the label capacity overflowed
     uint32_t n_strip_roots;        // entries of the strip-root list (interior nodes of the trees)
-    uint32_t pad0[1];
+    uint32_t n_pair_rows;          // entries of the pair stage's row list (k_row_pairs -> k_task_pairs)
     unsigned long long tot_roots;  // hi32 = False roots, lo32 = True roots
     unsigned long long tot_comps;  // hi32 = negative components, lo32 = positive components
     uint32_t pad1[48];
@@ -44,8 +44,8 @@ struct Dims {
 };
 
 struct Layout {
-    size_t hdr, rowoff, rowpol, tile32, tile64, runstart, parent, lab, runcomp, scan64, vol, lparent, lut, lscan,
-        ccount, cset, bset, ckeys, bkeys, crows, brows, total;
+    size_t hdr, rowoff, rowpol, rowflag, pairrows, tile32, tile64, runstart, parent, lab, runcomp, scan64, vol, lparent,
+        lut, lscan, ccount, cset, bset, ckeys, bkeys, crows, brows, total;
 };
 
 static inline size_t align_up(size_t v) { return (v + 255) & ~(size_t)255; }
@@ -65,6 +65,8 @@ static Layout make_layout(long long rows, const mdvc_frame_caps *c) {
     L.hdr = take(sizeof(Hdr));
     L.rowoff = take(((size_t)rows + 2) * 4);
     L.rowpol = take((size_t)rows + 4);                 // value of the first voxel of every row (1 byte each)
+    L.rowflag = take((size_t)rows + 4);                // bit q: the row does not mirror its q-th raster-order predecessor row
+    L.pairrows = take(((size_t)rows + 1) * 4);         // rows whose run lists the pair stage has to compare
     L.tile32 = take(mdvc_scan_scratch_elems((uint32_t)scan_cap) * 4);
     L.tile64 = take(mdvc_scan_scratch_elems((uint32_t)scan_cap) * 8);
     L.runstart = take((M + 1) * 4);
@@ -441,20 +443,31 @@ struct BlockSetT {
     __device__ void clear() {
         for (int i = threadIdx.x; i < SLOTS; i += blockDim.x) slot[i] = MDVC_KEY_EMPTY;
     }
-    // true if the key was not yet known to this block (or the block cache is full)
-    __device__ bool add(unsigned long long key) {
+    // 0: the key was already known to this block, 1: stored now, 2: no room for it (16 probes)
+    __device__ int add_state(unsigned long long key) {
         uint32_t h = (((uint32_t)key ^ (uint32_t)(key >> 31)) * 2654435761u >> 16) & (SLOTS - 1);
         for (int probe = 0; probe < 16; ++probe) {
             unsigned long long cur = slot[h];
-            if (cur == key) return false;
+            if (cur == key) return 0;
             if (cur == MDVC_KEY_EMPTY) {
                 unsigned long long old = atomicCAS(&slot[h], MDVC_KEY_EMPTY, key);
-                if (old == MDVC_KEY_EMPTY) return true;
-                if (old == key) return false;
+                if (old == MDVC_KEY_EMPTY) return 1;
+                if (old == key) return 0;
             }
             h = (h + 1) & (SLOTS - 1);
         }
-        return true;
+        return 2;
+    }
+    // true if the key was not yet known to this block (or the block cache is full)
+    __device__ bool add(unsigned long long key) { return add_state(key) != 0; }
+    // Every key stored here goes into a global set, one key per thread (all threads of the CTA, after a barrier).
+    // Pair kernels park their keys in the cache and flush once: an insertion is an L2 round trip, and the thread
+    // that walks a wrapped row would otherwise pay one per new key, back to back.
+    __device__ void flush(unsigned long long *set, uint32_t n_slots, uint32_t *flags, uint32_t overflow_bit) {
+        for (int i = threadIdx.x; i < SLOTS; i += blockDim.x) {
+            const unsigned long long k = slot[i];
+            if (k != MDVC_KEY_EMPTY && !mdvc_set_insert(set, n_slots, k)) atomicOr(flags, overflow_bit);
+        }
     }
 };
 typedef BlockSetT<256> BlockSet;
@@ -516,7 +529,8 @@ __device__ __forceinline__ uint32_t climb_ro(const uint32_t *parent, uint32_t v)
 
 __global__ void __launch_bounds__(256)
 k_link_round(const uint32_t *__restrict__ bits, Dims D, const Hdr *__restrict__ h, const uint32_t *__restrict__ rowoff,
-             const uint32_t *__restrict__ runstart, uint32_t *parent, int phase, int s, int radix, int force_lpr) {
+             const uint32_t *__restrict__ runstart, uint32_t *parent, int phase, int s, int radix, int force_lpr,
+             uint8_t *__restrict__ rowflag) {
     __shared__ BlockSet seen;
     seen.clear();
     __syncthreads();
@@ -536,6 +550,16 @@ k_link_round(const uint32_t *__restrict__ bits, Dims D, const Hdr *__restrict__ 
         if (m % radix == 0) continue;                       // border of a later round
         const uint32_t r = (uint32_t)x * D.Y + y;
         const uint32_t i1 = rowoff[r + 1];
+        if (phase == 0 && rowflag && sub == 0) {
+            // a strip's first row against the row before it (the previous strip's last): same test as rows_mirror,
+            // on the global run table
+            const uint32_t a0 = rowoff[r], b0 = rowoff[r - 1], n = i1 - a0;
+            const uint32_t za = r * (uint32_t)D.Z, zb = (r - 1) * (uint32_t)D.Z;
+            bool mir = (a0 - b0) == n && bit_at(bits, D, r, 0) == bit_at(bits, D, r - 1, 0);
+            for (uint32_t k = 0; mir && k + 1 < n; ++k)
+                mir = runstart[b0 + k] - zb < runstart[a0 + k + 1] - za && runstart[a0 + k] - za < runstart[b0 + k + 1] - zb;
+            rowflag[r] = (uint8_t)!mir;
+        }
         for (uint32_t i = rowoff[r] + sub; i < i1; i += lpr) {
             uint32_t lin = runstart[i];
             int a = (int)(lin - r * (uint32_t)D.Z);
@@ -644,7 +668,8 @@ __device__ __forceinline__ bool rows_mirror(const uint32_t *tz, uint32_t a0, uin
 
 __global__ void __launch_bounds__(TILE_THREADS, 8)
 k_strip_link(const uint32_t *__restrict__ bits, Dims D, Hdr *h, const uint32_t *__restrict__ rowoff,
-             const uint8_t *__restrict__ rowpol, const uint32_t *__restrict__ runstart, uint32_t *parent, uint32_t *rootlist) {
+             const uint8_t *__restrict__ rowpol, const uint32_t *__restrict__ runstart, uint32_t *parent, uint32_t *rootlist,
+             uint8_t *__restrict__ rowflag) {
     __shared__ uint32_t srow[STRIP_TY + 1];
     __shared__ uint32_t spol[STRIP_TY];
     __shared__ uint8_t smir[STRIP_TY], stop[STRIP_TY];
@@ -676,9 +701,13 @@ k_strip_link(const uint32_t *__restrict__ bits, Dims D, Hdr *h, const uint32_t *
             __syncthreads();
             // rows that mirror the previous row (same run count, same first value, interleaving starts): run m
             // touches run m of that row and no other run of its value, so the link needs no search
-            for (int t = threadIdx.x; t < ny; t += blockDim.x)
+            // rowflag bit 0 = "does not mirror row y-1": the pair kernel only walks such rows (this store initialises
+            // the byte; the strip's first row is judged by k_link_round, the other plane's rows by k_tile_link_x)
+            for (int t = threadIdx.x; t < ny; t += blockDim.x) {
                 smir[t] = t > 0 && rows_mirror(sz, srow[t] - gbase, srow[t + 1] - gbase, srow[t - 1] - gbase,
                                                srow[t] - gbase, spol[t] == spol[t - 1]);
+                rowflag[r0 + t] = (uint8_t)(t > 0 && !smir[t]);
+            }
             __syncthreads();
             // a stack of consecutively mirrored rows links run m of every row straight to run m of the stack's top
             // row (the correspondence m -> m is transitive), which keeps the trees one level deep
@@ -748,6 +777,7 @@ k_strip_link(const uint32_t *__restrict__ bits, Dims D, Hdr *h, const uint32_t *
         } else {
             // too many runs for shared memory: link the rows of this strip through global memory
             seen.clear();
+            for (int t = threadIdx.x; t < ny; t += blockDim.x) rowflag[r0 + t] = (uint8_t)(t > 0);
             __syncthreads();
             for (uint32_t k = threadIdx.x; k < nloc; k += blockDim.x) {
                 uint32_t i = gbase + k;
@@ -786,7 +816,8 @@ k_flatten_list(const Hdr *__restrict__ h, const uint32_t *__restrict__ list, uin
 // in shared memory; only new (root,root) pairs of the CTA reach the global union.
 __global__ void __launch_bounds__(TILE_THREADS, 8)
 k_tile_link_x(const uint32_t *__restrict__ bits, Dims D, const Hdr *__restrict__ h, const uint32_t *__restrict__ rowoff,
-              const uint8_t *__restrict__ rowpol, const uint32_t *__restrict__ runstart, uint32_t *parent, int s, int radix) {
+              const uint8_t *__restrict__ rowpol, const uint32_t *__restrict__ runstart, uint32_t *parent, int s, int radix,
+              uint8_t *__restrict__ rowflag) {
     __shared__ uint32_t orow[STRIP_TY + 1], brow[STRIP_TY + 3];
     __shared__ uint32_t opol[STRIP_TY], bpol[STRIP_TY + 2];
     __shared__ uint32_t tz[STRIP_CAP], troot[STRIP_CAP];       // own runs first, then the other plane's
@@ -851,6 +882,14 @@ k_tile_link_x(const uint32_t *__restrict__ bits, Dims D, const Hdr *__restrict__
                 smir[t] = mir;
             }
             __syncthreads();
+            for (int lr = threadIdx.x; lr < ny; lr += blockDim.x) {          // rowflag bits 1..3: (-1,-1) (-1,0) (-1,+1)
+                uint32_t f = 0;
+                for (int dy = -1; dy <= 1; ++dy) {
+                    const int yy = y0 + lr + dy;
+                    if (yy >= 0 && yy < D.Y && !smir[3 * lr + dy + 1]) f |= 2u << (dy + 1);
+                }
+                if (f) rowflag[r0 + lr] |= (uint8_t)f;
+            }
             for (uint32_t k = threadIdx.x; k < no; k += blockDim.x) {
                 uint32_t e = tz[k], lr = e >> 24;
                 uint32_t rb0 = orow[lr] - go, re0 = orow[lr + 1] - go;
@@ -882,6 +921,7 @@ k_tile_link_x(const uint32_t *__restrict__ bits, Dims D, const Hdr *__restrict__
                 }
             }
         } else {
+            for (int lr = threadIdx.x; lr < ny; lr += blockDim.x) rowflag[r0 + lr] |= (uint8_t)0xe;
             for (uint32_t k = threadIdx.x; k < no; k += blockDim.x) {
                 uint32_t i = go + k;
                 uint32_t lin = runstart[i];
@@ -1083,9 +1123,14 @@ struct PairSink {
     __device__ __noinline__ void put_slow(unsigned long long key) {
         last2 = last;
         last = key;
-        if (!cache->add(key)) return;
+        if (cache->add_state(key) != 2) return;                       // known, or parked until flush()
         if (*(volatile uint32_t *)flags & overflow_bit) return;       // already overflowed: this attempt is void anyway
         if (!mdvc_set_insert(slots, n_slots, key)) atomicOr(flags, overflow_bit);
+    }
+    // all threads of the CTA, once, after the last put
+    __device__ void flush() {
+        __syncthreads();
+        cache->flush(slots, n_slots, flags, overflow_bit);
     }
 };
 
@@ -1104,278 +1149,187 @@ __device__ __forceinline__ void emit_bridge(PairSink &s, int la, int lb, int sx,
     }
 }
 
-// Global-memory version of the pair detection for one run A = [a,b] of row r (fallback for tiles that
-// do not fit shared memory).  Row relations are visited once each: the four raster-order predecessor
-// offsets for x/y neighbours (in-box -> contacts, through a face -> bridges with shift (sx,sy,0)), and
-// all nine (dx,dy) for the step through the z-max face (shift (sx,sy,+1)) taken by the last run of the
-// row.  The reverse steps give the same normalised rows (emit_bridge).
-__device__ __noinline__ void pairs_one_run_global(const uint32_t *__restrict__ bits, const Dims &D, const uint32_t *__restrict__ rowoff,
-                                     const uint32_t *__restrict__ runstart, const int32_t *__restrict__ lab,
-                                     PairSink &cs, PairSink &bs, int periodic, uint32_t i) {
-    uint32_t lin = runstart[i];
-    uint32_t r = lin / (uint32_t)D.Z;
-    int a = (int)(lin - r * (uint32_t)D.Z);
-    int b = (int)(runstart[i + 1] - r * (uint32_t)D.Z) - 1;
-    int y = (int)(r % (uint32_t)D.Y), x = (int)(r / (uint32_t)D.Y);
-    uint32_t v = bit_at(bits, D, r, a);
-    int la = lab[i];
-    if (a > 0) emit_contact(cs, lab[i - 1], la);              // previous run of the same row
-    int lo = a > 0 ? a - 1 : 0, hi = b + 1 < D.Z ? b + 1 : D.Z - 1;
-    for (int k = 0; k < 4; ++k) {
-        int nx = x + (k < 3 ? -1 : 0), ny = y + (k < 3 ? k - 1 : -1), sx = 0, sy = 0;
-        if (nx < 0) { nx = D.X - 1; sx = -1; }
-        if (ny < 0) { ny = D.Y - 1; sy = -1; } else if (ny >= D.Y) { ny = 0; sy = 1; }
-        bool wraps = (sx | sy) != 0;
-        if ((sy && !periodic) || (sx && periodic != 1)) continue;
-        uint32_t r2 = (uint32_t)nx * D.Y + ny;
-        uint32_t j = run_at(runstart, rowoff, D, r2, lo);
-        uint32_t end = rowoff[r2 + 1], limit = r2 * (uint32_t)D.Z + (uint32_t)hi;
-        if (!wraps) {                                          // contacts: runs of the other value
-            if (bit_at(bits, D, r2, lo) == v) ++j;
-            for (; j < end && runstart[j] <= limit; j += 2) emit_contact(cs, la, lab[j]);
-        } else {                                               // bridges: every run in reach
-            for (; j < end && runstart[j] <= limit; ++j) emit_bridge(bs, la, lab[j], sx, sy, 0);
+// Stage 2b, the row pairs that do need their run lists compared.  Relation q of a row: 0 = (0,-1) in the own plane,
+// 1..3 = (-1, dy = q-2) in the plane before; every unordered pair of neighbouring rows is one relation of its later
+// row.  In-box relations are skipped when the two rows mirror each other: same number of runs, same first value, and
+// starts that interleave (every run starts before the next run of the other row: s'_m < s_{m+1} and s_m < s'_{m+1}).
+// Then run k overlaps run k of the neighbour voxel on voxel (same value, adjacent rows: one 26-connected set, hence the
+// same label) and otherwise only reaches its runs k-1 and k+1, whose labels are this row's own neighbours' labels, so
+// every cross-row contact is already among the in-row contacts (k_row_pairs).  The link kernels ran that test on the
+// same row pairs and left the outcome in rowflag (bit q set = not mirrored): 1-2 % of the rows of a smooth grid.
+// Relations through a periodic x or y face (bridges) are always walked.
+__device__ __forceinline__ uint32_t pair_relations(const Dims &D, int periodic, const uint8_t *__restrict__ rowflag,
+                                                   uint32_t row, int x, int y) {
+    uint32_t need = rowflag[row];                                  // in-box relations that are not mirrored
+    if (periodic) {
+        if (y == 0) need |= 1u;
+        if (x != 0 || periodic == 1) {                             // periodic == 2: the x faces belong to the caller
+            if (x == 0 || y == 0) need |= 2u;
+            if (x == 0) need |= 4u;
+            if (x == 0 || y == D.Y - 1) need |= 8u;
         }
     }
-    if (periodic && b == D.Z - 1) {                            // steps through the z-max face
-        for (int dx = -1; dx <= 1; ++dx) {
-            int nx = x + dx, sx = 0;
-            if (nx < 0) { nx = D.X - 1; sx = -1; } else if (nx >= D.X) { nx = 0; sx = 1; }
-            if (sx && periodic != 1) continue;
-            for (int dy = -1; dy <= 1; ++dy) {
-                int ny = y + dy, sy = 0;
-                if (ny < 0) { ny = D.Y - 1; sy = -1; } else if (ny >= D.Y) { ny = 0; sy = 1; }
-                emit_bridge(bs, la, lab[rowoff[(uint32_t)nx * D.Y + ny]], sx, sy, 1);
-            }
-        }
-    }
-    if (periodic && a == 0) {
-        // -z steps into the last runs of plane x-1: neighbouring tiles on the shared-memory path rely
-        // on this direction for their dx = +1 relations (see k_tile_pairs)
-        int nx = x - 1, sx = 0;
-        if (nx < 0) { nx = D.X - 1; sx = -1; }
-        for (int dy = -1; dy <= 1 && !(sx && periodic != 1); ++dy) {
-            int ny = y + dy, sy = 0;
-            if (ny < 0) { ny = D.Y - 1; sy = -1; } else if (ny >= D.Y) { ny = 0; sy = 1; }
-            emit_bridge(bs, la, lab[rowoff[(uint32_t)nx * D.Y + ny + 1] - 1], sx, sy, -1);
-        }
-    }
+    return need;
 }
 
-// Pair detection on tiles: PT_TY rows of plane x plus their halo rows (y0-1, y0+ny) and the rows
-// y0-1 .. y0+ny of plane x-1 (periodic wrap included) are loaded -- run z-starts and labels -- into
-// shared memory; every lookup of the walk then stays on chip.  Slot = plane * (PT_TY+2) + (yl+1).
-// z-face bridges use both directions so that only planes x and x-1 are needed: the last run of a row
-// steps +z into the first runs of the 6 rows with dx in {0,-1}; the first run steps -z into the last
-// runs of the 3 rows with dx = -1 (the reverse of the dx = +1, +z steps).
-#ifndef PT_TY
-#define PT_TY 64                    // 64 rows x 2 threads per tile: 189-193 us at 1024^3 against 202 (128 rows) and 214-222 (32 rows)
-#endif
-#define PT_ROWS (PT_TY + 2)
-#define PT_SLOTS (2 * PT_ROWS)
-#ifndef PT_CAP
-#define PT_CAP (24 * PT_TY)
-#endif
-#ifndef PT_MIN_CTAS
-#define PT_MIN_CTAS (512 / PT_TY)
-#endif
-__global__ void __launch_bounds__(2 * PT_TY, PT_MIN_CTAS)
-k_tile_pairs(const uint32_t *__restrict__ bits, Dims D, Hdr *h, const uint32_t *__restrict__ rowoff,
-             const uint8_t *__restrict__ rowpol, const uint32_t *__restrict__ runstart, const int32_t *__restrict__ lab,
-             unsigned long long *cset, uint32_t c_slots, unsigned long long *bset, uint32_t b_slots, int periodic) {
-    __shared__ uint32_t srow[PT_SLOTS], sgb[PT_SLOTS], scnt[PT_SLOTS], soff[PT_SLOTS + 1], spol[PT_SLOTS];
-    __shared__ int ssy[PT_SLOTS];
-    __shared__ uint32_t tz[PT_CAP];
-    __shared__ int32_t tv[PT_CAP];
+// Stage 2a, one thread per row: everything the pair stage finds without comparing run lists --
+//   * contacts between consecutive runs of a row (they always differ in value);
+//   * bridges through the z faces: the last run steps +z into the first runs of the six rows with dx in {0,-1}, the
+//     first run steps -z into the last runs of the three rows with dx = -1 (the reverse of the dx = +1, +z steps), so
+//     only rows at or before this one in raster order are read.
+// The eleven labels of the z-face steps almost always repeat from one row to the next: a row whose labels equal the
+// previous row's (and neither row touches an x or y face, where the shift vectors differ) has nothing new to say.
+// A warp takes 31 consecutive rows; lane 0 holds the row before them, which only seeds the comparison.
+// periodic: 0 none, 1 all axes, 2 y and z only (slab interior: the x faces belong to the caller).
+__global__ void __launch_bounds__(256)
+k_row_pairs(Dims D, Hdr *h, const uint32_t *__restrict__ rowoff, const uint8_t *__restrict__ rowflag,
+            const int32_t *__restrict__ lab, uint32_t *__restrict__ pairrows, unsigned long long *cset, uint32_t c_slots,
+            unsigned long long *bset, uint32_t b_slots, int periodic) {
     __shared__ BlockSet c_cache, b_cache;
     c_cache.clear(); b_cache.clear();
     __syncthreads();
     if (h->n_labels == 0) return;
     PairSink cs{&c_cache, cset, c_slots, &h->flags, MDVC_OVERFLOW_CONTACTS, MDVC_KEY_EMPTY, MDVC_KEY_EMPTY};
     PairSink bs{&b_cache, bset, b_slots, &h->flags, MDVC_OVERFLOW_BRIDGES, MDVC_KEY_EMPTY, MDVC_KEY_EMPTY};
-    const int spp = (D.Y + PT_TY - 1) / PT_TY;
-    const long long n_tiles = (long long)D.X * spp;
-    int zc[9], zc_first = 0, zc_last = 0, zc_flags = -1;        // last emitted z-face signature of this thread
-#pragma unroll
-    for (int q = 0; q < 9; ++q) zc[q] = 0;
-    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const int x = (int)(tile / spp), y0 = (int)(tile % spp) * PT_TY;
-        const int ny = min(PT_TY, D.Y - y0);
-        const int sx_other = x == 0 ? -1 : 0;
-        __syncthreads();
-        for (int t = threadIdx.x; t < PT_SLOTS; t += blockDim.x) {
-            int p = t / PT_ROWS, j = t - p * PT_ROWS;
-            int yy = y0 + j - 1, sy = 0;
-            if (yy < 0) { yy = D.Y - 1; sy = -1; } else if (yy >= D.Y) { yy = 0; sy = 1; }
-            int xx = p == 0 ? x : (x == 0 ? D.X - 1 : x - 1);
-            // periodic: 0 none, 1 all axes, 2 y and z only (slab interior: the x faces belong to the caller)
-            bool valid = j <= ny + 1 && (sy == 0 || periodic != 0) && (!(p == 1 && x == 0) || periodic == 1);
-            uint32_t rg = (uint32_t)xx * D.Y + yy;
-            uint32_t g0 = valid ? rowoff[rg] : 0u, g1 = valid ? rowoff[rg + 1] : 0u;
-            srow[t] = rg; sgb[t] = g0; scnt[t] = g1 - g0; ssy[t] = sy;
-            spol[t] = valid ? rowpol[rg] : 0u;
+    const int lane = threadIdx.x & 31;
+    const uint32_t n_rows = (uint32_t)D.rows;                      // < 2^31
+    const uint32_t n_warps = (n_rows + 30u) / 31u, warp_stride = (gridDim.x * blockDim.x) >> 5;
+    int c_lo = 0, c_hi = 0, c_lo2 = 0, c_hi2 = 0;                  // the two contact pairs this thread emitted last
+    for (uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < n_warps; w += warp_stride) {
+        const uint32_t row = w * 31u + (uint32_t)lane - 1u;        // lane 0 of warp 0: 0xffffffff, not live
+        const bool live = row < n_rows, seed = lane == 0;
+        const int x = live ? (int)(row / (uint32_t)D.Y) : 0, y = live ? (int)(row - (uint32_t)x * (uint32_t)D.Y) : 0;
+        const int xo = x == 0 ? D.X - 1 : x - 1, sxo = x == 0 ? -1 : 0;
+        const bool other_ok = x != 0 || periodic == 1;
+        const uint32_t own0 = (uint32_t)x * D.Y, oth0 = (uint32_t)xo * D.Y;
+        const uint32_t b = live ? rowoff[own0 + y] : 0u, e = live ? rowoff[own0 + y + 1] : 0u;
+        {   // rows with relations to walk -> k_task_pairs' list (one atomic per warp)
+            const uint32_t need = live && !seed ? pair_relations(D, periodic, rowflag, row, x, y) : 0u;
+            const unsigned m = __ballot_sync(MDVC_FULL, need != 0);
+            if (m) {
+                uint32_t base = 0;
+                if (lane == 0) base = atomicAdd(&h->n_pair_rows, (uint32_t)__popc(m));
+                base = __shfl_sync(MDVC_FULL, base, 0);
+                if (need) pairrows[base + __popc(m & ((1u << lane) - 1u))] = row;
+            }
         }
-        __syncthreads();
-        if (threadIdx.x < 32) {                              // exclusive scan of the slot counts by one warp
-            constexpr int PER = (PT_SLOTS + 31) / 32;
-            uint32_t local[PER], sum = 0;
+        // q 0..2: first runs of the own plane's rows y-1, y, y+1; 3..5: first runs of the other plane's; 6..8: last
+        // runs of the other plane's; 9, 10: this row's first and last run
+        int cur[11], sy3[3];
+        if (periodic) {
+            uint32_t at[9];
 #pragma unroll
-            for (int q = 0; q < PER; ++q) {
-                int t = threadIdx.x * PER + q;
-                local[q] = t < PT_SLOTS ? scnt[t] : 0u;
-                sum += local[q];
+            for (int d = 0; d < 3; ++d) {
+                int yy = y + d - 1;
+                sy3[d] = 0;
+                if (yy < 0) { yy = D.Y - 1; sy3[d] = -1; } else if (yy >= D.Y) { yy = 0; sy3[d] = 1; }
+                at[d] = d == 1 ? b : (live ? rowoff[own0 + yy] : 0u);
+                at[3 + d] = live && other_ok ? rowoff[oth0 + yy] : 0u;
+                at[6 + d] = live && other_ok ? rowoff[oth0 + yy + 1] - 1u : 0u;
             }
-            uint32_t inc = sum;
-            for (int o = 1; o < 32; o <<= 1) {
-                uint32_t up = __shfl_up_sync(MDVC_FULL, inc, o);
-                if ((int)threadIdx.x >= o) inc += up;
-            }
-            uint32_t run = inc - sum;
 #pragma unroll
-            for (int q = 0; q < PER; ++q) {
-                int t = threadIdx.x * PER + q;
-                if (t < PT_SLOTS) soff[t] = run;
-                run += local[q];
+            for (int q = 0; q < 9; ++q) cur[q] = live && (q < 3 || other_ok) ? lab[at[q]] : 0;
+            cur[9] = cur[1];
+            cur[10] = live ? lab[e - 1] : 0;
+            const bool on_face = y == 0 || y == D.Y - 1 || x == 0;
+            const int up_other = __shfl_up_sync(MDVC_FULL, (int)(on_face || !live), 1);   // every lane shuffles
+            bool same = !on_face && !seed && !up_other;
+#pragma unroll
+            for (int q = 0; q < 11; ++q) {
+                const int up = __shfl_up_sync(MDVC_FULL, cur[q], 1);
+                same = same && cur[q] == up;
             }
-            if (threadIdx.x == 31) soff[PT_SLOTS] = inc;
+            if (live && !seed && !same) {
+#pragma unroll
+                for (int q = 0; q < 9; ++q) {
+                    if (q >= 3 && !other_ok) break;
+                    emit_bridge(bs, q < 6 ? cur[10] : cur[9], cur[q], q < 3 ? 0 : sxo, sy3[q % 3], q < 6 ? 1 : -1);
+                }
+            }
         }
-        __syncthreads();
-        const uint32_t total = soff[PT_SLOTS];
-        if (total <= PT_CAP) {
-            for (int t = threadIdx.x; t < PT_SLOTS; t += blockDim.x) {    // one thread copies one row (few runs each)
-                const uint32_t cnt = scnt[t], g0 = sgb[t], o = soff[t], zb = srow[t] * (uint32_t)D.Z;
-                for (uint32_t k = 0; k < cnt; k += 4) {
-                    uint32_t v[4]; int32_t l[4];
-#pragma unroll
-                    for (int u = 0; u < 4; ++u)
-                        if (k + u < cnt) { v[u] = runstart[g0 + k + u]; l[u] = lab[g0 + k + u]; }
-#pragma unroll
-                    for (int u = 0; u < 4; ++u)
-                        if (k + u < cnt) { tz[o + k + u] = v[u] - zb; tv[o + k + u] = l[u]; }
-                }
+        if (live && !seed) {
+            int before = periodic ? cur[9] : lab[b];
+            for (uint32_t k = b + 1; k < e; ++k) {
+                const int now = lab[k];
+                const int lo = min(before, now), hi = max(before, now);
+                before = now;
+                if ((lo == c_lo && hi == c_hi) || (lo == c_lo2 && hi == c_hi2) || lo == hi) continue;
+                c_lo2 = c_lo; c_hi2 = c_hi; c_lo = lo; c_hi = hi;
+                cs.put(mdvc_pack_key(lo, hi, 0));
             }
-            __syncthreads();
-            // two threads per own row (thread groups of PT_TY): group 0 takes the in-row contacts, the neighbour row
-            // in the own plane and the z-face steps, group 1 the three neighbour rows of the other plane.  The runs
-            // are visited in z order, so the position in a neighbour row only moves forward (merge walk, no searches).
-            const int grp = (int)threadIdx.x / PT_TY;
-            const int q_lo = grp == 0 ? 0 : 1, q_hi = grp == 0 ? 1 : 4;
-            for (int slot = 1 + (int)threadIdx.x % PT_TY; slot <= ny; slot += PT_TY) {
-                const uint32_t rb0 = soff[slot], re0 = soff[slot + 1];
-                int nsl[4]; uint32_t pj[4], pe[4];
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    // q = 0: (0,-1) in the own plane; q = 1..3: (-1, dy = q-2) in the other plane
-                    nsl[q] = q == 0 ? slot - 1 : PT_ROWS + slot + (q - 2);
-                    pj[q] = soff[nsl[q]]; pe[q] = soff[nsl[q] + 1];
-                }
-                const uint32_t pol0 = spol[slot];
-                // Shortcut for in-box neighbour rows that mirror this row: same number of runs, same first
-                // value, and starts that interleave (every run starts before the next run of the other row:
-                // s'_m < s_{m+1} and s_m < s'_{m+1}).  Then run k overlaps run k of the neighbour voxel on voxel
-                // (same value, adjacent rows: one 26-connected set, hence the same label) and otherwise only
-                // reaches its runs k-1 and k+1, whose labels are this row's own neighbours' labels, so every
-                // cross-row contact is already among the in-row contacts emitted below.  True for most row
-                // pairs of smooth structures; anything else takes the walk.
-                // All candidate rows are checked in one sweep over this row's starts (each own start is loaded once
-                // for the up to three neighbours, each neighbour start once: every row starts at z = 0).
-                const uint32_t n = re0 - rb0;
-                bool mir[4];
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const int ns = nsl[q];
-                    if (q < q_lo || q >= q_hi) { pj[q] = pe[q]; mir[q] = false; continue; }
-                    mir[q] = pj[q] != pe[q] && !((q == 0 ? 0 : sx_other) | ssy[ns]) && (pe[q] - pj[q]) == n && spol[ns] == pol0;
-                }
-                if (mir[0] | mir[1] | mir[2] | mir[3]) {
-                    uint32_t a_k = 0, b_k[4] = {0, 0, 0, 0};
-                    for (uint32_t k = 0; k + 1 < n; ++k) {
-                        const uint32_t a_k1 = tz[rb0 + k + 1];
-#pragma unroll
-                        for (int q = 0; q < 4; ++q) {
-                            if (!mir[q]) continue;
-                            const uint32_t b_k1 = tz[pj[q] + k + 1];
-                            mir[q] = b_k[q] < a_k1 && a_k < b_k1;
-                            b_k[q] = b_k1;
-                        }
-                        a_k = a_k1;
-                        if (!(mir[0] | mir[1] | mir[2] | mir[3])) break;
-                    }
-#pragma unroll
-                    for (int q = 0; q < 4; ++q)
-                        if (mir[q]) pj[q] = pe[q];
-                }
-                for (uint32_t k = rb0; k < re0; ++k) {
-                    const int a = (int)tz[k];
-                    const int b = (k + 1 < re0) ? (int)tz[k + 1] - 1 : D.Z - 1;
-                    const uint32_t pol = pol0 ^ ((k - rb0) & 1u);
-                    const int la = tv[k];
-                    if (grp == 0 && k > rb0) emit_contact(cs, tv[k - 1], la);
-                    // Bridges take every run of the neighbour row within one voxel of [a, b].  Contacts only need the
-                    // runs of the other value that overlap [a, b] itself: a run that merely touches diagonally sits
-                    // next to a run of this run's value that overlaps it (same label as this run), so that pair is
-                    // one of the neighbour row's own in-row contacts.
-                    const uint32_t lo = a > 0 ? a - 1 : 0, hi = b + 1 < D.Z ? b + 1 : D.Z - 1;
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        if (pj[q] == pe[q]) continue;
-                        const int ns = nsl[q];
-                        const int sx = q == 0 ? 0 : sx_other, sy = ssy[ns];
-                        const bool wrapped = (sx | sy) != 0;
-                        const uint32_t from = wrapped ? lo : (uint32_t)a;
-                        uint32_t j = pj[q];
-                        while (j + 1 < pe[q] && tz[j + 1] <= from) ++j;    // run containing `from`
-                        pj[q] = j;
-                        if (!wrapped) {
-                            if ((spol[ns] ^ ((j - soff[ns]) & 1u)) == pol) ++j;
-                            for (; j < pe[q] && tz[j] <= (uint32_t)b; j += 2) emit_contact(cs, la, tv[j]);
-                        } else {
-                            for (; j < pe[q] && tz[j] <= hi; ++j) emit_bridge(bs, la, tv[j], sx, sy, 0);
-                        }
-                    }
-                }
-                if (periodic && grp == 0) {
-                    // z-face steps: nine records per row whose labels and wrap flags almost always repeat from
-                    // the previous row this thread handled.  The nine keys cycle through the 2-key cache, so
-                    // each would take the out-of-line set insertion; instead the row's z-face signature (the
-                    // labels involved + wrap flags) is compared with the last one emitted and skipped if equal.
-                    const int la_first = tv[rb0], la_last = tv[re0 - 1];
-                    int zl[9], flags = sx_other + 1;
-#pragma unroll
-                    for (int q = 0; q < 6; ++q) {
-                        const int ns = (q < 3 ? 0 : PT_ROWS) + slot + (q % 3) - 1;
-                        zl[q] = soff[ns] == soff[ns + 1] ? INT_MIN : tv[soff[ns]];
-                        flags = flags * 4 + (ssy[ns] + 1);
-                    }
-#pragma unroll
-                    for (int q = 0; q < 3; ++q) {
-                        const int ns = PT_ROWS + slot + q - 1;
-                        zl[6 + q] = soff[ns] == soff[ns + 1] ? INT_MIN : tv[soff[ns + 1] - 1];
-                    }
-                    bool same = la_first == zc_first && la_last == zc_last && flags == zc_flags;
-#pragma unroll
-                    for (int q = 0; q < 9; ++q) same = same && zl[q] == zc[q];
-                    if (!same) {
-                        zc_first = la_first; zc_last = la_last; zc_flags = flags;
-#pragma unroll
-                        for (int q = 0; q < 9; ++q) zc[q] = zl[q];
-                        for (int q = 0; q < 6; ++q) {                      // +z from the last run
-                            const int ns = (q < 3 ? 0 : PT_ROWS) + slot + (q % 3) - 1;
-                            if (zl[q] != INT_MIN) emit_bridge(bs, la_last, zl[q], q < 3 ? 0 : sx_other, ssy[ns], 1);
-                        }
-                        for (int q = 0; q < 3; ++q) {                      // -z from the first run
-                            const int ns = PT_ROWS + slot + q - 1;
-                            if (zl[6 + q] != INT_MIN) emit_bridge(bs, la_first, zl[6 + q], sx_other, ssy[ns], -1);
-                        }
-                    }
-                }
-            }
-        } else {
-            const uint32_t g0 = sgb[1], g1 = sgb[ny] + scnt[ny];       // own rows are contiguous in run ids
-            for (uint32_t i = g0 + threadIdx.x; i < g1; i += blockDim.x)
-                pairs_one_run_global(bits, D, rowoff, runstart, lab, cs, bs, periodic, i);
         }
     }
+    cs.flush();
+    bs.flush();
+}
+
+// One task = one listed row; PR_LANES lanes share it, each takes every PR_LANES-th run A = [a,b] and walks the runs of
+// the neighbour row that A reaches: contacts for in-box neighbours (runs of the other value that overlap [a,b] itself
+// -- a run that merely touches diagonally sits next to a run of A's value that overlaps it, same label as A, so that
+// pair is one of the neighbour row's own in-row contacts), bridges for wrapped neighbours (every run within one voxel
+// of [a,b], any value, with the image shift).  The reverse steps give the same normalised rows (emit_bridge).
+#define PR_LANES 8
+__global__ void __launch_bounds__(256)
+k_task_pairs(Dims D, Hdr *h, const uint32_t *__restrict__ rowoff, const uint8_t *__restrict__ rowpol,
+             const uint8_t *__restrict__ rowflag, const uint32_t *__restrict__ tasks, const uint32_t *__restrict__ runstart,
+             const int32_t *__restrict__ lab, unsigned long long *cset, uint32_t c_slots, unsigned long long *bset,
+             uint32_t b_slots, int periodic) {
+    __shared__ BlockSet c_cache, b_cache;
+    if (h->n_labels == 0) return;
+    const uint32_t n_tasks = h->n_pair_rows;
+    if (blockIdx.x * (blockDim.x / PR_LANES) >= n_tasks) return;
+    c_cache.clear(); b_cache.clear();
+    __syncthreads();
+    PairSink cs{&c_cache, cset, c_slots, &h->flags, MDVC_OVERFLOW_CONTACTS, MDVC_KEY_EMPTY, MDVC_KEY_EMPTY};
+    PairSink bs{&b_cache, bset, b_slots, &h->flags, MDVC_OVERFLOW_BRIDGES, MDVC_KEY_EMPTY, MDVC_KEY_EMPTY};
+    const uint32_t sub = threadIdx.x % PR_LANES;
+    const uint32_t stride = gridDim.x * (blockDim.x / PR_LANES);
+    for (uint32_t t = blockIdx.x * (blockDim.x / PR_LANES) + threadIdx.x / PR_LANES; t < n_tasks; t += stride) {
+        const uint32_t r = tasks[t];
+        const int x = (int)(r / (uint32_t)D.Y), y = (int)(r - (uint32_t)x * (uint32_t)D.Y);
+        const uint32_t need = pair_relations(D, periodic, rowflag, r, x, y);
+        const uint32_t rb = rowoff[r], re = rowoff[r + 1], zr = r * (uint32_t)D.Z;
+        const uint32_t pol0 = rowpol[r];
+        // the (up to four) neighbour rows: run range, first value, image shift
+        uint32_t nb[4], ne[4], npol[4], nz[4];
+        int nsx[4], nsy[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            int nx = q == 0 ? x : x - 1, ny = q == 0 ? y - 1 : y + q - 2;
+            nsx[q] = 0; nsy[q] = 0;
+            if (nx < 0) { nx = D.X - 1; nsx[q] = -1; }
+            if (ny < 0) { ny = D.Y - 1; nsy[q] = -1; } else if (ny >= D.Y) { ny = 0; nsy[q] = 1; }
+            const uint32_t r2 = (uint32_t)nx * D.Y + ny;
+            const bool on = (need >> q) & 1u;
+            nb[q] = on ? rowoff[r2] : 0u; ne[q] = on ? rowoff[r2 + 1] : 0u;
+            npol[q] = on ? rowpol[r2] : 0u; nz[q] = r2 * (uint32_t)D.Z;
+        }
+        for (uint32_t i = rb + sub; i < re; i += PR_LANES) {
+            const uint32_t a = runstart[i] - zr, b = (i + 1 < re ? runstart[i + 1] - zr : (uint32_t)D.Z) - 1u;
+            const uint32_t pol = pol0 ^ ((i - rb) & 1u);
+            const int la = lab[i];
+            const uint32_t lo = a > 0 ? a - 1 : 0, hi = b + 1 < (uint32_t)D.Z ? b + 1 : (uint32_t)D.Z - 1;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                if (nb[q] == ne[q]) continue;
+                const bool wrapped = (nsx[q] | nsy[q]) != 0;
+                const uint32_t from = (wrapped ? lo : a) + nz[q];
+                uint32_t j = nb[q], top = ne[q];                   // last run of the row that starts at or before `from`
+                while (top - j > 1) {
+                    const uint32_t mid = (j + top) >> 1;
+                    if (runstart[mid] <= from) j = mid; else top = mid;
+                }
+                if (!wrapped) {
+                    if ((npol[q] ^ ((j - nb[q]) & 1u)) == pol) ++j;
+                    for (; j < ne[q] && runstart[j] <= b + nz[q]; j += 2) emit_contact(cs, la, lab[j]);
+                } else {
+                    for (; j < ne[q] && runstart[j] <= hi + nz[q]; ++j) emit_bridge(bs, la, lab[j], nsx[q], nsy[q], 0);
+                }
+            }
+        }
+    }
+    cs.flush();
+    bs.flush();
 }
 
 // compact a hash set into a dense key list
@@ -1744,15 +1698,18 @@ __global__ void __launch_bounds__(256)
 k_expand_row32(const uint32_t *__restrict__ bits, Dims D, const Hdr *__restrict__ h, const uint32_t *__restrict__ rowoff,
                const int32_t *__restrict__ lab, const int32_t *__restrict__ runcomp,
                int32_t *__restrict__ out_lab, int32_t *__restrict__ out_comp, long long row_begin, long long row_end) {
-    if (h->n_labels == 0) return;
     const int lane = threadIdx.x & 31;
     const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
     long long row = row_begin + warp;
     if (row >= row_end) return;
     const uint32_t vmask = mdvc_valid_mask(lane, D.Z);
+    // a CTA lives for three or four rows per warp: the loads that do not depend on each other go out together (the
+    // "labels overflowed" flag is only looked at afterwards instead of stalling every warp for one round trip first)
+    const uint32_t n_labels = h->n_labels;
     uint32_t base = rowoff[row], nrun = rowoff[row + 1] - base;
     uint32_t B = lane < D.nw ? (bits[(size_t)row * D.pitch + lane] & vmask) : 0u;
+    if (n_labels == 0) return;
     int lv = (HAS_LAB && (uint32_t)lane < nrun) ? __ldg(lab + base + lane) : 0;
     int cv = (HAS_COMP && (uint32_t)lane < nrun) ? __ldg(runcomp + base + lane) : 0;
     for (;;) {
@@ -1875,7 +1832,7 @@ static int frame_label(const uint32_t *bits, int X, int Y, int Z, int pitch, voi
     cudaStream_t st = (cudaStream_t)stream;
     Hdr *h = at<Hdr>(ws, L.hdr);
     uint32_t *rowoff = at<uint32_t>(ws, L.rowoff);
-    uint8_t *rowpol = at<uint8_t>(ws, L.rowpol);
+    uint8_t *rowpol = at<uint8_t>(ws, L.rowpol), *rowflag = at<uint8_t>(ws, L.rowflag);
     uint32_t *runstart = at<uint32_t>(ws, L.runstart);
     uint32_t *parent = at<uint32_t>(ws, L.parent);
     int32_t *lab = at<int32_t>(ws, L.lab);
@@ -1920,11 +1877,11 @@ static int frame_label(const uint32_t *bits, int X, int Y, int Z, int pitch, voi
         long long n_strips = (long long)D.X * spp;
         unsigned sgrid = (unsigned)(n_strips < (long long)mdvc_num_sms() * 32 ? n_strips : (long long)mdvc_num_sms() * 32);
         unsigned lgrid = mdvc_grid(caps->max_runs, 256, 4);
-        k_strip_link<<<sgrid, TILE_THREADS, 0, st>>>(bits, D, h, rowoff, rowpol, runstart, parent, rootlist);
+        k_strip_link<<<sgrid, TILE_THREADS, 0, st>>>(bits, D, h, rowoff, rowpol, runstart, parent, rootlist, rowflag);
         MDVC_LAUNCH_CHECK();
         if (D.Y > STRIP_TY) {
             long long items = (long long)D.X * ((D.Y - 1) / STRIP_TY);
-            k_link_round<<<mdvc_grid(items * 8, 256, 8), 256, 0, st>>>(bits, D, h, rowoff, runstart, parent, 0, STRIP_TY, 1 << 30, 8);
+            k_link_round<<<mdvc_grid(items * 8, 256, 8), 256, 0, st>>>(bits, D, h, rowoff, runstart, parent, 0, STRIP_TY, 1 << 30, 8, rowflag);
             MDVC_LAUNCH_CHECK();
             k_flatten_list<<<lgrid, 256, 0, st>>>(h, rootlist, parent);
             MDVC_LAUNCH_CHECK();
@@ -1932,7 +1889,7 @@ static int frame_label(const uint32_t *bits, int X, int Y, int Z, int pitch, voi
         for (long long s = 1; s < D.X; s *= LINK_RADIX) {
             long long tiles = (long long)((D.X - 1) / s) * spp;
             unsigned tgrid = (unsigned)(tiles < (long long)mdvc_num_sms() * 32 ? tiles : (long long)mdvc_num_sms() * 32);
-            k_tile_link_x<<<tgrid, TILE_THREADS, 0, st>>>(bits, D, h, rowoff, rowpol, runstart, parent, (int)s, LINK_RADIX);
+            k_tile_link_x<<<tgrid, TILE_THREADS, 0, st>>>(bits, D, h, rowoff, rowpol, runstart, parent, (int)s, LINK_RADIX, rowflag);
             MDVC_LAUNCH_CHECK();
             k_flatten_list<<<lgrid, 256, 0, st>>>(h, rootlist, parent);
             MDVC_LAUNCH_CHECK();
@@ -1964,16 +1921,19 @@ extern "C" int mdvc_frame_pairs(const uint32_t *bits, int X, int Y, int Z, int p
     MDVC_CUDA_CHECK(cudaMemsetAsync(cset, 0xff, (size_t)caps->contact_slots * 8, st));
     MDVC_CUDA_CHECK(cudaMemsetAsync(bset, 0xff, (size_t)caps->bridge_slots * 8, st));
     MDVC_CUDA_CHECK(cudaMemsetAsync(&h->n_contacts, 0, 2 * sizeof(uint32_t), st));
-    {
-        long long tiles = (long long)D.X * ((D.Y + PT_TY - 1) / PT_TY);
-        // four CTAs are resident per SM; 16 per SM keeps the tail short while the per-CTA set-up (clearing the two
-        // key caches) is paid four times less often than with one CTA per tile (measured: 0.219 -> 0.198 ms)
-        unsigned tgrid = (unsigned)(tiles < (long long)mdvc_num_sms() * 16 ? tiles : (long long)mdvc_num_sms() * 16);
-        k_tile_pairs<<<tgrid, 2 * PT_TY, 0, st>>>(bits, D, h, at<uint32_t>(ws, L.rowoff), at<uint8_t>(ws, L.rowpol), at<uint32_t>(ws, L.runstart),
-                                            at<int32_t>(ws, L.lab), cset, caps->contact_slots, bset,
-                                            caps->bridge_slots, periodic);
-        MDVC_LAUNCH_CHECK();
-    }
+    MDVC_CUDA_CHECK(cudaMemsetAsync(&h->n_pair_rows, 0, sizeof(uint32_t), st));
+    const int32_t *lab = at<int32_t>(ws, L.lab);
+    const uint32_t *rowoff = at<uint32_t>(ws, L.rowoff);
+    const uint8_t *rowflag = at<uint8_t>(ws, L.rowflag);
+    uint32_t *pairrows = at<uint32_t>(ws, L.pairrows);
+    k_row_pairs<<<mdvc_grid(D.rows + D.rows / 31 + 32, 256, 8), 256, 0, st>>>(D, h, rowoff, rowflag, lab, pairrows, cset,
+                                                                           caps->contact_slots, bset, caps->bridge_slots, periodic);
+    MDVC_LAUNCH_CHECK();
+    // the list is short on smooth grids (CTAs past its end leave at once) and holds every row on noise
+    k_task_pairs<<<mdvc_grid(D.rows * PR_LANES, 256, 8), 256, 0, st>>>(D, h, rowoff, at<uint8_t>(ws, L.rowpol), rowflag, pairrows,
+                                                                       at<uint32_t>(ws, L.runstart), lab, cset, caps->contact_slots,
+                                                                       bset, caps->bridge_slots, periodic);
+    MDVC_LAUNCH_CHECK();
     k_compact_set<<<mdvc_grid(caps->contact_slots, 256, 4), 256, 0, st>>>(cset, caps->contact_slots, ckeys, &h->n_contacts);
     MDVC_LAUNCH_CHECK();
     rc = sort_keys(ckeys, &h->n_contacts, caps->contact_slots, st);

@@ -18,6 +18,8 @@ def main():
     bits0 = dev.BitGrid((n, n, n))
     dev.bin_grid(torch.from_numpy(pos).cuda(), T, invT, nbox, bits0)
     closed = dev.morph(bits0, "de")
+    if "--empty" in sys.argv:                       # one run per row: the dense write with nothing to look up
+        closed.words.zero_()
     plan = dev.FramePlan((n, n, n))
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
     for r in range(reps):
@@ -29,7 +31,8 @@ def main():
         torch.cuda.synchronize()
         h = plan.read_header()
         print(f"[{r}] label {ev[0].elapsed_time(ev[1]) * 1e3:7.1f} us  pairs {ev[1].elapsed_time(ev[2]) * 1e3:7.1f} us  "
-              f"runs {h.total_runs} labels +{h.n_true}/-{h.n_false} contacts {h.n_contacts} bridges {h.n_bridges} flags {h.flags}")
+              f"runs {h.total_runs} labels +{h.n_true}/-{h.n_false} contacts {h.n_contacts} bridges {h.n_bridges} flags {h.flags} "
+              f"pair rows {int(plan.ws[:256].view(torch.int32)[11])}")
     # the dense write alone (components from the device-side periodic merge), labels + components and components only
     plan.components(True)
     labels = torch.empty((n, n, n), dtype=torch.int32, device="cuda")

@@ -1,6 +1,6 @@
 """Per-CUDA-source-line instruction shares from an ncu report (needs -lineinfo + --import-source on).
 
-    python tools/ncu_lines.py report.ncu-rep [top=40]
+    python tools/ncu_lines.py report.ncu-rep [top=40] [kernel name (regex:... allowed)]
 """
 import csv
 import io
@@ -11,7 +11,8 @@ import sys
 def main():
     rep = sys.argv[1]
     top = int(sys.argv[2]) if len(sys.argv) > 2 else 40
-    txt = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass"],
+    only = ["-k", sys.argv[3]] if len(sys.argv) > 3 and not sys.argv[3].startswith("--") else []
+    txt = subprocess.run(["ncu", "-i", rep, *only, "--page", "source", "--csv", "--print-source", "cuda,sass"],
                          capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(txt)))
     hdr = [i for i, r in enumerate(rows) if "Source" in r and "Instructions Executed" in r]
@@ -38,7 +39,11 @@ def main():
             tot += n
             stot += sm
     print(f"warp instructions {tot}, stall samples {stot}")
-    for n, s, ln, src in sorted(items, reverse=True)[:top]:
+    if "--by-samples" in sys.argv:
+        items.sort(key=lambda it: it[1], reverse=True)
+    else:
+        items.sort(reverse=True)
+    for n, s, ln, src in items[:top]:
         print(f"{100 * n / tot:5.1f}% inst {100 * s / max(stot, 1):5.1f}% samp  {ln:>16}  {src}")
 
 
