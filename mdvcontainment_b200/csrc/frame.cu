@@ -1473,6 +1473,63 @@ k_decode_rows(const unsigned long long *__restrict__ keys, const uint32_t *count
     }
 }
 
+// Small sets (the default capacity): compaction, sort and decoding of one set by one CTA -- block 0 the contacts,
+// block 1 the bridges -- instead of three launches per set.
+__global__ void __launch_bounds__(1024)
+k_finish_sets(const unsigned long long *__restrict__ cset, unsigned long long *ckeys, int32_t *__restrict__ crows,
+              uint32_t *n_contacts, uint32_t c_cap, const unsigned long long *__restrict__ bset, unsigned long long *bkeys,
+              int32_t *__restrict__ brows, uint32_t *n_bridges, uint32_t b_cap) {
+    __shared__ unsigned long long sk[SORT_SMEM_KEYS];
+    __shared__ uint32_t s_n;
+    const bool bridges = blockIdx.x == 1;
+    const unsigned long long *set = bridges ? bset : cset;
+    unsigned long long *keys = bridges ? bkeys : ckeys;
+    int32_t *rows = bridges ? brows : crows;
+    const uint32_t cap = bridges ? b_cap : c_cap;
+    if (threadIdx.x == 0) s_n = 0;
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < cap; i += blockDim.x) {
+        const unsigned long long k = set[i];
+        if (k == MDVC_KEY_EMPTY) continue;
+        const uint32_t at = atomicAdd(&s_n, 1u);
+        keys[at] = k;
+        if (at < SORT_SMEM_KEYS) sk[at] = k;
+    }
+    __syncthreads();
+    const uint32_t n = s_n;
+    if (threadIdx.x == 0) *(bridges ? n_bridges : n_contacts) = n;
+    uint32_t P = 1;
+    while (P < n) P <<= 1;
+    const bool in_smem = P <= SORT_SMEM_KEYS;
+    unsigned long long *a = in_smem ? sk : keys;
+    for (uint32_t i = n + threadIdx.x; i < P; i += blockDim.x) a[i] = MDVC_KEY_EMPTY;       // P <= cap (a power of two)
+    __syncthreads();
+    for (uint32_t k = 2; k <= P; k <<= 1) {
+        for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+            for (uint32_t i = threadIdx.x; i < P; i += blockDim.x) {
+                const uint32_t ixj = i ^ j;
+                if (ixj > i) {
+                    const unsigned long long u = a[i], w = a[ixj];
+                    if ((u > w) == ((i & k) == 0)) { a[i] = w; a[ixj] = u; }
+                }
+            }
+            __syncthreads();
+        }
+    }
+    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
+        const unsigned long long key = a[i];
+        if (in_smem) keys[i] = key;
+        int l1, l2, code;
+        mdvc_unpack_key(key, l1, l2, code);
+        if (bridges) {
+            int32_t *o = rows + (size_t)i * 5;
+            o[0] = l1; o[1] = l2; o[2] = code / 9 - 1; o[3] = (code / 3) % 3 - 1; o[4] = code % 3 - 1;
+        } else {
+            rows[2 * (size_t)i] = l1; rows[2 * (size_t)i + 1] = l2;
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------
 // stage 3: periodic components on the device
 // ------------------------------------------------------------------------------------------
@@ -1934,6 +1991,12 @@ extern "C" int mdvc_frame_pairs(const uint32_t *bits, int X, int Y, int Z, int p
                                                                        at<uint32_t>(ws, L.runstart), lab, cset, caps->contact_slots,
                                                                        bset, caps->bridge_slots, periodic);
     MDVC_LAUNCH_CHECK();
+    if (caps->contact_slots <= 4 * BSORT_TILE && caps->bridge_slots <= 4 * BSORT_TILE) {
+        k_finish_sets<<<periodic ? 2 : 1, 1024, 0, st>>>(cset, ckeys, at<int32_t>(ws, L.crows), &h->n_contacts, caps->contact_slots,
+                                                         bset, bkeys, at<int32_t>(ws, L.brows), &h->n_bridges, caps->bridge_slots);
+        MDVC_LAUNCH_CHECK();
+        return MDVC_OK;
+    }
     k_compact_set<<<mdvc_grid(caps->contact_slots, 256, 4), 256, 0, st>>>(cset, caps->contact_slots, ckeys, &h->n_contacts);
     MDVC_LAUNCH_CHECK();
     rc = sort_keys(ckeys, &h->n_contacts, caps->contact_slots, st);

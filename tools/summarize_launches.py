@@ -1,4 +1,7 @@
-"""Summarise an `ncu --metrics gpu__time_duration.sum --csv` launch list: per-kernel count, mean, share."""
+"""Summarise an `ncu --metrics gpu__time_duration.sum --csv` launch list: per-kernel count, mean, share.
+
+    python tools/summarize_launches.py launches.csv [last_frames | --frames A B]
+"""
 import collections
 import csv
 import re
@@ -23,8 +26,13 @@ def load(path):
 
 def main():
     path = sys.argv[1]
-    last_frames = int(sys.argv[2]) if len(sys.argv) > 2 else 0
+    last_frames = int(sys.argv[2]) if len(sys.argv) > 2 and sys.argv[2] != "--frames" else 0
     seq = load(path)
+    if "--frames" in sys.argv:      # --frames A B: frames A..B (1-based, inclusive) only; a frame starts with its binning
+        a, b = (int(v) for v in sys.argv[sys.argv.index("--frames") + 1:][:2])
+        first = "k_bin_bucket" if any(n.startswith("k_bin_bucket") for n, _ in seq) else "k_bin_atoms"
+        idx = [i for i, (n, _) in enumerate(seq) if n.startswith(first)] + [len(seq)]
+        seq = seq[idx[a - 1]:idx[b]]
     if last_frames:      # keep only the launches from the last `last_frames` frames on (a frame starts with its binning)
         first = "k_bin_bucket" if any(n.startswith("k_bin_bucket") for n, _ in seq) else "k_bin_atoms"
         idx = [i for i, (n, _) in enumerate(seq) if n.startswith(first)]
