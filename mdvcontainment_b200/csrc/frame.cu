@@ -1176,89 +1176,132 @@ __device__ __forceinline__ uint32_t pair_relations(const Dims &D, int periodic, 
 //   * contacts between consecutive runs of a row (they always differ in value);
 //   * bridges through the z faces: the last run steps +z into the first runs of the six rows with dx in {0,-1}, the
 //     first run steps -z into the last runs of the three rows with dx = -1 (the reverse of the dx = +1, +z steps), so
-//     only rows at or before this one in raster order are read.
-// The eleven labels of the z-face steps almost always repeat from one row to the next: a row whose labels equal the
-// previous row's (and neither row touches an x or y face, where the shift vectors differ) has nothing new to say.
-// A warp takes 31 consecutive rows; lane 0 holds the row before them, which only seeds the comparison.
+//     only rows at or before this one in raster order are read;
+//   * the list of rows whose run lists have to be compared (k_task_pairs).
+// The eleven labels of a row's z-face steps (first runs of rows y-1..y+1 of both planes, last runs of the other
+// plane's, the row's own first and last) almost always repeat from one row to the next, and a row whose labels equal
+// the previous row's -- neither of them on an x or y face, where the shift vectors differ -- has nothing new to say.
+// Every lane therefore loads the four labels of its own row only (first / last run here and in the plane before);
+// the neighbours' come by shuffle, and "equal to the previous row" is three ballots.  A warp emits for 29 consecutive
+// rows: lanes 0 and 1 hold the two rows before them, lane 31 the row after (comparison only).  Rows on a face take
+// the slow path with explicit, wrapped loads.
 // periodic: 0 none, 1 all axes, 2 y and z only (slab interior: the x faces belong to the caller).
-__global__ void __launch_bounds__(256)
+#define RP_ROWS 29
+#define RP_LIST 1024
+#ifndef RP_MIN_CTAS
+#define RP_MIN_CTAS 5
+#endif
+__global__ void __launch_bounds__(256, RP_MIN_CTAS)
 k_row_pairs(Dims D, Hdr *h, const uint32_t *__restrict__ rowoff, const uint8_t *__restrict__ rowflag,
             const int32_t *__restrict__ lab, uint32_t *__restrict__ pairrows, unsigned long long *cset, uint32_t c_slots,
             unsigned long long *bset, uint32_t b_slots, int periodic) {
     __shared__ BlockSet c_cache, b_cache;
+    __shared__ uint32_t s_list[RP_LIST], s_listed, s_valid, s_base;
     c_cache.clear(); b_cache.clear();
+    if (threadIdx.x == 0) { s_listed = 0; s_valid = RP_LIST; }
     __syncthreads();
     if (h->n_labels == 0) return;
     PairSink cs{&c_cache, cset, c_slots, &h->flags, MDVC_OVERFLOW_CONTACTS, MDVC_KEY_EMPTY, MDVC_KEY_EMPTY};
     PairSink bs{&b_cache, bset, b_slots, &h->flags, MDVC_OVERFLOW_BRIDGES, MDVC_KEY_EMPTY, MDVC_KEY_EMPTY};
     const int lane = threadIdx.x & 31;
     const uint32_t n_rows = (uint32_t)D.rows;                      // < 2^31
-    const uint32_t n_warps = (n_rows + 30u) / 31u, warp_stride = (gridDim.x * blockDim.x) >> 5;
+    const uint32_t n_warps = (n_rows + RP_ROWS - 1) / RP_ROWS, warp_stride = (gridDim.x * blockDim.x) >> 5;
     int c_lo = 0, c_hi = 0, c_lo2 = 0, c_hi2 = 0;                  // the two contact pairs this thread emitted last
     for (uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < n_warps; w += warp_stride) {
-        const uint32_t row = w * 31u + (uint32_t)lane - 1u;        // lane 0 of warp 0: 0xffffffff, not live
-        const bool live = row < n_rows, seed = lane == 0;
+        const uint32_t row = w * RP_ROWS + (uint32_t)lane - 2u;    // lanes 0, 1 of warp 0: wrapped around, not live
+        const bool live = row < n_rows, mine = live && lane >= 2 && lane <= RP_ROWS + 1;
         const int x = live ? (int)(row / (uint32_t)D.Y) : 0, y = live ? (int)(row - (uint32_t)x * (uint32_t)D.Y) : 0;
         const int xo = x == 0 ? D.X - 1 : x - 1, sxo = x == 0 ? -1 : 0;
         const bool other_ok = x != 0 || periodic == 1;
         const uint32_t own0 = (uint32_t)x * D.Y, oth0 = (uint32_t)xo * D.Y;
-        const uint32_t b = live ? rowoff[own0 + y] : 0u, e = live ? rowoff[own0 + y + 1] : 0u;
-        {   // rows with relations to walk -> k_task_pairs' list (one atomic per warp)
-            const uint32_t need = live && !seed ? pair_relations(D, periodic, rowflag, row, x, y) : 0u;
+        const uint32_t b = live ? rowoff[row] : 0u, e = live ? rowoff[row + 1] : 1u;
+        {   // rows with relations to walk -> k_task_pairs' list: gathered per CTA (thousands of warps adding to one
+            // global counter queue up behind each other), straight to the global list only when the buffer is full
+            const uint32_t need = mine ? pair_relations(D, periodic, rowflag, row, x, y) : 0u;
             const unsigned m = __ballot_sync(MDVC_FULL, need != 0);
             if (m) {
+                const uint32_t cnt = (uint32_t)__popc(m), rank = (uint32_t)__popc(m & ((1u << lane) - 1u));
                 uint32_t base = 0;
-                if (lane == 0) base = atomicAdd(&h->n_pair_rows, (uint32_t)__popc(m));
+                if (lane == 0) {
+                    base = atomicAdd(&s_listed, cnt);
+                    if (base + cnt > RP_LIST) {                  // buffer full from `base` on
+                        atomicMin(&s_valid, base);
+                        base = 0x80000000u | atomicAdd(&h->n_pair_rows, cnt);
+                    }
+                }
                 base = __shfl_sync(MDVC_FULL, base, 0);
-                if (need) pairrows[base + __popc(m & ((1u << lane) - 1u))] = row;
-            }
-        }
-        // q 0..2: first runs of the own plane's rows y-1, y, y+1; 3..5: first runs of the other plane's; 6..8: last
-        // runs of the other plane's; 9, 10: this row's first and last run
-        int cur[11], sy3[3];
-        if (periodic) {
-            uint32_t at[9];
-#pragma unroll
-            for (int d = 0; d < 3; ++d) {
-                int yy = y + d - 1;
-                sy3[d] = 0;
-                if (yy < 0) { yy = D.Y - 1; sy3[d] = -1; } else if (yy >= D.Y) { yy = 0; sy3[d] = 1; }
-                at[d] = d == 1 ? b : (live ? rowoff[own0 + yy] : 0u);
-                at[3 + d] = live && other_ok ? rowoff[oth0 + yy] : 0u;
-                at[6 + d] = live && other_ok ? rowoff[oth0 + yy + 1] - 1u : 0u;
-            }
-#pragma unroll
-            for (int q = 0; q < 9; ++q) cur[q] = live && (q < 3 || other_ok) ? lab[at[q]] : 0;
-            cur[9] = cur[1];
-            cur[10] = live ? lab[e - 1] : 0;
-            const bool on_face = y == 0 || y == D.Y - 1 || x == 0;
-            const int up_other = __shfl_up_sync(MDVC_FULL, (int)(on_face || !live), 1);   // every lane shuffles
-            bool same = !on_face && !seed && !up_other;
-#pragma unroll
-            for (int q = 0; q < 11; ++q) {
-                const int up = __shfl_up_sync(MDVC_FULL, cur[q], 1);
-                same = same && cur[q] == up;
-            }
-            if (live && !seed && !same) {
-#pragma unroll
-                for (int q = 0; q < 9; ++q) {
-                    if (q >= 3 && !other_ok) break;
-                    emit_bridge(bs, q < 6 ? cur[10] : cur[9], cur[q], q < 3 ? 0 : sxo, sy3[q % 3], q < 6 ? 1 : -1);
+                if (need) {
+                    if (base & 0x80000000u) pairrows[(base & 0x7fffffffu) + rank] = row;
+                    else s_list[base + rank] = row;
                 }
             }
         }
-        if (live && !seed) {
-            int before = periodic ? cur[9] : lab[b];
-            for (uint32_t k = b + 1; k < e; ++k) {
-                const int now = lab[k];
-                const int lo = min(before, now), hi = max(before, now);
-                before = now;
-                if ((lo == c_lo && hi == c_hi) || (lo == c_lo2 && hi == c_hi2) || lo == hi) continue;
-                c_lo2 = c_lo; c_hi2 = c_hi; c_lo = lo; c_hi = hi;
-                cs.put(mdvc_pack_key(lo, hi, 0));
+        const int first = live ? lab[b] : 0;
+        if (periodic) {
+            const bool face = y == 0 || y == D.Y - 1 || x == 0;
+            const bool ld_o = live && other_ok;
+            const uint32_t ob = ld_o ? rowoff[oth0 + y] : 0u, oe = ld_o ? rowoff[oth0 + y + 1] : 1u;
+            const int last = live ? lab[e - 1] : 0, ofirst = ld_o ? lab[ob] : 0, olast = ld_o ? lab[oe - 1] : 0;
+            // the rows before (m) and after (p) this one, valid when this row is not on a face
+            const int f_m = __shfl_up_sync(MDVC_FULL, first, 1), f_p = __shfl_down_sync(MDVC_FULL, first, 1);
+            const int of_m = __shfl_up_sync(MDVC_FULL, ofirst, 1), of_p = __shfl_down_sync(MDVC_FULL, ofirst, 1);
+            const int ol_m = __shfl_up_sync(MDVC_FULL, olast, 1), ol_p = __shfl_down_sync(MDVC_FULL, olast, 1);
+            const int l_m = __shfl_up_sync(MDVC_FULL, last, 1);
+            const unsigned eq3 = __ballot_sync(MDVC_FULL, first == f_m && ofirst == of_m && olast == ol_m);
+            const unsigned eqw = __ballot_sync(MDVC_FULL, last == l_m);
+            const unsigned inner = __ballot_sync(MDVC_FULL, live && !face);
+            // equal to the previous row <=> rows y-2..y+1 agree on the three neighbour labels, rows y-1, y on the last
+            const unsigned span = lane ? 7u << (lane - 1) : 0u;    // bits lane-1, lane, lane+1 (used by lanes 2..30)
+            const bool same = mine && (inner >> lane & 1u) && (inner >> (lane - 1) & 1u) && (eq3 & span) == span &&
+                              (eqw >> lane & 1u);
+            if (mine && !same) {
+                int cur[9], sy3[3] = {0, 0, 0};
+                if (!face) {
+                    cur[0] = f_m; cur[1] = first; cur[2] = f_p;
+                    cur[3] = of_m; cur[4] = ofirst; cur[5] = of_p;
+                    cur[6] = ol_m; cur[7] = olast; cur[8] = ol_p;
+                } else {
+#pragma unroll
+                    for (int d = 0; d < 3; ++d) {
+                        int yy = y + d - 1;
+                        if (yy < 0) { yy = D.Y - 1; sy3[d] = -1; } else if (yy >= D.Y) { yy = 0; sy3[d] = 1; }
+                        cur[d] = lab[rowoff[own0 + yy]];
+                        cur[3 + d] = other_ok ? lab[rowoff[oth0 + yy]] : 0;
+                        cur[6 + d] = other_ok ? lab[rowoff[oth0 + yy + 1] - 1u] : 0;
+                    }
+                }
+                // q 0..2: +z into the first runs of the own plane's rows y-1, y, y+1; 3..5: of the other plane's;
+                // 6..8: -z into the last runs of the other plane's
+#pragma unroll
+                for (int q = 0; q < 9; ++q) {
+                    if (q >= 3 && !other_ok) break;
+                    emit_bridge(bs, q < 6 ? last : first, cur[q], q < 3 ? 0 : sxo, sy3[q % 3], q < 6 ? 1 : -1);
+                }
+            }
+        }
+        if (mine) {
+            int before = first;
+            for (uint32_t k0 = b + 1; k0 < e; k0 += 4) {           // four labels in flight (the loop is load latency)
+                int now[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) now[u] = k0 + u < e ? lab[k0 + u] : 0;
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    if (k0 + u >= e) break;
+                    const int lo = min(before, now[u]), hi = max(before, now[u]);
+                    before = now[u];
+                    if ((lo == c_lo && hi == c_hi) || (lo == c_lo2 && hi == c_hi2) || lo == hi) continue;
+                    c_lo2 = c_lo; c_hi2 = c_hi; c_lo = lo; c_hi = hi;
+                    cs.put(mdvc_pack_key(lo, hi, 0));
+                }
             }
         }
     }
+    __syncthreads();
+    const uint32_t n_listed = min(s_listed, s_valid);              // reservations that did not fit went to the global list
+    if (threadIdx.x == 0 && n_listed) s_base = atomicAdd(&h->n_pair_rows, n_listed);
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < n_listed; i += blockDim.x) pairrows[s_base + i] = s_list[i];
     cs.flush();
     bs.flush();
 }
@@ -1983,7 +2026,7 @@ extern "C" int mdvc_frame_pairs(const uint32_t *bits, int X, int Y, int Z, int p
     const uint32_t *rowoff = at<uint32_t>(ws, L.rowoff);
     const uint8_t *rowflag = at<uint8_t>(ws, L.rowflag);
     uint32_t *pairrows = at<uint32_t>(ws, L.pairrows);
-    k_row_pairs<<<mdvc_grid(D.rows + D.rows / 31 + 32, 256, 8), 256, 0, st>>>(D, h, rowoff, rowflag, lab, pairrows, cset,
+    k_row_pairs<<<mdvc_grid(D.rows + D.rows / RP_ROWS * 3 + 32, 256, RP_MIN_CTAS), 256, 0, st>>>(D, h, rowoff, rowflag, lab, pairrows, cset,
                                                                            caps->contact_slots, bset, caps->bridge_slots, periodic);
     MDVC_LAUNCH_CHECK();
     // the list is short on smooth grids (CTAs past its end leave at once) and holds every row on noise

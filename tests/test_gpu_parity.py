@@ -320,6 +320,55 @@ def test_frame_random_shapes_vs_oracle(dev):
         assert gb.shape == wb.shape and np.array_equal(gb, wb), g.shape
 
 
+def smooth_grid(shape, seed, n_blobs=9, noise=0.0):
+    """Union of random periodic ellipsoids and slabs: most neighbouring rows mirror each other (the case the link
+    kernels flag as 'nothing for the pair stage to compare'), a few do not, some structures cross the box faces."""
+    rng = np.random.default_rng(seed)
+    X, Y, Z = shape
+    ax = np.meshgrid(np.arange(X), np.arange(Y), np.arange(Z), indexing="ij")
+    g = np.zeros(shape, bool)
+    for _ in range(n_blobs):
+        c = rng.random(3) * shape
+        r = (0.08 + 0.22 * rng.random(3)) * np.array(shape)
+        d = [np.minimum(np.abs(a - ci), n - np.abs(a - ci)) / ri for a, ci, ri, n in zip(ax, c, r, shape)]
+        blob = d[0] ** 2 + d[1] ** 2 + d[2] ** 2 < 1.0
+        if rng.random() < 0.35:                               # hollow: shells give rows with 5 runs
+            blob &= d[0] ** 2 + d[1] ** 2 + d[2] ** 2 > 0.45
+        g |= blob
+    k = int(rng.choice([i for i in range(3) if shape[i] > 8]))    # one slab through a pair of faces
+    sl = [slice(None)] * 3
+    lo = int(rng.integers(0, shape[k]))
+    sl[k] = slice(lo, lo + max(2, shape[k] // 9))
+    g[tuple(sl)] = True
+    if noise:
+        g ^= rng.random(shape) < noise
+    return g
+
+
+@pytest.mark.parametrize("shape,seed,noise", [((40, 150, 96), 1, 0.0), ((70, 67, 130), 2, 0.0), ((35, 130, 64), 3, 2e-4),
+                                              ((1, 200, 90), 4, 0.0), ((66, 1, 70), 5, 0.0), ((34, 129, 33), 6, 1e-3)])
+@pytest.mark.parametrize("periodic", [True, False])
+def test_frame_smooth_structures_vs_oracle(dev, shape, seed, noise, periodic):
+    """Grids of mostly mirrored rows: more than one 64-row strip per plane, more than 32 planes (both link rounds),
+    structures through the periodic faces, degenerate extents."""
+    g = smooth_grid(shape, seed, noise=noise)
+    bits, plan, h, labels = run_frame(dev, g, periodic=periodic)
+    want = vo.label_3d_grid(g).astype(np.int32)
+    assert np.array_equal(labels.cpu().numpy(), want)
+    assert np.array_equal(plan.contacts(), vo.find_label_contacts_c(want))
+    if periodic:
+        wb = vo.find_bridges_c(want)
+        gb = plan.bridges()
+        assert gb.shape == wb.shape and np.array_equal(gb, wb)
+        # the row list of the pair stage is short on such grids: the flags do skip
+        n_listed = int(plan.ws[:256].view(torch.int32)[11])
+        assert 0 < n_listed <= shape[0] * shape[1]
+        if noise == 0.0 and min(shape[:2]) > 8:
+            assert n_listed < 0.6 * shape[0] * shape[1]
+    else:
+        assert h.n_bridges == 0
+
+
 def test_frame_slab_mode_skips_bridges(dev):
     g = CASES["complex3D_roll11"]["grid"]
     bits, plan, h, labels = run_frame(dev, g, periodic=False)
