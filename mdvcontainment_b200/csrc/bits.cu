@@ -8,6 +8,8 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
+
 // ------------------------------------------------------------------------------------------
 // error state
 // ------------------------------------------------------------------------------------------
@@ -125,7 +127,8 @@ struct BinParams {
     long long nbox[9];
     int nbox32[9];       // the same matrix when every entry fits (fits32), for the all-32-bit fast path
     int fits32;
-    float Tf[9], Taf[9]; // T and |T| rounded to float32: the certified single-precision floor of bin_floor_f32
+    float Tf[9];         // T rounded to float32: the certified single-precision floor of bin_floor_f32
+    float Tcol[3];       // column sums |T0j| + |T1j| + |T2j| (float32, rounded up)
 };
 
 // Python floor division a // b for b > 0.  Atoms are almost always inside the box or one image away, so
@@ -206,17 +209,18 @@ __device__ __forceinline__ bool bin_one_atom(float x, float y, float z, const Bi
 // a voxel face, and for those the same floor follows from float32 arithmetic: with a = |p0 T0j| + |p1 T1j| + |p2 T2j|
 // the float32 chain differs from the exact value by less than 4 * 2^-24 * a (one rounding of T, one per product / sum),
 // and the float64 chain by ~1e-13, so a float32 result whose distance to the nearest integer exceeds 1e-6 * a (4x the
-// bound) has the reference's floor.  Anything closer -- beads ON a face, as coordinates rounded to 0.01 A often are,
-// huge coordinates, NaNs -- returns false and takes the float64 path.  ~20 instructions instead of ~190 per bead.
+// bound) has the reference's floor.  a is bounded from above by max|p_i| * (|T0j| + |T1j| + |T2j|), one multiplication
+// per column instead of three (the looser bound leaves a few more beads undecided, which is safe).  Anything closer --
+// beads ON a face, as coordinates rounded to 0.01 A often are, huge coordinates, NaNs -- returns false and takes the
+// float64 path.  ~12 instructions per column instead of ~60.
 __device__ __forceinline__ bool bin_floor_f32(float x, float y, float z, const BinParams &P, int (&u)[3]) {
-    const float ax = fabsf(x), ay = fabsf(y), az = fabsf(z);
-    bool sure = true;
+    const float m = fmaxf(fmaxf(fabsf(x), fabsf(y)), fabsf(z));
+    bool sure = m < 1e5f;                                         // false for NaNs too
 #pragma unroll
     for (int j = 0; j < 3; ++j) {
         const float f = fmaf(z, P.Tf[6 + j], fmaf(y, P.Tf[3 + j], x * P.Tf[j]));
-        const float a = fmaf(az, P.Taf[6 + j], fmaf(ay, P.Taf[3 + j], ax * P.Taf[j]));
-        const float fl = floorf(f), frac = f - fl, eps = fmaf(a, 1e-6f, 1e-30f);
-        sure = sure && frac >= eps && frac <= 1.0f - eps && a < 1e5f;
+        const float fl = floorf(f), frac = f - fl, eps = fmaf(m, P.Tcol[j] * 1e-6f, 1e-30f);
+        sure = sure && frac >= eps && frac <= 1.0f - eps && P.Tcol[j] * m < 1e5f;
         u[j] = (int)fl;
     }
     return sure;
@@ -224,6 +228,9 @@ __device__ __forceinline__ bool bin_floor_f32(float x, float y, float z, const B
 
 // triclinic-aware wrap of floored voxel coordinates (dims 2, 1, 0; Python floor division), 32-bit
 __device__ __forceinline__ bool bin_wrap32(const BinParams &P, int (&w3)[3]) {
+    // already inside the box (nearly every bead): each of the three steps below would shift by zero
+    if ((unsigned)w3[0] < (unsigned)P.nbox32[0] && (unsigned)w3[1] < (unsigned)P.nbox32[4] && (unsigned)w3[2] < (unsigned)P.nbox32[8])
+        return true;
 #pragma unroll
     for (int dim = 2; dim >= 0; --dim) {
         const int nn = P.nbox32[4 * dim], a = w3[dim];
@@ -312,8 +319,9 @@ static void bin_params(BinParams &P, const double *T_host, const double *invT_ho
         if (nbox_host[k] <= -(1ll << 28) || nbox_host[k] >= (1ll << 28)) P.fits32 = 0;
         P.nbox32[k] = (int)nbox_host[k];
         P.Tf[k] = (float)T_host[k];
-        P.Taf[k] = fabsf(P.Tf[k]);
     }
+    for (int j = 0; j < 3; ++j)
+        P.Tcol[j] = nextafterf((fabsf(P.Tf[j]) + fabsf(P.Tf[3 + j]) + fabsf(P.Tf[6 + j])) * 1.000001f, INFINITY);
 }
 
 extern "C" int mdvc_bin_atoms(const float *pos, long long n, const double *T_host, const double *invT_host,
@@ -340,54 +348,78 @@ extern "C" int mdvc_bin_atoms(const float *pos, long long n, const double *T_hos
     return MDVC_OK;
 }
 
-// ------------------------------------------------------------------------------------------
-// A1  binning into a freshly cleared grid, x-chunk by x-chunk
-// ------------------------------------------------------------------------------------------
-// The plain kernels above fire one RED.OR per bead at a grid that does not fit the L2 (128 MiB at 1024^3) in an
-// order that has nothing to do with the grid: every RED is a read-modify-write of a random 32-byte DRAM sector
-// (ncu: 475 MB of DRAM traffic + the 128 MB memset for 122 MB of coordinates, and the kernel's whole duration
-// comes straight off the frame time because that scattered traffic shares the DRAM with the dense write).
-// Here the beads are first dropped into at most BIN_CHUNKS buckets by x-plane range (a per-CTA count in shared
-// memory, one global atomicAdd per CTA and bucket to reserve a contiguous stretch, keys written next to each other),
-// then the grid is cleared and filled one plane range at a time: a range is 16 MiB at 1024^3, so its clearing stores
-// and its REDs meet in the L2 and every line goes to DRAM once.  DRAM traffic: coordinates read once, 4 B/bead of keys
-// (L2-resident), grid written once.
-#ifndef BIN_CHUNKS
-#define BIN_CHUNKS 8
-#endif
-#define BIN_TILE_ATOMS 2048                  // 256 threads x 8 beads per iteration
+// the REDs of one key list (the spill list of mdvc_bin_grid): count read from device memory
+__global__ void __launch_bounds__(256)
+k_bin_keys(const uint32_t *__restrict__ keys, const uint32_t *__restrict__ count_ptr, uint32_t cap, uint32_t *__restrict__ occ) {
+    const uint32_t n = min(*count_ptr, cap);
+    const uint32_t stride = gridDim.x * blockDim.x;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const uint32_t k = __ldcs(keys + i);
+        atomicOr(&occ[k >> 5], 1u << (k & 31));
+    }
+}
 
-struct BinBuckets {
-    uint32_t *cursor;        // [BIN_CHUNKS] beads offered to each bucket (may exceed cap), [BIN_CHUNKS] = spill count
-    uint32_t *keys;          // [BIN_CHUNKS][cap] then the spill list [n]
-    uint32_t cap;
-    int px_shift;            // bucket = x >> px_shift
-    uint32_t row_bits;       // pitch * 32: key = row * row_bits + z  (word = key >> 5, bit = key & 31)
+// ------------------------------------------------------------------------------------------
+// A1  binning into a fresh grid, slab by slab in shared memory (the default path of mdvc_bin_grid)
+// ------------------------------------------------------------------------------------------
+// The bit grid is cut into slabs of 2^slab_shift bits (64 KiB of consecutive words at 1024^3: half an x-plane), small
+// enough to be built in shared memory.  k_bin_sort drops every bead's key (= its bit index in the padded grid) into the
+// key list of its slab; k_bin_fill, one CTA per slab, clears the slab in shared memory, ORs the listed beads in with
+// shared-memory atomics and writes the finished words once with 16-byte stores.  No memset of the grid, no atomics on
+// global memory outside the few that reserve list space, DRAM traffic = coordinates read once + grid written once
+// (+ 4 B/bead of keys that stay in the L2).
+// k_bin_sort works on tiles of BIN_TILE beads: keys and a per-slab count in shared memory (the shared atomicAdd also
+// hands each key its rank inside the tile's share of the slab), an exclusive scan of the counts, ONE global atomicAdd per
+// tile and non-empty slab to reserve a contiguous stretch of the slab's list, a counting sort of the keys inside shared
+// memory, and a write-out in sorted order, so that neighbouring threads store neighbouring words.  A list that is full
+// (very uneven systems: every list holds 3x the average) spills into a common list that k_bin_keys ORs into the finished
+// grid afterwards.
+#define BIN_TILE 8192                        // beads per tile
+#define BIN_THREADS 512                      // 4 groups of four beads per thread and tile
+#define BIN_MAX_SLABS 2048
+#define BIN_KEY_NONE 0xffffffffu             // no bit index reaches this: the padded grid has fewer than 2^32 bits
+
+struct BinSlabs {
+    uint32_t *cursor;        // [BIN_MAX_SLABS] beads offered to each slab's list (may exceed cap), [BIN_MAX_SLABS] = spill count
+    uint32_t *keys;          // [n_slabs][cap], then the spill list [n]
+    uint32_t cap, n_slabs;
+    int slab_shift;          // slab = key >> slab_shift
+    uint32_t row_bits;       // pitch * 32: key = row * row_bits + z
 };
 
+static size_t bin_sort_smem() { return (2 * BIN_TILE + 2 * BIN_MAX_SLABS) * sizeof(uint32_t) + BIN_TILE * sizeof(unsigned short); }
+
 // FAST (occupancy only, 32-bit box): the certified float32 floor decides almost every bead; the few it cannot decide
-// (on or next to a voxel face) are queued in shared memory and redone in float64 by the first threads of the CTA --
-// densely, not as a divergent branch that a third of all warps would have to sit through -- and go to the spill list.
+// (on or next to a voxel face) are queued in shared memory and redone in float64, one per thread -- densely, not as a
+// divergent branch that a third of all warps would have to sit through -- before the counts are scanned.
 template <bool FAST>
-__global__ void __launch_bounds__(256, FAST ? 5 : 3)
-k_bin_bucket(const float *__restrict__ pos, long long n, BinParams P, BinBuckets B, int32_t *__restrict__ vox_out, float *pos_out) {
-    __shared__ uint32_t s_cnt[BIN_CHUNKS], s_base[BIN_CHUNKS];
-    __shared__ uint32_t s_nslow;
-    __shared__ unsigned short s_slow[FAST ? BIN_TILE_ATOMS : 1];
-    const long long n4 = n >> 2;                                  // groups of four beads (three float4)
-    const long long tile_groups = BIN_TILE_ATOMS / 4;
-    const long long n_tiles = (n4 + tile_groups - 1) / tile_groups;
-    const uint32_t Y = (uint32_t)P.nbox[4];
+__global__ void __launch_bounds__(BIN_THREADS, FAST ? 2 : 1)
+k_bin_sort(const float *__restrict__ pos, long long n, BinParams P, BinSlabs B, int tile_groups, int32_t *__restrict__ vox_out,
+           float *pos_out) {
+    extern __shared__ __align__(16) uint32_t s_dyn[];
+    uint32_t *s_key = s_dyn;                                      // [BIN_TILE] key of bead (k, group) at k * BIN_TILE/4 + group
+    uint32_t *s_sorted = s_key + BIN_TILE;                        // [BIN_TILE] the tile's keys grouped by slab
+    uint32_t *s_cnt = s_sorted + BIN_TILE;                        // [BIN_MAX_SLABS] beads per slab, then list offset - s_off
+    uint32_t *s_off = s_cnt + BIN_MAX_SLABS;                      // [BIN_MAX_SLABS] exclusive scan of the counts
+    unsigned short *s_slot = reinterpret_cast<unsigned short *>(s_off + BIN_MAX_SLABS);   // [BIN_TILE] rank inside (tile, slab)
+    unsigned short *s_slow = reinterpret_cast<unsigned short *>(s_sorted);                // undecided beads (dead before s_sorted is written)
+    __shared__ uint32_t s_nslow, s_total, s_wsum[BIN_THREADS / 32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int TG = BIN_TILE / 4;                                  // at most this many groups of four beads (three float4) per tile
+    const long long n4 = n >> 2;
+    const long long n_tiles = (n4 + tile_groups - 1) / tile_groups;   // tile_groups <= TG: tiles sized so that every CTA gets the same number
+    const uint32_t Y = (uint32_t)P.nbox32[4];
     for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        if (threadIdx.x < BIN_CHUNKS) s_cnt[threadIdx.x] = 0;
-        if (threadIdx.x == 0) s_nslow = 0;
+        reinterpret_cast<uint4 *>(s_cnt)[tid] = make_uint4(0u, 0u, 0u, 0u);          // BIN_THREADS * 4 == BIN_MAX_SLABS
+        if (tid == 0) s_nslow = 0;
         __syncthreads();
-        uint32_t key[8], slot[8];
-        int bucket[8];
-#pragma unroll
-        for (int half = 0; half < 2; ++half) {
-            const long long g = tile * tile_groups + half * 256 + threadIdx.x;
-            if (g < n4) {
+        // ---- keys, counts and ranks
+#pragma unroll 2
+        for (int it = 0; it < TG / BIN_THREADS; ++it) {
+            const int gl = it * BIN_THREADS + tid;
+            const long long g = tile * tile_groups + gl;
+            uint32_t key[4] = {BIN_KEY_NONE, BIN_KEY_NONE, BIN_KEY_NONE, BIN_KEY_NONE};
+            if (gl < tile_groups && g < n4) {
                 const float4 *src = reinterpret_cast<const float4 *>(pos) + 3 * g;
                 const float4 q0 = __ldcs(src), q1 = __ldcs(src + 1), q2 = __ldcs(src + 2);
                 const float f[12] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w};
@@ -395,14 +427,10 @@ k_bin_bucket(const float *__restrict__ pos, long long n, BinParams P, BinBuckets
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
                         int vk[3];
-                        bucket[4 * half + k] = -1;
                         if (bin_floor_f32(f[3 * k], f[3 * k + 1], f[3 * k + 2], P, vk)) {
-                            if (bin_wrap32(P, vk)) {
-                                bucket[4 * half + k] = vk[0] >> B.px_shift;
-                                key[4 * half + k] = ((uint32_t)vk[0] * Y + (uint32_t)vk[1]) * B.row_bits + (uint32_t)vk[2];
-                            }
+                            if (bin_wrap32(P, vk)) key[k] = ((uint32_t)vk[0] * Y + (uint32_t)vk[1]) * B.row_bits + (uint32_t)vk[2];
                         } else {
-                            s_slow[atomicAdd(&s_nslow, 1u)] = (unsigned short)((half * 256 + threadIdx.x) * 4 + k);
+                            s_slow[atomicAdd(&s_nslow, 1u)] = (unsigned short)(gl * 4 + k);
                         }
                     }
                 } else {
@@ -415,8 +443,7 @@ k_bin_bucket(const float *__restrict__ pos, long long n, BinParams P, BinBuckets
                         const bool inside = bin_one_atom(f[3 * k], f[3 * k + 1], f[3 * k + 2], P, pos_out != nullptr, vk, wk);
 #pragma unroll
                         for (int j = 0; j < 3; ++j) { v[3 * k + j] = vk[j]; w[3 * k + j] = wk[j]; }
-                        bucket[4 * half + k] = inside ? (vk[0] >> B.px_shift) : -1;
-                        key[4 * half + k] = ((uint32_t)vk[0] * Y + (uint32_t)vk[1]) * B.row_bits + (uint32_t)vk[2];
+                        if (inside) key[k] = ((uint32_t)vk[0] * Y + (uint32_t)vk[1]) * B.row_bits + (uint32_t)vk[2];
                     }
                     if (vox_out) {
                         int4 *dst = reinterpret_cast<int4 *>(vox_out) + 3 * g;
@@ -431,54 +458,125 @@ k_bin_bucket(const float *__restrict__ pos, long long n, BinParams P, BinBuckets
                         dst[2] = make_float4(w[8], w[9], w[10], w[11]);
                     }
                 }
-            } else {
+            }
 #pragma unroll
-                for (int k = 0; k < 4; ++k) bucket[4 * half + k] = -1;
+            for (int k = 0; k < 4; ++k) {
+                s_key[k * TG + gl] = key[k];
+                if (key[k] != BIN_KEY_NONE) s_slot[k * TG + gl] = (unsigned short)atomicAdd(&s_cnt[key[k] >> B.slab_shift], 1u);
             }
         }
-#pragma unroll
-        for (int k = 0; k < 8; ++k)
-            if (bucket[k] >= 0) slot[k] = atomicAdd(&s_cnt[bucket[k]], 1u);
-        __syncthreads();
-        if (threadIdx.x < BIN_CHUNKS) s_base[threadIdx.x] = s_cnt[threadIdx.x] ? atomicAdd(&B.cursor[threadIdx.x], s_cnt[threadIdx.x]) : 0u;
         if (FAST) {
-            // the undecided beads again, in float64, one per thread; they join the spill list
-            for (uint32_t i = threadIdx.x; i < s_nslow; i += blockDim.x) {
-                const long long atom = tile * BIN_TILE_ATOMS + s_slow[i];
+            __syncthreads();
+            for (uint32_t i = tid; i < s_nslow; i += BIN_THREADS) {
+                const uint32_t nat = s_slow[i];                   // bead number inside the tile
+                const long long atom = tile * tile_groups * 4 + nat;
                 int vk[3];
                 float wk[3];
-                if (bin_one_atom(pos[3 * atom], pos[3 * atom + 1], pos[3 * atom + 2], P, false, vk, wk))
-                    B.keys[(size_t)BIN_CHUNKS * B.cap + atomicAdd(&B.cursor[BIN_CHUNKS], 1u)] =
-                        ((uint32_t)vk[0] * Y + (uint32_t)vk[1]) * B.row_bits + (uint32_t)vk[2];
+                if (bin_one_atom(pos[3 * atom], pos[3 * atom + 1], pos[3 * atom + 2], P, false, vk, wk)) {
+                    const uint32_t key = ((uint32_t)vk[0] * Y + (uint32_t)vk[1]) * B.row_bits + (uint32_t)vk[2];
+                    const uint32_t at = (nat & 3u) * TG + (nat >> 2);
+                    s_key[at] = key;
+                    s_slot[at] = (unsigned short)atomicAdd(&s_cnt[key >> B.slab_shift], 1u);
+                }
             }
         }
         __syncthreads();
+        // ---- exclusive scan of the counts (four slabs per thread); list space reserved per (tile, slab)
+        {
+            const uint4 c = reinterpret_cast<const uint4 *>(s_cnt)[tid];
+            const uint32_t mine = c.x + c.y + c.z + c.w;
+            uint32_t incl = mine;
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            if (bucket[k] < 0) continue;
-            const uint32_t at = s_base[bucket[k]] + slot[k];
-            if (at < B.cap) B.keys[(size_t)bucket[k] * B.cap + at] = key[k];
-            else B.keys[(size_t)BIN_CHUNKS * B.cap + atomicAdd(&B.cursor[BIN_CHUNKS], 1u)] = key[k];   // bucket full: spill list
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t up = __shfl_up_sync(MDVC_FULL, incl, d);
+                if (lane >= d) incl += up;
+            }
+            if (lane == 31) s_wsum[warp] = incl;
+            __syncthreads();
+            if (warp == 0) {
+                const uint32_t ws = lane < BIN_THREADS / 32 ? s_wsum[lane] : 0u;
+                uint32_t wi = ws;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const uint32_t up = __shfl_up_sync(MDVC_FULL, wi, d);
+                    if (lane >= d) wi += up;
+                }
+                if (lane < BIN_THREADS / 32) s_wsum[lane] = wi - ws;
+                if (lane == BIN_THREADS / 32 - 1) s_total = wi;
+            }
+            __syncthreads();
+            uint4 o;
+            o.x = s_wsum[warp] + incl - mine;
+            o.y = o.x + c.x;
+            o.z = o.y + c.y;
+            o.w = o.z + c.z;
+            reinterpret_cast<uint4 *>(s_off)[tid] = o;
+            uint4 b;                                              // reserved list offset minus the tile-local offset
+            b.x = (c.x ? atomicAdd(&B.cursor[4 * tid], c.x) : 0u) - o.x;
+            b.y = (c.y ? atomicAdd(&B.cursor[4 * tid + 1], c.y) : 0u) - o.y;
+            b.z = (c.z ? atomicAdd(&B.cursor[4 * tid + 2], c.z) : 0u) - o.z;
+            b.w = (c.w ? atomicAdd(&B.cursor[4 * tid + 3], c.w) : 0u) - o.w;
+            reinterpret_cast<uint4 *>(s_cnt)[tid] = b;
         }
-        __syncthreads();                                          // s_base / s_slow are reused by the next tile
+        __syncthreads();
+        // ---- counting sort inside shared memory
+#pragma unroll 4
+        for (int i = tid; i < BIN_TILE; i += BIN_THREADS) {
+            const uint32_t k = s_key[i];
+            if (k != BIN_KEY_NONE) s_sorted[s_off[k >> B.slab_shift] + s_slot[i]] = k;
+        }
+        __syncthreads();
+        // ---- write-out: position j of the sorted tile is entry j - s_off[slab] of this tile's stretch of the slab's list
+        const uint32_t total = s_total;
+#pragma unroll 4
+        for (uint32_t j = tid; j < total; j += BIN_THREADS) {
+            const uint32_t k = s_sorted[j], slab = k >> B.slab_shift;
+            const uint32_t at = s_cnt[slab] + j;
+            if (at < B.cap) B.keys[(size_t)slab * B.cap + at] = k;
+            else B.keys[(size_t)B.n_slabs * B.cap + atomicAdd(&B.cursor[BIN_MAX_SLABS], 1u)] = k;   // list full: spill
+        }
+        __syncthreads();                                          // every array is reused by the next tile
     }
 }
 
-// the REDs of one key list (a bucket, or the spill list): count read from device memory
-__global__ void __launch_bounds__(256)
-k_bin_keys(const uint32_t *__restrict__ keys, const uint32_t *__restrict__ count_ptr, uint32_t cap, uint32_t *__restrict__ occ) {
-    const uint32_t n = min(*count_ptr, cap);
-    const uint32_t stride = gridDim.x * blockDim.x;
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-        const uint32_t k = __ldcs(keys + i);
-        atomicOr(&occ[k >> 5], 1u << (k & 31));
+// One CTA per slab: clear it in shared memory, OR the listed beads in, write the words once.
+__global__ void __launch_bounds__(BIN_THREADS)
+k_bin_fill(BinSlabs B, uint32_t *__restrict__ occ, unsigned long long grid_words) {
+    extern __shared__ __align__(16) uint32_t s_bits[];
+    const uint32_t slab_words = 1u << (B.slab_shift - 5), mask = (1u << B.slab_shift) - 1u;
+    const int tid = threadIdx.x;
+    for (uint32_t slab = blockIdx.x; slab < B.n_slabs; slab += gridDim.x) {
+        for (uint32_t w = tid; w < slab_words / 4; w += BIN_THREADS) reinterpret_cast<uint4 *>(s_bits)[w] = make_uint4(0u, 0u, 0u, 0u);
+        __syncthreads();
+        const uint32_t cnt = min(__ldcg(B.cursor + slab), B.cap);
+        const uint32_t *__restrict__ keys = B.keys + (size_t)slab * B.cap;
+        uint32_t i = tid;
+        for (; i + 3 * BIN_THREADS < cnt; i += 4 * BIN_THREADS) {          // four loads in flight per thread
+            const uint32_t k0 = __ldcs(keys + i), k1 = __ldcs(keys + i + BIN_THREADS), k2 = __ldcs(keys + i + 2 * BIN_THREADS),
+                           k3 = __ldcs(keys + i + 3 * BIN_THREADS);
+            atomicOr(&s_bits[(k0 & mask) >> 5], 1u << (k0 & 31));
+            atomicOr(&s_bits[(k1 & mask) >> 5], 1u << (k1 & 31));
+            atomicOr(&s_bits[(k2 & mask) >> 5], 1u << (k2 & 31));
+            atomicOr(&s_bits[(k3 & mask) >> 5], 1u << (k3 & 31));
+        }
+        for (; i < cnt; i += BIN_THREADS) {
+            const uint32_t k = __ldcs(keys + i);
+            atomicOr(&s_bits[(k & mask) >> 5], 1u << (k & 31));
+        }
+        __syncthreads();
+        const unsigned long long w0 = (unsigned long long)slab * slab_words;
+        const unsigned long long left = grid_words - w0;                   // > 0: n_slabs = ceil(grid_words / slab_words)
+        const uint32_t nq = (uint32_t)((left < slab_words ? left : slab_words) / 4);   // pitch is a multiple of 4 words
+        uint4 *dst = reinterpret_cast<uint4 *>(occ + w0);
+        for (uint32_t w = tid; w < nq; w += BIN_THREADS) dst[w] = reinterpret_cast<const uint4 *>(s_bits)[w];
+        __syncthreads();
     }
 }
 
 extern "C" size_t mdvc_bin_scratch_bytes(long long n) {
     if (n < 0) return 0;
-    const size_t cap = (((size_t)n * 2 / BIN_CHUNKS + 3) & ~(size_t)3) + 1024;
-    return (64 + BIN_CHUNKS * cap + (size_t)n) * sizeof(uint32_t);
+    // counters, the slab lists (3x the average each + 256) and the spill list
+    return (2 * BIN_MAX_SLABS + 3 * (size_t)n + 260 * (size_t)BIN_MAX_SLABS + (size_t)n) * sizeof(uint32_t);
 }
 
 extern "C" int mdvc_bin_grid(const float *pos, long long n, const double *T_host, const double *invT_host,
@@ -493,36 +591,49 @@ extern "C" int mdvc_bin_grid(const float *pos, long long n, const double *T_host
     const uintptr_t ptrs = (uintptr_t)pos | (uintptr_t)vox_out | (uintptr_t)pos_out;
     // small inputs, unaligned arrays, grids whose padded bit count does not fit 32 bits or a missing / short scratch:
     // clear everything and take the plain kernels
-    if (n < 4 * BIN_TILE_ATOMS || (ptrs & 15) != 0 || grid_bits >= (1ull << 32) || !scratch ||
-        scratch_bytes < mdvc_bin_scratch_bytes(n) || ((uintptr_t)scratch & 15) != 0) {
+    bool plain = n < 4 * BIN_TILE || (ptrs & 15) != 0 || grid_bits >= (1ull << 32) || !scratch ||
+                 scratch_bytes < mdvc_bin_scratch_bytes(n) || ((uintptr_t)scratch & 15) != 0;
+    // slab size: 64 KiB of grid words, smaller for small grids (so that at least ~512 CTAs fill), 128 KiB beyond 1024^3
+    int slab_shift = 19;
+    while (slab_shift > 15 && ((grid_bits + (1ull << slab_shift) - 1) >> slab_shift) < 512) --slab_shift;
+    while (((grid_bits + (1ull << slab_shift) - 1) >> slab_shift) > BIN_MAX_SLABS) ++slab_shift;
+    if (slab_shift > 20 || ((uintptr_t)occ_bits & 15) != 0 || (pitch & 3) != 0) plain = true;
+    // a grid that stays in the L2 takes the scattered REDs without DRAM traffic: 512^3 (16 MiB) 30 us plain against 56 us
+    // here, 768^3 (54 MiB) 54 against 91 us, 1024^3 (128 MiB) 198 against 155 us (B200, profiles/r2_bin_slabs.txt)
+    if (grid_bytes <= ((size_t)64 << 20)) plain = true;
+    if (plain) {
         MDVC_CUDA_CHECK(cudaMemsetAsync(occ_bits, 0, grid_bytes, st));
         return mdvc_bin_atoms(pos, n, T_host, invT_host, nbox_host, occ_bits, pitch, vox_out, pos_out, stream);
     }
     BinParams P;
     bin_params(P, T_host, invT_host, nbox_host);
-    BinBuckets B;
+    // per device and cheap; not a stream operation, so it is fine inside a stream capture
+    MDVC_CUDA_CHECK(cudaFuncSetAttribute(k_bin_sort<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bin_sort_smem()));
+    MDVC_CUDA_CHECK(cudaFuncSetAttribute(k_bin_sort<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bin_sort_smem()));
+    MDVC_CUDA_CHECK(cudaFuncSetAttribute(k_bin_fill, cudaFuncAttributeMaxDynamicSharedMemorySize, 1 << 17));
+    BinSlabs B;
     B.cursor = reinterpret_cast<uint32_t *>(scratch);
-    B.keys = B.cursor + 64;
-    B.cap = (uint32_t)((((size_t)n * 2 / BIN_CHUNKS + 3) & ~(size_t)3) + 1024);
-    B.px_shift = 0;
-    while (((X + (1ll << B.px_shift) - 1) >> B.px_shift) > BIN_CHUNKS) ++B.px_shift;
+    B.keys = B.cursor + 2 * BIN_MAX_SLABS;
+    B.slab_shift = slab_shift;
+    B.n_slabs = (uint32_t)((grid_bits + (1ull << slab_shift) - 1) >> slab_shift);
+    B.cap = (uint32_t)(((size_t)n * 3 / B.n_slabs) & ~(size_t)3) + 256u;
     B.row_bits = (uint32_t)pitch * 32u;
-    const int n_chunks = (int)((X + (1ll << B.px_shift) - 1) >> B.px_shift);
-    MDVC_CUDA_CHECK(cudaMemsetAsync(B.cursor, 0, 64 * sizeof(uint32_t), st));
-    const long long n_tiles = ((n >> 2) + BIN_TILE_ATOMS / 4 - 1) / (BIN_TILE_ATOMS / 4);
-    if (P.fits32 && !vox_out && !pos_out)
-        k_bin_bucket<true><<<mdvc_grid(n_tiles * 256, 256, 5), 256, 0, st>>>(pos, n, P, B, vox_out, pos_out);
-    else
-        k_bin_bucket<false><<<mdvc_grid(n_tiles * 256, 256, 3), 256, 0, st>>>(pos, n, P, B, vox_out, pos_out);
+    MDVC_CUDA_CHECK(cudaMemsetAsync(B.cursor, 0, (BIN_MAX_SLABS + 1) * sizeof(uint32_t), st));
+    const bool fast = P.fits32 && !vox_out && !pos_out;
+    // every resident CTA gets the same number of tiles: the tile size shrinks below BIN_TILE instead of leaving a last,
+    // mostly idle round (10.2 M beads: 296 CTAs x 5 tiles of 6892 beads rather than 4.2 rounds of 8192)
+    const long long n4 = n >> 2, slots = (long long)mdvc_num_sms() * (fast ? 2 : 1);
+    const long long min_tiles = (n4 + BIN_TILE / 4 - 1) / (BIN_TILE / 4);
+    const long long sort_grid = std::min(min_tiles, slots);
+    const long long rounds = (min_tiles + sort_grid - 1) / sort_grid;
+    const int tile_groups = (int)((n4 + rounds * sort_grid - 1) / (rounds * sort_grid));
+    if (fast) k_bin_sort<true><<<(unsigned)sort_grid, BIN_THREADS, bin_sort_smem(), st>>>(pos, n, P, B, tile_groups, vox_out, pos_out);
+    else k_bin_sort<false><<<(unsigned)sort_grid, BIN_THREADS, bin_sort_smem(), st>>>(pos, n, P, B, tile_groups, vox_out, pos_out);
     MDVC_LAUNCH_CHECK();
-    for (int c = 0; c < n_chunks; ++c) {
-        const long long x0 = (long long)c << B.px_shift, x1 = (x0 + (1ll << B.px_shift)) < X ? x0 + (1ll << B.px_shift) : X;
-        MDVC_CUDA_CHECK(cudaMemsetAsync(occ_bits + (size_t)x0 * plane_words, 0, (size_t)(x1 - x0) * plane_words * sizeof(uint32_t), st));
-        k_bin_keys<<<mdvc_grid((long long)B.cap, 256, 4), 256, 0, st>>>(B.keys + (size_t)c * B.cap, B.cursor + c, B.cap, occ_bits);
-        MDVC_LAUNCH_CHECK();
-    }
-    // beads that found their bucket full (very uneven systems) and the last n % 4 beads
-    k_bin_keys<<<mdvc_grid(n, 256, 4), 256, 0, st>>>(B.keys + (size_t)BIN_CHUNKS * B.cap, B.cursor + BIN_CHUNKS, (uint32_t)n, occ_bits);
+    k_bin_fill<<<B.n_slabs, BIN_THREADS, (size_t)1 << (slab_shift - 3), st>>>(B, occ_bits, (unsigned long long)X * plane_words);
+    MDVC_LAUNCH_CHECK();
+    // beads that found their slab's list full (very uneven systems) and the last n % 4 beads
+    k_bin_keys<<<mdvc_grid(n, 256, 4), 256, 0, st>>>(B.keys + (size_t)B.n_slabs * B.cap, B.cursor + BIN_MAX_SLABS, (uint32_t)n, occ_bits);
     MDVC_LAUNCH_CHECK();
     if (n & 3) {
         k_bin_atoms1<<<1, 256, 0, st>>>(pos, n & ~3ll, n, P, occ_bits, pitch, vox_out, pos_out);

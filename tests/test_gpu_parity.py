@@ -146,11 +146,12 @@ def test_morph_rejects_unknown_op(dev):
 @pytest.mark.parametrize("case", ["uniform", "one_plane_range", "two_blobs", "outside_and_far", "on_and_next_to_faces"])
 @pytest.mark.parametrize("n", [8192, 50001, 262147])
 def test_bin_grid_bucketed_path_equals_plain_binning(dev, case, n):
-    """mdvc_bin_grid (beads bucketed by x-plane range, grid cleared and filled range by range) against clear +
+    """mdvc_bin_grid (bead keys sorted into the key lists of 64 KiB grid slabs, every slab built in shared memory and
+    written once; the grid is larger than the 64 MiB below which the call takes the plain kernels) against clear +
     mdvc_bin_atoms and the oracle: same occupancy, voxels and rewritten positions -- for even and very uneven bead
-    distributions (a full bucket spills), bead counts that are no multiple of four, beads far outside the box."""
+    distributions (a full list spills), bead counts that are no multiple of four, beads far outside the box."""
     rng = np.random.default_rng(n + len(case))
-    dims = np.array([403.0, 251.5, 330.0, 90, 90, 90], dtype=np.float32)
+    dims = np.array([5050.0, 3525.0, 4000.0, 90, 90, 90], dtype=np.float32)
     res = 0.5
     _, nbox, T, invT = vo.voxel_transform(dims, res)
     shape = tuple(int(v) for v in np.diagonal(nbox))
@@ -164,7 +165,7 @@ def test_bin_grid_bucketed_path_equals_plain_binning(dev, case, n):
     elif case == "on_and_next_to_faces":
         # voxel faces (multiples of the 5 A voxel edge, also outside the box) and their float32 neighbours: the
         # certified single-precision floor must hand every one of them to the float64 path
-        faces = (rng.integers(-90, 180, (n, 3)) * 5.0).astype(np.float32)
+        faces = (rng.integers(-900, 1800, (n, 3)) * 5.0).astype(np.float32)
         step = rng.integers(-3, 4, (n, 3))
         pos = faces.copy()
         for k in range(1, 4):
@@ -185,8 +186,11 @@ def test_bin_grid_bucketed_path_equals_plain_binning(dev, case, n):
     v1, p1 = dev.bin_grid(pos_d, T, invT, nbox, fresh, want_voxels=True, want_positions=True)
     assert torch.equal(fresh.words, plain.words)
     assert torch.equal(v0, v1) and torch.equal(p0.view(torch.int32), p1.view(torch.int32))
+    assert fresh.words.numel() * 4 > 64 << 20                   # the slab path, not the small-grid shortcut
     vox, _, newpos = vo.voxelate_fma(pos, dims, res)
-    assert np.array_equal(fresh.to_bool().cpu().numpy(), vo.occupancy(vox, nbox))
+    want_words = np.zeros(tuple(fresh.words.shape), dtype=np.uint32)   # vo.occupancy (atomgroup_to_voxels.py:192-197), bit-packed
+    np.bitwise_or.at(want_words, (vox[:, 0], vox[:, 1], vox[:, 2] >> 5), np.uint32(1) << (vox[:, 2] & 31).astype(np.uint32))
+    assert np.array_equal(fresh.words.cpu().numpy().view(np.uint32), want_words)
     assert np.array_equal(v1.cpu().numpy(), vox.astype(np.int32))
     # occupancy only, into a reused scratch, unaligned view (falls back to the plain kernels)
     scratch = dev.bin_scratch(n, "cuda")
