@@ -76,9 +76,10 @@ int mdvc_bin_atoms(const float *pos, long long n, const double *T_host, const do
 
 /* A1 into a grid that this call also CLEARS (the usual case: one occupancy grid per frame).  Same arguments as
  * mdvc_bin_atoms plus a scratch buffer of mdvc_bin_scratch_bytes(n) bytes (16-byte aligned device memory; NULL or
- * too small = clear + mdvc_bin_atoms).  Beads are first bucketed by x-plane range, then the grid is cleared and
- * filled range by range so that the clearing stores and the atomics of a range meet in the L2: the coordinates are
- * read once and the grid is written once, instead of one DRAM read-modify-write per bead.  Result identical to
+ * too small = clear + mdvc_bin_atoms).  For grids of more than 64 MiB of bit words the beads' keys are first sorted
+ * into one list per 64 KiB slab of the grid; every slab is then built in shared memory and written once: the
+ * coordinates are read once and the grid is written once, instead of a memset plus one DRAM read-modify-write per
+ * bead.  Smaller grids stay in the L2 and are cleared and filled with plain atomics.  Result identical to
  * clear + mdvc_bin_atoms (the OR of the same bits). */
 size_t mdvc_bin_scratch_bytes(long long n);
 int mdvc_bin_grid(const float *pos, long long n, const double *T_host, const double *invT_host,

@@ -593,9 +593,8 @@ extern "C" int mdvc_bin_grid(const float *pos, long long n, const double *T_host
     // clear everything and take the plain kernels
     bool plain = n < 4 * BIN_TILE || (ptrs & 15) != 0 || grid_bits >= (1ull << 32) || !scratch ||
                  scratch_bytes < mdvc_bin_scratch_bytes(n) || ((uintptr_t)scratch & 15) != 0;
-    // slab size: 64 KiB of grid words, smaller for small grids (so that at least ~512 CTAs fill), 128 KiB beyond 1024^3
+    // slab size: 64 KiB of grid words (three CTAs of k_bin_fill per SM), 128 KiB beyond 1024^3 (more than BIN_MAX_SLABS slabs)
     int slab_shift = 19;
-    while (slab_shift > 15 && ((grid_bits + (1ull << slab_shift) - 1) >> slab_shift) < 512) --slab_shift;
     while (((grid_bits + (1ull << slab_shift) - 1) >> slab_shift) > BIN_MAX_SLABS) ++slab_shift;
     if (slab_shift > 20 || ((uintptr_t)occ_bits & 15) != 0 || (pitch & 3) != 0) plain = true;
     // a grid that stays in the L2 takes the scattered REDs without DRAM traffic: 512^3 (16 MiB) 30 us plain against 56 us

@@ -601,8 +601,13 @@ k_link_round(const uint32_t *__restrict__ bits, Dims D, const Hdr *__restrict__ 
 #ifndef STRIP_TY
 #define STRIP_TY 64
 #endif
+#ifndef STRIP_CAP
 #define STRIP_CAP 2048
+#endif
+#ifndef TILE_THREADS
 #define TILE_THREADS 128
+#endif
+#define TILE_MIN_CTAS (1024 / TILE_THREADS)
 #define ZMASK 0xffffffu            // packed run entry: (local row << 24) | z   (Z < 2^24, STRIP_TY + 2 < 256)
 
 __device__ __forceinline__ void smem_union(volatile uint32_t *par, uint32_t a, uint32_t b) {
@@ -666,7 +671,7 @@ __device__ __forceinline__ bool rows_mirror(const uint32_t *tz, uint32_t a0, uin
     return mirror;
 }
 
-__global__ void __launch_bounds__(TILE_THREADS, 8)
+__global__ void __launch_bounds__(TILE_THREADS, TILE_MIN_CTAS)
 k_strip_link(const uint32_t *__restrict__ bits, Dims D, Hdr *h, const uint32_t *__restrict__ rowoff,
              const uint8_t *__restrict__ rowpol, const uint32_t *__restrict__ runstart, uint32_t *parent, uint32_t *rootlist,
              uint8_t *__restrict__ rowflag) {
@@ -814,7 +819,7 @@ k_flatten_list(const Hdr *__restrict__ h, const uint32_t *__restrict__ list, uin
 
 // x-phase tile: TY rows of plane x against rows y0-1 .. y0+TY of plane x-1, run lists and current roots
 // in shared memory; only new (root,root) pairs of the CTA reach the global union.
-__global__ void __launch_bounds__(TILE_THREADS, 8)
+__global__ void __launch_bounds__(TILE_THREADS, TILE_MIN_CTAS)
 k_tile_link_x(const uint32_t *__restrict__ bits, Dims D, const Hdr *__restrict__ h, const uint32_t *__restrict__ rowoff,
               const uint8_t *__restrict__ rowpol, const uint32_t *__restrict__ runstart, uint32_t *parent, int s, int radix,
               uint8_t *__restrict__ rowflag) {

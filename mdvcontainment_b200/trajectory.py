@@ -23,6 +23,78 @@ def frames_of_rank(n_frames: int, rank: int, world: int):
     return list(range(rank, n_frames, world))
 
 
+class SharedFrameCounter:
+    """Frame numbers handed out first come, first served to the ranks of ONE node: an 8-byte counter in a file under
+    /dev/shm, incremented under ``flock`` (a few microseconds per claim, no collective, no server).  Ranks whose GPU sits
+    behind a slower host link -- on an 8-GPU box the pinned-copy rates differ by 1.5x between ranks
+    -- then simply take fewer frames instead of holding everybody up.  ``name`` must be the same on all ranks and new for
+    every pass (e.g. derived from MASTER_PORT and a pass number); rank 0 creates the file, the others open it after a
+    barrier (``create=False``)."""
+
+    def __init__(self, name: str, create: bool):
+        import fcntl
+        self._fcntl = fcntl
+        self.path = os.path.join("/dev/shm" if os.path.isdir("/dev/shm") else "/tmp", f"mdvc_frames_{name}")
+        if create:
+            fd = os.open(self.path, os.O_RDWR | os.O_CREAT | os.O_TRUNC, 0o600)
+            os.pwrite(fd, (0).to_bytes(8, "little"), 0)
+        else:
+            fd = os.open(self.path, os.O_RDWR)
+        self.fd = fd
+
+    def claim(self) -> int:
+        """The next unclaimed frame number (monotone over all ranks)."""
+        self._fcntl.flock(self.fd, self._fcntl.LOCK_EX)
+        try:
+            v = int.from_bytes(os.pread(self.fd, 8, 0), "little")
+            os.pwrite(self.fd, (v + 1).to_bytes(8, "little"), 0)
+        finally:
+            self._fcntl.flock(self.fd, self._fcntl.LOCK_UN)
+        return v
+
+    def peek(self) -> int:
+        return int.from_bytes(os.pread(self.fd, 8, 0), "little")
+
+    def close(self, unlink: bool = False):
+        os.close(self.fd)
+        if unlink:
+            try:
+                os.unlink(self.path)
+            except OSError:
+                pass
+
+
+def _frame_source(n_frames: int, rank: int, world: int, schedule: str, counter_name: str | None):
+    """(next_frame, tail_start, close): ``next_frame()`` -> frame number or None.  ``static``: frame f on rank f mod world.
+    ``dynamic``: first come, first served from a SharedFrameCounter (single node); every rank must call this function,
+    it synchronises the creation of the counter with a barrier."""
+    if schedule == "static" or world == 1:
+        it = iter(frames_of_rank(n_frames, rank, world))
+        return (lambda: next(it, None)), n_frames, (lambda: None), None
+    if schedule != "dynamic":
+        raise ValueError(f"schedule must be 'static' or 'dynamic', not {schedule!r}")
+    import torch.distributed as dist
+    name = counter_name or f"{os.environ.get('MASTER_PORT', '0')}_{_frame_source.passes}"
+    _frame_source.passes += 1
+    counter = SharedFrameCounter(name, create=True) if rank == 0 else None
+    dist.barrier()
+    if counter is None:
+        counter = SharedFrameCounter(name, create=False)
+
+    def next_frame():
+        f = counter.claim()
+        return f if f < n_frames else None
+
+    def close():
+        dist.barrier()                                   # nobody still claims
+        counter.close(unlink=rank == 0)
+
+    return next_frame, n_frames, close, counter
+
+
+_frame_source.passes = 0
+
+
 def summarise(out) -> dict:
     """Small, picklable summary of a FrameOutput."""
     return {
@@ -98,8 +170,13 @@ class PipelinePool:
 
 def run_trajectory(frames, dimensions, resolution, closing=True, morph="", n_frames=None,
                    frame_fn: Callable | None = None, in_flight: int = 3, stats: dict | None = None,
-                   bind_numa: bool = True, pool: "PipelinePool | None" = None):
+                   bind_numa: bool = True, pool: "PipelinePool | None" = None, schedule: str = "static"):
     """Process every frame of a trajectory, sharded over the ranks of the current process group.
+
+    ``schedule="static"``: frame f on rank f mod world.  ``"dynamic"`` (ranks of one node): frames are claimed first come,
+    first served from a ``SharedFrameCounter``, so that ranks behind a slower host link -- or frames that cost more --
+    do not hold the others up; near the end of the trajectory a rank only claims another frame once its own frames in
+    flight are finished, which leaves the last frames to whoever is ahead.
 
     Default (CUDA): ``in_flight`` FramePipelines per rank, each with its own streams and a reusable pinned staging
     buffer, so that the copy / device stages of frame f+1.. overlap the host graph stage of frame f.
@@ -113,9 +190,12 @@ def run_trajectory(frames, dimensions, resolution, closing=True, morph="", n_fra
     if n_frames is None:
         n_frames = len(frames)
     get = frames if callable(frames) else (lambda f: frames[f])
-    mine = frames_of_rank(n_frames, rank, world)
+    next_frame, _, close_source, counter = _frame_source(n_frames, rank, world, schedule, None)
     if frame_fn is not None:
-        local = {f: frame_fn(get(f)) for f in mine}
+        local = {}
+        while (f := next_frame()) is not None:
+            local[f] = frame_fn(get(f))
+        close_source()
         return gather_results(local, n_frames, rank, world)
 
     import torch
@@ -127,7 +207,7 @@ def run_trajectory(frames, dimensions, resolution, closing=True, morph="", n_fra
         if stats is not None:
             stats["placement"] = placement
     if pool is None:
-        depth = max(1, min(int(in_flight), len(mine) or 1))
+        depth = max(1, min(int(in_flight), -(-n_frames // world) or 1))
         pool = PipelinePool(resolution, closing, morph, depth)
     elif pool.args != (resolution, closing, morph):
         raise ValueError("the pipeline pool was made for another resolution / closing / morph")
@@ -135,7 +215,18 @@ def run_trajectory(frames, dimensions, resolution, closing=True, morph="", n_fra
     memo0 = pool.memo_counters()
     pins = [None] * depth
     local, pending = {}, []
-    for k, f in enumerate(mine):
+    k = -1
+    tail_start = n_frames - world * (depth - 1) if counter is not None else n_frames
+    while True:
+        if counter is not None and pending and counter.peek() >= tail_start:
+            # the last frames go to whoever gets there first with nothing left in flight
+            f0, p0 = pending.pop(0)
+            local[f0] = summarise(p0.finish())
+            continue
+        f = next_frame()
+        if f is None:
+            break
+        k += 1
         i = k % depth
         if len(pending) == depth:                       # the oldest frame in flight is the one that used slot i
             f0, p0 = pending.pop(0)
@@ -161,9 +252,10 @@ def run_trajectory(frames, dimensions, resolution, closing=True, morph="", n_fra
         pending.append((f, pipe))
     for f0, p0 in pending:
         local[f0] = summarise(p0.finish())
+    close_source()
     if stats is not None:
         lookups, hits = (b - a for a, b in zip(memo0, pool.memo_counters()))
-        stats.update(frames=len(mine), memo_lookups=lookups, memo_hits=hits, memo_hit_rate=(hits / lookups) if lookups else None)
+        stats.update(frames=len(local), memo_lookups=lookups, memo_hits=hits, memo_hit_rate=(hits / lookups) if lookups else None)
     return gather_results(local, n_frames, rank, world)
 
 

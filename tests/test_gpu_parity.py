@@ -204,6 +204,25 @@ def test_bin_grid_bucketed_path_equals_plain_binning(dev, case, n):
     assert torch.equal(odd.words, want.words)
 
 
+def test_bin_grid_beyond_1024_cubed_uses_128k_slabs(dev):
+    """A grid of more than 2048 slabs of 64 KiB (1200 x 1200 x 1280 voxels, 220 MiB of bit words) is built from 128 KiB
+    slabs, one CTA of the fill kernel per SM: same words as clear + mdvc_bin_atoms."""
+    rng = np.random.default_rng(77)
+    dims = np.array([6000.0, 6000.0, 6400.0, 90, 90, 90], dtype=np.float32)
+    _, nbox, T, invT = vo.voxel_transform(dims, 0.5)
+    shape = tuple(int(v) for v in np.diagonal(nbox))
+    assert shape == (1200, 1200, 1280)
+    pos = (rng.random((150001, 3)) * dims[:3] * 1.2 - 0.1 * dims[:3]).astype(np.float32)
+    pos_d = torch.from_numpy(pos).cuda()
+    plain = dev.BitGrid(shape)
+    dev.bin_atoms(pos_d, T, invT, nbox, plain)
+    fresh = dev.BitGrid(shape, words=torch.full((shape[0], shape[1], dev.pitch_words(shape[2])), -1, dtype=torch.int32, device="cuda"))
+    dev.bin_grid(pos_d, T, invT, nbox, fresh)
+    assert torch.equal(fresh.words, plain.words)
+    vox = vo.voxelate_fma(pos, dims, 0.5)[0]
+    assert fresh.count() == len(np.unique(vox[:, 0] * (1 << 42) + vox[:, 1] * (1 << 21) + vox[:, 2]))
+
+
 @pytest.mark.parametrize("name", sorted(binning_cases()))
 def test_binning_matches_golden(dev, name):
     c = binning_cases()[name]

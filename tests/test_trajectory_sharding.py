@@ -6,6 +6,7 @@ import sys
 import textwrap
 
 import numpy as np
+import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
@@ -48,16 +49,43 @@ WORKER = textwrap.dedent("""
                 "edges": [(int(a), int(b)) for a, b in dag.edges()],
                 "counts": {int(k): int(v) for k, v in vo.counts(comps).items()}}
 
-    res = run_trajectory(frame, dims, 0.5, n_frames=5, frame_fn=cpu_frame)
+    res = run_trajectory(frame, dims, 0.5, n_frames=5, frame_fn=cpu_frame, schedule=%r)
     if int(os.environ["RANK"]) == 0:
         print("RESULT" + json.dumps(res))
     dist.destroy_process_group()
 """)
 
 
-def test_two_rank_gloo_trajectory_matches_single_rank(tmp_path):
+def _claim_worker(args):
+    from mdvcontainment_b200.trajectory import SharedFrameCounter
+    name, n = args
+    c = SharedFrameCounter(name, create=False)
+    got = [c.claim() for _ in range(n)]
+    c.close()
+    return got
+
+
+def test_shared_frame_counter_hands_out_every_number_once():
+    """Four processes claiming concurrently: the numbers 0 .. 4n-1, each exactly once, increasing per process."""
+    import multiprocessing as mp
+    from mdvcontainment_b200.trajectory import SharedFrameCounter
+    name = f"test_{os.getpid()}"
+    c = SharedFrameCounter(name, create=True)
+    try:
+        with mp.get_context("fork").Pool(4) as pool:
+            parts = pool.map(_claim_worker, [(name, 500)] * 4)
+        assert all(p == sorted(p) for p in parts)
+        assert sorted(v for p in parts for v in p) == list(range(2000))
+        assert c.peek() == 2000 and c.claim() == 2000
+    finally:
+        c.close(unlink=True)
+    assert not os.path.exists(c.path)
+
+
+@pytest.mark.parametrize("schedule", ["static", "dynamic"])
+def test_two_rank_gloo_trajectory_matches_single_rank(tmp_path, schedule):
     script = tmp_path / "worker.py"
-    script.write_text(WORKER % (ROOT, os.path.join(ROOT, "oracle")))
+    script.write_text(WORKER % (ROOT, os.path.join(ROOT, "oracle"), schedule))
 
     def launch(world):
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
@@ -71,6 +99,9 @@ def test_two_rank_gloo_trajectory_matches_single_rank(tmp_path):
     two = launch(2)
     one = launch(1)
     assert len(two) == len(one) == 5
-    assert [r["rank"] for r in two] == [0, 1, 0, 1, 0]            # frame f ran on rank f mod 2
+    if schedule == "static":
+        assert [r["rank"] for r in two] == [0, 1, 0, 1, 0]        # frame f ran on rank f mod 2
+    else:
+        assert set(r["rank"] for r in two) <= {0, 1}              # first come, first served
     for a, b in zip(one, two):
         assert a["nodes"] == b["nodes"] and a["edges"] == b["edges"] and a["counts"] == b["counts"]
