@@ -331,10 +331,25 @@ def run_ours(args):
         from mdvcontainment_b200.trajectory import SharedFrameCounter
         name = f"bench_{os.environ.get('MASTER_PORT', '0')}_{claim_pass[0]}"
         claim_pass[0] += 1
-        counter = SharedFrameCounter(name, create=True) if rank == 0 else None
+        # every rank takes the same path through the collectives whatever happens to its own open()
+        counter, ok = None, 1
+        if rank == 0:
+            try:
+                counter = SharedFrameCounter(name, create=True)
+            except OSError:
+                ok = 0
         barrier()
-        if counter is None:
-            counter = SharedFrameCounter(name, create=False)
+        if rank != 0:
+            try:
+                counter = SharedFrameCounter(name, create=False)
+            except OSError:
+                ok = 0
+        t_ok = torch.tensor([ok], device="cuda")
+        dist.all_reduce(t_ok, op=dist.ReduceOp.MIN)
+        if int(t_ok.item()) == 0:
+            if counter is not None:
+                counter.close(unlink=rank == 0)
+            return None
         total = world * steps
         tail_start = total - world * (n_flight - 1)
         barrier()
@@ -394,9 +409,10 @@ def run_ours(args):
     ms_e2e, _, _ = repeated(True, reps)
     hits = sum(p.memo_hits for p in pipes) / max(1, sum(p.memo_lookups for p in pipes))
     ms_e2e_claimed, claimed_per_rank = None, None
-    if world > 1:
-        timed_claimed(args.steps)                                          # warm-up of the claiming loop
+    if world > 1 and timed_claimed(args.steps) is not None:               # warm-up of the claiming loop
         ms_e2e_claimed = [timed_claimed(args.steps) for _ in range(reps)]
+        if any(m is None for m in ms_e2e_claimed):
+            ms_e2e_claimed = None
         t = torch.zeros(world, device="cuda", dtype=torch.int64)
         t[rank] = claimed_frames[0]
         dist.all_reduce(t)

@@ -128,7 +128,8 @@ struct BinParams {
     int nbox32[9];       // the same matrix when every entry fits (fits32), for the all-32-bit fast path
     int fits32;
     float Tf[9];         // T rounded to float32: the certified single-precision floor of bin_floor_f32
-    float Tcol[3];       // column sums |T0j| + |T1j| + |T2j| (float32, rounded up)
+    float Teps[3];       // 5e-7 x the column sums |T0j| + |T1j| + |T2j| (float32, rounded up)
+    float mmax;          // 1e5 / the largest column sum: beyond it the single-precision floor is not attempted
 };
 
 // Python floor division a // b for b > 0.  Atoms are almost always inside the box or one image away, so
@@ -206,21 +207,22 @@ __device__ __forceinline__ bool bin_one_atom(float x, float y, float z, const Bi
 }
 
 // Certified single-precision floor.  The reference floors the float64 chain above; almost every bead lies nowhere near
-// a voxel face, and for those the same floor follows from float32 arithmetic: with a = |p0 T0j| + |p1 T1j| + |p2 T2j|
-// the float32 chain differs from the exact value by less than 4 * 2^-24 * a (one rounding of T, one per product / sum),
-// and the float64 chain by ~1e-13, so a float32 result whose distance to the nearest integer exceeds 1e-6 * a (4x the
-// bound) has the reference's floor.  a is bounded from above by max|p_i| * (|T0j| + |T1j| + |T2j|), one multiplication
-// per column instead of three (the looser bound leaves a few more beads undecided, which is safe).  Anything closer --
-// beads ON a face, as coordinates rounded to 0.01 A often are, huge coordinates, NaNs -- returns false and takes the
-// float64 path.  ~12 instructions per column instead of ~60.
+// a voxel face, and for those the same floor follows from float32 arithmetic.  With a = |p0 T0j| + |p1 T1j| + |p2 T2j|
+// the float32 chain f = fma(p2, T2j, fma(p1, T1j, p0 * T0j)) differs from the exact value by less than 4 * 2^-24 * a
+// = 2.4e-7 * a (every term passes through at most four roundings: T to float32, the product, the two sums), the float64
+// chain by ~1e-13 * a, so a float32 result whose distance to the nearest integer exceeds 5e-7 * a (twice the bound) has
+// the reference's floor.  a is bounded from above by max|p_i| * (|T0j| + |T1j| + |T2j|), one multiplication per column
+// instead of three (the looser bound leaves a few more beads undecided, which is safe).  Anything closer -- beads ON a
+// face, as coordinates rounded to 0.01 A often are, huge coordinates, NaNs -- returns false and takes the float64
+// path (0.3 % of the beads of the 1024^3 scene).  ~12 instructions per column instead of ~60.
 __device__ __forceinline__ bool bin_floor_f32(float x, float y, float z, const BinParams &P, int (&u)[3]) {
     const float m = fmaxf(fmaxf(fabsf(x), fabsf(y)), fabsf(z));
-    bool sure = m < 1e5f;                                         // false for NaNs too
+    bool sure = m < P.mmax;                                       // |f| < 1e5: exact f - floor(f), int conversion safe
 #pragma unroll
     for (int j = 0; j < 3; ++j) {
         const float f = fmaf(z, P.Tf[6 + j], fmaf(y, P.Tf[3 + j], x * P.Tf[j]));
-        const float fl = floorf(f), frac = f - fl, eps = fmaf(m, P.Tcol[j] * 1e-6f, 1e-30f);
-        sure = sure && frac >= eps && frac <= 1.0f - eps && P.Tcol[j] * m < 1e5f;
+        const float fl = floorf(f), frac = f - fl, eps = fmaf(m, P.Teps[j], 1e-30f);
+        sure = sure && frac >= eps && frac <= 1.0f - eps;         // false for NaNs too
         u[j] = (int)fl;
     }
     return sure;
@@ -320,8 +322,13 @@ static void bin_params(BinParams &P, const double *T_host, const double *invT_ho
         P.nbox32[k] = (int)nbox_host[k];
         P.Tf[k] = (float)T_host[k];
     }
-    for (int j = 0; j < 3; ++j)
-        P.Tcol[j] = nextafterf((fabsf(P.Tf[j]) + fabsf(P.Tf[3 + j]) + fabsf(P.Tf[6 + j])) * 1.000001f, INFINITY);
+    float cmax = 0.f;
+    for (int j = 0; j < 3; ++j) {
+        const float col = nextafterf((fabsf(P.Tf[j]) + fabsf(P.Tf[3 + j]) + fabsf(P.Tf[6 + j])) * 1.000001f, INFINITY);
+        P.Teps[j] = nextafterf(col * 5e-7f, INFINITY);
+        cmax = fmaxf(cmax, col);
+    }
+    P.mmax = cmax > 0.f ? 1e5f / cmax : 0.f;
 }
 
 extern "C" int mdvc_bin_atoms(const float *pos, long long n, const double *T_host, const double *invT_host,
@@ -484,6 +491,11 @@ k_bin_sort(const float *__restrict__ pos, long long n, BinParams P, BinSlabs B, 
         // ---- exclusive scan of the counts (four slabs per thread); list space reserved per (tile, slab)
         {
             const uint4 c = reinterpret_cast<const uint4 *>(s_cnt)[tid];
+            uint4 b;                                              // reserved list offsets: issued first, the round trip
+            b.x = c.x ? atomicAdd(&B.cursor[4 * tid], c.x) : 0u;  // to the L2 overlaps the scan below
+            b.y = c.y ? atomicAdd(&B.cursor[4 * tid + 1], c.y) : 0u;
+            b.z = c.z ? atomicAdd(&B.cursor[4 * tid + 2], c.z) : 0u;
+            b.w = c.w ? atomicAdd(&B.cursor[4 * tid + 3], c.w) : 0u;
             const uint32_t mine = c.x + c.y + c.z + c.w;
             uint32_t incl = mine;
 #pragma unroll
@@ -511,11 +523,7 @@ k_bin_sort(const float *__restrict__ pos, long long n, BinParams P, BinSlabs B, 
             o.z = o.y + c.y;
             o.w = o.z + c.z;
             reinterpret_cast<uint4 *>(s_off)[tid] = o;
-            uint4 b;                                              // reserved list offset minus the tile-local offset
-            b.x = (c.x ? atomicAdd(&B.cursor[4 * tid], c.x) : 0u) - o.x;
-            b.y = (c.y ? atomicAdd(&B.cursor[4 * tid + 1], c.y) : 0u) - o.y;
-            b.z = (c.z ? atomicAdd(&B.cursor[4 * tid + 2], c.z) : 0u) - o.z;
-            b.w = (c.w ? atomicAdd(&B.cursor[4 * tid + 3], c.w) : 0u) - o.w;
+            b.x -= o.x; b.y -= o.y; b.z -= o.z; b.w -= o.w;       // reserved list offset minus the tile-local offset
             reinterpret_cast<uint4 *>(s_cnt)[tid] = b;
         }
         __syncthreads();

@@ -248,7 +248,7 @@ class FramePipeline:
             if host_positions is not None:
                 # Frames of a trajectory differ in their bead count (selections, breathing shells): the count is a launch
                 # parameter of the captured stage-1 graph, so it is rounded up to a multiple of ATOM_QUANTUM and the tail
-                # filled with copies of bead 0 (binning a bead twice sets the same bit) -- a handful of graphs instead
+                # filled with copies of the first beads (binning a bead twice sets the same bit) -- a handful of graphs instead
                 # of one capture per frame.
                 n = int(host_positions.shape[0])
                 n_pad = -(-n // self.ATOM_QUANTUM) * self.ATOM_QUANTUM if n else 0
@@ -258,7 +258,10 @@ class FramePipeline:
                 with _Range("mdvc.h2d_positions"):
                     self.pos_dev[:n].copy_(host_positions, non_blocking=True)
                 if n_pad > n:
-                    self.pos_dev[n:n_pad] = self.pos_dev[0]
+                    # copies of the first beads rather than of one bead: thousands of keys for one voxel would overflow
+                    # that grid slab's key list in the binning and go the slow way through its spill list
+                    k = n_pad - n
+                    self.pos_dev[n:n_pad] = self.pos_dev[:k] if k <= n else self.pos_dev[0]
                 positions_dev = self.pos_dev[:n_pad]
             if not self._run_graph(positions_dev):
                 self._bits = self.voxelize(positions_dev)

@@ -76,10 +76,27 @@ def _frame_source(n_frames: int, rank: int, world: int, schedule: str, counter_n
     import torch.distributed as dist
     name = counter_name or f"{os.environ.get('MASTER_PORT', '0')}_{_frame_source.passes}"
     _frame_source.passes += 1
-    counter = SharedFrameCounter(name, create=True) if rank == 0 else None
+    # every rank takes the same path through the collectives whatever happens to its own open(); if any rank cannot
+    # reach the counter (ranks on different nodes, no shared /dev/shm) all of them fall back to the static map
+    counter, ok = None, True
+    if rank == 0:
+        try:
+            counter = SharedFrameCounter(name, create=True)
+        except OSError:
+            ok = False
     dist.barrier()
-    if counter is None:
-        counter = SharedFrameCounter(name, create=False)
+    if rank != 0:
+        try:
+            counter = SharedFrameCounter(name, create=False)
+        except OSError:
+            ok = False
+    oks = [None] * world
+    dist.all_gather_object(oks, ok)
+    if not all(oks):
+        if counter is not None:
+            counter.close(unlink=rank == 0)
+        it = iter(frames_of_rank(n_frames, rank, world))
+        return (lambda: next(it, None)), n_frames, (lambda: None), None
 
     def next_frame():
         f = counter.claim()

@@ -30,11 +30,11 @@ def main():
     seq = load(path)
     if "--frames" in sys.argv:      # --frames A B: frames A..B (1-based, inclusive) only; a frame starts with its binning
         a, b = (int(v) for v in sys.argv[sys.argv.index("--frames") + 1:][:2])
-        first = "k_bin_bucket" if any(n.startswith("k_bin_bucket") for n, _ in seq) else "k_bin_atoms"
+        first = next((f for f in ("k_bin_sort", "k_bin_bucket") if any(n.startswith(f) for n, _ in seq)), "k_bin_atoms")
         idx = [i for i, (n, _) in enumerate(seq) if n.startswith(first)] + [len(seq)]
         seq = seq[idx[a - 1]:idx[b]]
     if last_frames:      # keep only the launches from the last `last_frames` frames on (a frame starts with its binning)
-        first = "k_bin_bucket" if any(n.startswith("k_bin_bucket") for n, _ in seq) else "k_bin_atoms"
+        first = next((f for f in ("k_bin_sort", "k_bin_bucket") if any(n.startswith(f) for n, _ in seq)), "k_bin_atoms")
         idx = [i for i, (n, _) in enumerate(seq) if n.startswith(first)]
         seq = seq[idx[-last_frames]:]
     agg = collections.OrderedDict()
