@@ -357,7 +357,7 @@ def run_ours(args):
         e0.record()
         pending, k = [], 0
         while True:
-            if pending and counter.peek() >= tail_start:          # the last frames go to whoever is ahead
+            if len(pending) > 1 and counter.peek() >= tail_start:   # the last frames go to whoever is ahead
                 out = pending.pop(0).finish()
                 continue
             i = counter.claim()

@@ -297,6 +297,28 @@ int mdvc_host_component_neighbours(long long n_nodes, const int32_t *comp_of_nod
 int mdvc_host_adjacency(int32_t n_comps, const int32_t *eu_host, const int32_t *ev_host, long long n,
                         long long *offsets_out_host, int32_t *nbrs_out_host);
 
+/* Slab decomposition (no reference counterpart: the reference is one process on one grid): the global labels,
+ * contacts, bridges and volumes from the per-slab results of n_slabs x-slabs, HOST function.  Slab g has local labels
+ * 1..n_true[g] and -1..-n_false[g]; boundary rows (la, lb, sx, sy, sz) of mdvc_plane_pairs relate the last plane of
+ * slab g (la) to the first plane of slab (g+1) % n_slabs (lb); contacts int32[.][2], bridges int32[.][5] (y/z faces
+ * only) and volumes int64 (index = label + n_false[g]) are the slabs' own results.  All per-slab arrays are
+ * concatenated, *_off int64[n_slabs + 1] are row offsets (lut_off: element offsets of the volume / lut tables,
+ * lut_off[g+1] - lut_off[g] == n_false[g] + n_true[g] + 1).  Labels joined through an in-box step across a boundary
+ * become one global label, numbered per polarity by first voxel in C order like scipy.ndimage.label (label.py:10-17);
+ * contacts / bridges come out as the reference's sorted unique rows (find_label_contacts.pyx:41-77,
+ * find_bridges.pyx:84-87).  Outputs: lut_out (local label + n_false[g] -> global label, same offsets), the global
+ * label counts, contacts_out (capacity: all contact + boundary rows), bridges_out (capacity: twice all bridge +
+ * boundary rows), volumes_out (capacity: sum of all label counts + 1; index = global label + n_false_out). */
+int mdvc_host_merge_slabs(int n_slabs, const long long *n_true_host, const long long *n_false_host,
+                          const int32_t *boundary_host, const long long *boundary_off_host,
+                          const int32_t *contacts_host, const long long *contacts_off_host,
+                          const int32_t *bridges_host, const long long *bridges_off_host,
+                          const long long *volumes_host, const long long *lut_off_host,
+                          int32_t *lut_out_host, long long *n_true_out_host, long long *n_false_out_host,
+                          int32_t *contacts_out_host, long long *n_contacts_out_host,
+                          int32_t *bridges_out_host, long long *n_bridges_out_host,
+                          long long *volumes_out_host);
+
 #ifdef __cplusplus
 }
 #endif

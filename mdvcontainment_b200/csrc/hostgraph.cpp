@@ -254,3 +254,195 @@ extern "C" int mdvc_host_adjacency(int32_t n_comps, const int32_t *eu_host, cons
     }
     return MDVC_OK;
 }
+
+// ------------------------------------------------------------------------------------------
+// slab decomposition: the global problem from the slabs' results (mdvcontainment_b200/slab.py: merge_slabs)
+// ------------------------------------------------------------------------------------------
+// No reference counterpart (the reference is one process on one grid); the rules it has to
+// reproduce are the reference's: global labels numbered by first voxel in C order per polarity (label.py:10-17 through
+// scipy), contacts as sorted unique (min, max) rows (find_label_contacts.pyx:41-77), bridges as sorted unique
+// (min, max, +-shift) rows with both signs for a label bridged to itself (find_bridges.pyx:84-87).
+// One pass each over the slabs' rows instead of ~40 NumPy passes over 10^7-row arrays: union-find over one node per
+// (slab, local label) -- positives first, each polarity in (slab, |label|) order, so that the smallest node of a merged
+// group is the group's first voxel in C order --, numbering by a running count of the roots, rows mapped through the
+// per-slab tables, packed into one 64-bit key per row (key order == row order), LSD radix sort, unique.
+namespace {
+
+static int32_t uf_find(std::vector<int32_t> &p, int32_t v) {
+    int32_t r = v;
+    while (p[(size_t)r] != r) r = p[(size_t)r];
+    while (p[(size_t)v] != r) { const int32_t n = p[(size_t)v]; p[(size_t)v] = r; v = n; }
+    return r;
+}
+
+// ascending LSD radix sort, 11 bits per pass, only over the bits any key uses
+static void radix_sort_u64(std::vector<unsigned long long> &a) {
+    const size_t n = a.size();
+    if (n < 2) return;
+    unsigned long long all = 0;
+    for (size_t i = 0; i < n; ++i) all |= a[i];
+    std::vector<unsigned long long> b(n);
+    std::vector<size_t> cnt(2048);
+    for (int shift = 0; shift < 64 && (all >> shift) != 0; shift += 11) {
+        std::fill(cnt.begin(), cnt.end(), (size_t)0);
+        for (size_t i = 0; i < n; ++i) ++cnt[(size_t)((a[i] >> shift) & 2047u)];
+        size_t run = 0;
+        for (size_t d = 0; d < 2048; ++d) { const size_t c = cnt[d]; cnt[d] = run; run += c; }
+        for (size_t i = 0; i < n; ++i) b[cnt[(size_t)((a[i] >> shift) & 2047u)]++] = a[i];
+        a.swap(b);
+    }
+}
+
+static size_t unique_sorted(std::vector<unsigned long long> &a) {
+    size_t m = 0;
+    for (size_t i = 0; i < a.size(); ++i)
+        if (m == 0 || a[i] != a[m - 1]) a[m++] = a[i];
+    a.resize(m);
+    return m;
+}
+
+}  // namespace
+
+extern "C" int mdvc_host_merge_slabs(int n_slabs, const long long *n_true_host, const long long *n_false_host,
+                                     const int32_t *boundary_host, const long long *boundary_off_host,
+                                     const int32_t *contacts_host, const long long *contacts_off_host,
+                                     const int32_t *bridges_host, const long long *bridges_off_host,
+                                     const long long *volumes_host, const long long *lut_off_host,
+                                     int32_t *lut_out_host, long long *n_true_out_host, long long *n_false_out_host,
+                                     int32_t *contacts_out_host, long long *n_contacts_out_host,
+                                     int32_t *bridges_out_host, long long *n_bridges_out_host,
+                                     long long *volumes_out_host) {
+    const int G = n_slabs;
+    if (G < 1 || !n_true_host || !n_false_host || !boundary_off_host || !contacts_off_host || !bridges_off_host ||
+        !lut_off_host || !lut_out_host || !n_true_out_host || !n_false_out_host || !n_contacts_out_host ||
+        !n_bridges_out_host || !volumes_out_host)
+        return MDVC_ERR_BADARG;
+    std::vector<long long> base_pos((size_t)G + 1, 0), base_neg((size_t)G + 1, 0);
+    for (int g = 0; g < G; ++g) {
+        if (n_true_host[g] < 0 || n_false_host[g] < 0) return MDVC_ERR_BADARG;
+        if (lut_off_host[g + 1] - lut_off_host[g] != n_true_host[g] + n_false_host[g] + 1) return MDVC_ERR_BADARG;
+        base_pos[(size_t)g + 1] = base_pos[(size_t)g] + n_true_host[g];
+    }
+    const long long total_pos = base_pos[(size_t)G];
+    base_neg[0] = total_pos;
+    for (int g = 0; g < G; ++g) base_neg[(size_t)g + 1] = base_neg[(size_t)g] + n_false_host[g];
+    const long long n_nodes = base_neg[(size_t)G];
+    if (n_nodes >= (1ll << 31)) return MDVC_ERR_BADARG;
+    // local label of slab g -> node, -1 for labels outside the slab's range (bad input)
+    auto node = [&](int g, int32_t lab) -> long long {
+        if (lab > 0) return lab <= n_true_host[g] ? base_pos[(size_t)g] + lab - 1 : -1;
+        if (lab < 0) return -(long long)lab <= n_false_host[g] ? base_neg[(size_t)g] - lab - 1 : -1;
+        return -1;
+    };
+    auto has_shift = [](const int32_t *r) { return (r[2] | r[3] | r[4]) != 0; };
+
+    // --- labels joined through an in-box step across a slab boundary: one global label -----------------------------
+    std::vector<int32_t> parent((size_t)n_nodes);
+    for (long long i = 0; i < n_nodes; ++i) parent[(size_t)i] = (int32_t)i;
+    for (int g = 0; g < G; ++g) {
+        const int h = (g + 1) % G;
+        for (long long k = boundary_off_host[g]; k < boundary_off_host[g + 1]; ++k) {
+            const int32_t *r = boundary_host + 5 * k;
+            if (has_shift(r) || (r[0] > 0) != (r[1] > 0)) continue;
+            const long long a = node(g, r[0]), b = node(h, r[1]);
+            if (a < 0 || b < 0) return MDVC_ERR_BADARG;
+            int32_t ra = uf_find(parent, (int32_t)a), rb = uf_find(parent, (int32_t)b);
+            if (ra == rb) continue;
+            if (ra > rb) { const int32_t t = ra; ra = rb; rb = t; }
+            parent[(size_t)rb] = ra;                             // the smaller index stays the root
+        }
+    }
+    // --- numbering: the k-th root of a polarity (in node order) is label +-k -----------------------------------------
+    std::vector<int32_t> number((size_t)n_nodes);
+    long long NT = 0, NF = 0;
+    for (long long i = 0; i < total_pos; ++i)
+        if (parent[(size_t)i] == i) number[(size_t)i] = (int32_t)++NT;
+    for (long long i = total_pos; i < n_nodes; ++i)
+        if (parent[(size_t)i] == i) number[(size_t)i] = (int32_t)++NF;
+    for (long long i = 0; i < n_nodes; ++i) {
+        const int32_t r = uf_find(parent, (int32_t)i);
+        number[(size_t)i] = number[(size_t)r];                   // roots precede their members: already final
+    }
+    *n_true_out_host = NT;
+    *n_false_out_host = NF;
+    for (int g = 0; g < G; ++g) {
+        int32_t *lut = lut_out_host + lut_off_host[g];
+        const long long nf = n_false_host[g], nt = n_true_host[g];
+        for (long long k = 1; k <= nf; ++k) lut[nf - k] = -number[(size_t)(base_neg[(size_t)g] + k - 1)];
+        lut[nf] = 0;
+        for (long long k = 1; k <= nt; ++k) lut[nf + k] = number[(size_t)(base_pos[(size_t)g] + k - 1)];
+    }
+    // --- volumes ---------------------------------------------------------------------------------------------------------
+    for (long long i = 0; i < NF + NT + 1; ++i) volumes_out_host[i] = 0;
+    if (volumes_host)
+        for (int g = 0; g < G; ++g) {
+            const int32_t *lut = lut_out_host + lut_off_host[g];
+            const long long *vol = volumes_host + lut_off_host[g];
+            const long long n = lut_off_host[g + 1] - lut_off_host[g];
+            for (long long i = 0; i < n; ++i) volumes_out_host[(long long)lut[i] + NF] += vol[i];
+        }
+    volumes_out_host[NF] = 0;
+
+    // --- contacts and bridges as packed keys ----------------------------------------------------------------------------
+    const unsigned long long R = (unsigned long long)(NF + NT + 1);
+    if (R >= (1ull << 29)) return MDVC_ERR_BADARG;             // (R * R * 27 must fit 64 bits)
+    std::vector<unsigned long long> ckeys, bkeys;
+    ckeys.reserve((size_t)(contacts_off_host[G] + boundary_off_host[G]));
+    bkeys.reserve((size_t)(2 * (bridges_off_host[G] + boundary_off_host[G])));
+    auto add_contact = [&](long long a, long long b) {
+        if (a > b) { const long long t = a; a = b; b = t; }
+        ckeys.push_back((unsigned long long)(a + NF) * R + (unsigned long long)(b + NF));
+    };
+    auto add_bridge = [&](long long a, long long b, int sx, int sy, int sz) {
+        if (a > b) { const long long t = a; a = b; b = t; sx = -sx; sy = -sy; sz = -sz; }
+        const unsigned long long pair = (unsigned long long)(a + NF) * R + (unsigned long long)(b + NF);
+        bkeys.push_back(pair * 27ull + (unsigned long long)((sx + 1) * 9 + (sy + 1) * 3 + (sz + 1)));
+        if (a == b) bkeys.push_back(pair * 27ull + (unsigned long long)((1 - sx) * 9 + (1 - sy) * 3 + (1 - sz)));
+    };
+    for (int g = 0; g < G; ++g) {
+        const int h = (g + 1) % G;
+        const int32_t *lut = lut_out_host + lut_off_host[g], *lut_h = lut_out_host + lut_off_host[h];
+        const long long nf = n_false_host[g], nl = lut_off_host[g + 1] - lut_off_host[g];
+        const long long nf_h = n_false_host[h], nl_h = lut_off_host[h + 1] - lut_off_host[h];
+        for (long long k = contacts_off_host[g]; k < contacts_off_host[g + 1]; ++k) {
+            const long long ia = contacts_host[2 * k] + nf, ib = contacts_host[2 * k + 1] + nf;
+            if (ia < 0 || ib < 0 || ia >= nl || ib >= nl) return MDVC_ERR_BADARG;
+            add_contact(lut[ia], lut[ib]);
+        }
+        for (long long k = bridges_off_host[g]; k < bridges_off_host[g + 1]; ++k) {
+            const int32_t *r = bridges_host + 5 * k;
+            const long long ia = r[0] + nf, ib = r[1] + nf;
+            if (ia < 0 || ib < 0 || ia >= nl || ib >= nl || r[2] < -1 || r[2] > 1 || r[3] < -1 || r[3] > 1 || r[4] < -1 || r[4] > 1)
+                return MDVC_ERR_BADARG;
+            add_bridge(lut[ia], lut[ib], r[2], r[3], r[4]);
+        }
+        for (long long k = boundary_off_host[g]; k < boundary_off_host[g + 1]; ++k) {
+            const int32_t *r = boundary_host + 5 * k;
+            const long long ia = r[0] + nf, ib = r[1] + nf_h;
+            if (ia < 0 || ib < 0 || ia >= nl || ib >= nl_h || r[2] < -1 || r[2] > 1 || r[3] < -1 || r[3] > 1 || r[4] < -1 || r[4] > 1)
+                return MDVC_ERR_BADARG;
+            const long long ga = lut[ia], gb = lut_h[ib];
+            if (has_shift(r)) add_bridge(ga, gb, r[2], r[3], r[4]);
+            else if ((ga > 0) != (gb > 0)) add_contact(ga, gb);
+        }
+    }
+    radix_sort_u64(ckeys);
+    radix_sort_u64(bkeys);
+    const size_t nc = unique_sorted(ckeys), nb = unique_sorted(bkeys);
+    if ((nc && !contacts_out_host) || (nb && !bridges_out_host)) return MDVC_ERR_BADARG;
+    for (size_t i = 0; i < nc; ++i) {
+        contacts_out_host[2 * i] = (int32_t)((long long)(ckeys[i] / R) - NF);
+        contacts_out_host[2 * i + 1] = (int32_t)((long long)(ckeys[i] % R) - NF);
+    }
+    for (size_t i = 0; i < nb; ++i) {
+        const unsigned long long pair = bkeys[i] / 27ull;
+        const int code = (int)(bkeys[i] % 27ull);
+        int32_t *o = bridges_out_host + 5 * i;
+        o[0] = (int32_t)((long long)(pair / R) - NF);
+        o[1] = (int32_t)((long long)(pair % R) - NF);
+        o[2] = code / 9 - 1; o[3] = code / 3 % 3 - 1; o[4] = code % 3 - 1;
+    }
+    *n_contacts_out_host = (long long)nc;
+    *n_bridges_out_host = (long long)nb;
+    return MDVC_OK;
+}

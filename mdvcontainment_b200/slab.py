@@ -56,6 +56,51 @@ def _normalise_bridges(l1, l2, s):
 
 
 def merge_slabs(n_true, n_false, boundary_rows, local_contacts, local_bridges, local_volumes):
+    """Global labels, contacts, bridges and volumes from per-slab results: the compiled host routine
+    ``mdvc_host_merge_slabs`` (``csrc/hostgraph.cpp``; one pass over the slabs' rows, radix-sorted packed keys).  Same
+    arguments and result as ``merge_slabs_numpy`` below, which documents the rules and is kept as their NumPy statement
+    (``tests/test_slab_merge.py`` holds the two against each other and against the whole-grid oracle)."""
+    import ctypes
+    from . import _lib
+    G = len(n_true)
+    nt = np.asarray([int(v) for v in n_true], dtype=np.int64)
+    nf = np.asarray([int(v) for v in n_false], dtype=np.int64)
+
+    def cat(parts, cols):
+        arrs = [np.ascontiguousarray(np.asarray(a, dtype=np.int32).reshape(-1, cols)) for a in parts]
+        off = np.zeros(G + 1, dtype=np.int64)
+        off[1:] = np.cumsum([len(a) for a in arrs])
+        return (np.concatenate(arrs) if arrs else np.empty((0, cols), np.int32)), off
+
+    brows, boff = cat(boundary_rows, 5)
+    crows, coff = cat(local_contacts, 2)
+    grows, goff = cat(local_bridges, 5)
+    loff = np.zeros(G + 1, dtype=np.int64)
+    loff[1:] = np.cumsum(nt + nf + 1)
+    vols = np.concatenate([np.ascontiguousarray(v, dtype=np.int64).reshape(-1) for v in local_volumes])
+    if len(vols) != loff[-1]:
+        raise ValueError("local_volumes must hold n_false + n_true + 1 entries per slab")
+    lut = np.empty(int(loff[-1]), dtype=np.int32)
+    contacts = np.empty((len(crows) + len(brows), 2), dtype=np.int32)
+    bridges = np.empty((2 * (len(grows) + len(brows)), 5), dtype=np.int32)
+    volumes = np.empty(int((nt + nf).sum()) + 1, dtype=np.int64)
+    out = [ctypes.c_longlong(0) for _ in range(4)]                # NT, NF, contacts, bridges
+
+    def ptr(a):
+        return a.ctypes.data if a.size else None
+
+    rc = _lib.load().mdvc_host_merge_slabs(G, ptr(nt), ptr(nf), ptr(brows), ptr(boff), ptr(crows), ptr(coff), ptr(grows),
+                                           ptr(goff), ptr(vols), ptr(loff), ptr(lut), ctypes.addressof(out[0]),
+                                           ctypes.addressof(out[1]), ptr(contacts), ctypes.addressof(out[2]), ptr(bridges),
+                                           ctypes.addressof(out[3]), ptr(volumes))
+    _lib.check(rc, "mdvc_host_merge_slabs")
+    NT, NF, n_c, n_b = (int(o.value) for o in out)
+    return {"luts": [lut[loff[g]:loff[g + 1]] for g in range(G)], "n_true": NT, "n_false": NF,
+            "contacts": contacts[:n_c], "bridges": bridges[:n_b] if n_b else np.array([], dtype=np.int32),
+            "volumes": volumes[:NF + NT + 1]}
+
+
+def merge_slabs_numpy(n_true, n_false, boundary_rows, local_contacts, local_bridges, local_volumes):
     """Global labels, contacts, bridges and volumes from per-slab results.
 
     n_true[g], n_false[g]     label counts of slab g (local labels 1..n_true, -1..-n_false)

@@ -192,8 +192,8 @@ def run_trajectory(frames, dimensions, resolution, closing=True, morph="", n_fra
 
     ``schedule="static"``: frame f on rank f mod world.  ``"dynamic"`` (ranks of one node): frames are claimed first come,
     first served from a ``SharedFrameCounter``, so that ranks behind a slower host link -- or frames that cost more --
-    do not hold the others up; near the end of the trajectory a rank only claims another frame once its own frames in
-    flight are finished, which leaves the last frames to whoever is ahead.
+    do not hold the others up; near the end of the trajectory a rank only claims another frame once it has at most one
+    frame left in flight, which leaves the last frames to whoever is ahead.
 
     Default (CUDA): ``in_flight`` FramePipelines per rank, each with its own streams and a reusable pinned staging
     buffer, so that the copy / device stages of frame f+1.. overlap the host graph stage of frame f.
@@ -235,8 +235,9 @@ def run_trajectory(frames, dimensions, resolution, closing=True, morph="", n_fra
     k = -1
     tail_start = n_frames - world * (depth - 1) if counter is not None else n_frames
     while True:
-        if counter is not None and pending and counter.peek() >= tail_start:
-            # the last frames go to whoever gets there first with nothing left in flight
+        if counter is not None and len(pending) > 1 and counter.peek() >= tail_start:
+            # the last frames go to whoever gets there first with at most one frame left in flight (draining completely
+            # would restart the copy / compute pipeline from empty for every one of them)
             f0, p0 = pending.pop(0)
             local[f0] = summarise(p0.finish())
             continue

@@ -5,7 +5,7 @@ import pytest
 import voxel_oracle as vo
 from golden_util import voxel_cases
 from mdvcontainment_b200 import host_graph as hg
-from mdvcontainment_b200.slab import merge_slabs, slab_extents
+from mdvcontainment_b200.slab import merge_slabs, merge_slabs_numpy, slab_extents
 
 
 def plane_pairs_numpy(A, B, sx):
@@ -42,6 +42,12 @@ def solve_by_slabs(grid, n_slabs):
     boundary = [plane_pairs_numpy(labels[g][-1], labels[(g + 1) % n_slabs][0], 1 if g == n_slabs - 1 else 0)
                 for g in range(n_slabs)]
     m = merge_slabs(nt, nf, boundary, contacts, bridges, volumes)
+    ref = merge_slabs_numpy(nt, nf, boundary, contacts, bridges, volumes)     # the NumPy statement of the same rules
+    assert (m["n_true"], m["n_false"]) == (ref["n_true"], ref["n_false"])
+    assert all(np.array_equal(a, b) for a, b in zip(m["luts"], ref["luts"]))
+    assert m["contacts"].shape == ref["contacts"].shape and np.array_equal(m["contacts"], ref["contacts"])
+    assert m["bridges"].shape == ref["bridges"].shape and np.array_equal(m["bridges"], ref["bridges"])
+    assert np.array_equal(m["volumes"], ref["volumes"])
     glob = np.concatenate([m["luts"][g][labels[g] + nf[g]] for g in range(n_slabs)], axis=0)
     return m, glob
 
