@@ -517,6 +517,7 @@ def run_ours(args):
         "gvoxel_per_s": value * N / 1e9,
         "frame_algorithmic_gbs": frame_bytes * value / world / 1e9,
         "frame_roofline_frac": frame_bytes * value / world / 1e9 / peak,
+        "frame_roofline_frac_nominal_8tbs": frame_bytes * value / world / 1e9 / 8000.0,   # north star's nominal HBM3e figure
         # rows of 17..32 words (512 < Z <= 1024) take the one-warp-per-row form of the dense write
         "roofline": {"kernel": ("k_expand_row32" if 16 < (size + 31) // 32 <= 32 and size % 8 == 0 else "k_expand") +
                                " (dense write of labels + components)", "bound": "hbm", "achieved": achieved,

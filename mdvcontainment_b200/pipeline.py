@@ -235,17 +235,16 @@ class FramePipeline:
         """Enqueue bin -> morph -> label -> pairs and the small read-backs on this pipeline's stream; returns
         immediately so the caller can finish() another pipeline's frame meanwhile."""
         self._t0 = time.perf_counter()
-        self.stream.wait_stream(self.stream_x)               # the previous frame's dense write still reads our buffers
-        # whatever produced positions_dev on the caller's stream (a unit conversion, .cuda(non_blocking=True)) must
-        # be complete before the binning reads it on this pipeline's side stream
-        self.stream.wait_stream(torch.cuda.current_stream(self.device))
-        if positions_dev is not None:
-            _check_positions(positions_dev)
-            positions_dev.record_stream(self.stream)         # the caching allocator must not recycle it under us
         n_beads = int((host_positions if host_positions is not None else positions_dev).shape[0])
         self._ensure_bin_scratch(-(-n_beads // self.ATOM_QUANTUM) * self.ATOM_QUANTUM)    # before any graph capture
         with torch.cuda.stream(self.stream):
             if host_positions is not None:
+                # The copy goes FIRST, before this stream is made to wait for the previous frame's dense write: the
+                # position buffer was last read by that frame's binning, which is long finished (its stage-1 results
+                # were read on the host), while the dense write only reads the bit grid and the run tables.  (Measured:
+                # no change at 1024^3 -- 421 against 420 frames/s end to end -- the copies were already back to back; the
+                # 7 % between this loop and the stand-alone copy rate are the copy engine's writes competing with the
+                # dense write for the HBM.)
                 # Frames of a trajectory differ in their bead count (selections, breathing shells): the count is a launch
                 # parameter of the captured stage-1 graph, so it is rounded up to a multiple of ATOM_QUANTUM and the tail
                 # filled with copies of the first beads (binning a bead twice sets the same bit) -- a handful of graphs instead
@@ -263,6 +262,14 @@ class FramePipeline:
                     k = n_pad - n
                     self.pos_dev[n:n_pad] = self.pos_dev[:k] if k <= n else self.pos_dev[0]
                 positions_dev = self.pos_dev[:n_pad]
+        self.stream.wait_stream(self.stream_x)               # the previous frame's dense write still reads our buffers
+        # whatever produced positions_dev on the caller's stream (a unit conversion, .cuda(non_blocking=True)) must
+        # be complete before the binning reads it on this pipeline's side stream
+        self.stream.wait_stream(torch.cuda.current_stream(self.device))
+        if host_positions is None:
+            _check_positions(positions_dev)
+            positions_dev.record_stream(self.stream)         # the caching allocator must not recycle it under us
+        with torch.cuda.stream(self.stream):
             if not self._run_graph(positions_dev):
                 self._bits = self.voxelize(positions_dev)
                 self._enqueue_stage1(self._bits, self._rows_counted)
