@@ -459,7 +459,7 @@ def run_ours(args):
 
     extra = {}
     if not args.no_legs:
-        extra["trajectory"] = trajectory_leg(torch, dist, rank, world, barrier)
+        extra["trajectory"] = trajectory_leg(torch, dist, rank, world, barrier, h2d_gbs=h2d.get("per_rank_min_gbs"))
         torch.cuda.empty_cache()
         if world > 1:
             extra["slab"] = slab_leg(torch, dist, rank, world, barrier, args.slab_size)
@@ -593,7 +593,7 @@ def h2d_ceiling(torch, dist, world, pinned, dev_buf, n_copies=20):
             "bytes_per_copy": int(pinned.numel() * 4)}
 
 
-def trajectory_leg(torch, dist, rank, world, barrier, frames_per_rank=64, box_nm=256.0):
+def trajectory_leg(torch, dist, rank, world, barrier, frames_per_rank=64, box_nm=256.0, h2d_gbs=None):
     """Config 4: distinct frames of the synthetic 512^3 trajectory (vesicle drifting through the periodic box and
     breathing, fresh bead jitter per frame), sharded f -> rank f mod world, through trajectory.run_trajectory."""
     from mdvcontainment_b200 import synth
@@ -643,6 +643,11 @@ def trajectory_leg(torch, dist, rank, world, barrier, frames_per_rank=64, box_nm
            "memo_hit_rate": stats.get("memo_hit_rate"),
            "memo_note": "graph-stage memo emptied before every timed pass: hits are repeats of a topology within the pass",
            "timing": "wall clock around run_trajectory incl. the result gather, max over ranks"}
+    if h2d_gbs:
+        # the positions cross PCIe once per frame: what the slowest rank's measured pinned-copy rate allows
+        out["h2d_bytes_per_frame"] = int(beads * 12)
+        out["h2d_bound_frames_per_s"] = world * h2d_gbs * 1e9 / (beads * 12)
+        out["frac_of_h2d_bound"] = out["frames_per_s"] / out["h2d_bound_frames_per_s"]
     if rank == 0 and res is not None:
         out["distinct_component_counts"] = sorted({len(r["nodes"]) for r in res})
     return out

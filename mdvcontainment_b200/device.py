@@ -19,8 +19,54 @@ def _require_cuda():
         raise MdvcError("mdvcontainment_b200 needs a CUDA device (B200); there is no CPU fallback.")
 
 
+# torch.cuda.current_stream() resolves its device argument through is_available() / NVML / os.getenv on every call
+# (14 us each; thirteen calls per frame were a third of the host time of a 512^3 trajectory frame).  The helpers below
+# go straight to the C bindings the public functions wrap, and fall back to the public functions if a torch build
+# lacks them.
+_RAW = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+_CUR = getattr(torch._C, "_cuda_getCurrentStream", None)
+_SET = getattr(torch._C, "_cuda_setStream", None)
+
+
 def _stream():
+    """The current stream of the current device as a ctypes handle for the C-ABI."""
+    if _RAW is not None:
+        return ctypes.c_void_p(_RAW(torch._C._cuda_getDevice()))
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def current_stream(device_index: int | None = None) -> torch.cuda.Stream:
+    """torch.cuda.current_stream() without the device bookkeeping."""
+    if _CUR is None:
+        return torch.cuda.current_stream(device_index)
+    sd = _CUR(torch._C._cuda_getDevice() if device_index is None else device_index)
+    return torch.cuda.Stream(stream_id=sd[0], device_index=sd[1], device_type=sd[2])
+
+
+class on_stream:
+    """``with on_stream(s):`` = ``with torch.cuda.stream(s):`` for a stream of the current device, two C calls each way."""
+    __slots__ = ("s", "prev")
+
+    def __init__(self, s: torch.cuda.Stream):
+        self.s = s
+
+    def __enter__(self):
+        s = self.s
+        if _CUR is None or _SET is None:
+            self.prev = torch.cuda.current_stream(s.device_index)
+            torch.cuda.set_stream(s)
+        else:
+            self.prev = _CUR(s.device_index)
+            _SET(stream_id=s.stream_id, device_index=s.device_index, device_type=s.device_type)
+        return s
+
+    def __exit__(self, *exc):
+        p = self.prev
+        if isinstance(p, tuple):
+            _SET(stream_id=p[0], device_index=p[1], device_type=p[2])
+        else:
+            torch.cuda.set_stream(p)
+        return False
 
 
 def _ptr(t):

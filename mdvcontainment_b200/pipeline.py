@@ -109,6 +109,7 @@ class FramePipeline:
             raise NotImplementedError("FramePipeline handles periodic frames; slab frames go through "
                                       "VoxelContainment(slab=True)")
         self.device = torch.device(device)
+        self._dev_index = self.device.index if self.device.index is not None else torch.cuda.current_device()
         self.dimensions = np.asarray(dimensions, dtype=np.float32)
         self.resolution = resolution
         self.ops = ("de" if closing else "") + morph
@@ -211,7 +212,7 @@ class FramePipeline:
                                          self.bits_tmp.words.data_ptr() if self.bits_tmp is not None else None,
                                          X, Y, Z, self.bits_a.pitch, self.ops.encode(),
                                          ctypes.c_void_p(self.plan.row_counts_ptr()), ctypes.byref(counted),
-                                         ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+                                         dev._stream())
         torch.cuda.nvtx.range_pop()
         _lib.check(rc, "mdvc_morph_counted")
         self._rows_counted = bool(counted.value)
@@ -237,7 +238,7 @@ class FramePipeline:
         self._t0 = time.perf_counter()
         n_beads = int((host_positions if host_positions is not None else positions_dev).shape[0])
         self._ensure_bin_scratch(-(-n_beads // self.ATOM_QUANTUM) * self.ATOM_QUANTUM)    # before any graph capture
-        with torch.cuda.stream(self.stream):
+        with dev.on_stream(self.stream):
             if host_positions is not None:
                 # The copy goes FIRST, before this stream is made to wait for the previous frame's dense write: the
                 # position buffer was last read by that frame's binning, which is long finished (its stage-1 results
@@ -265,11 +266,11 @@ class FramePipeline:
         self.stream.wait_stream(self.stream_x)               # the previous frame's dense write still reads our buffers
         # whatever produced positions_dev on the caller's stream (a unit conversion, .cuda(non_blocking=True)) must
         # be complete before the binning reads it on this pipeline's side stream
-        self.stream.wait_stream(torch.cuda.current_stream(self.device))
+        self.stream.wait_stream(dev.current_stream(self._dev_index))
         if host_positions is None:
             _check_positions(positions_dev)
             positions_dev.record_stream(self.stream)         # the caching allocator must not recycle it under us
-        with torch.cuda.stream(self.stream):
+        with dev.on_stream(self.stream):
             if not self._run_graph(positions_dev):
                 self._bits = self.voxelize(positions_dev)
                 self._enqueue_stage1(self._bits, self._rows_counted)
@@ -324,15 +325,15 @@ class FramePipeline:
     def finish(self) -> FrameOutput:
         """Wait for the small results, run the host graph stage, upload the LUT, enqueue the dense write."""
         bits = self._bits
-        with torch.cuda.stream(self.stream):
+        with dev.on_stream(self.stream):
             out = self._finish(bits)
-        torch.cuda.current_stream().wait_stream(self.stream_x)   # the caller's stream sees the finished grids
+        dev.current_stream(self._dev_index).wait_stream(self.stream_x)   # the caller's stream sees the finished grids
         return out
 
     def analyse(self, bits: dev.BitGrid) -> FrameOutput:
         """label -> pairs -> (one sync) host graph -> LUT -> dense write, on the current stream."""
         self._t0 = time.perf_counter()
-        torch.cuda.current_stream(self.device).wait_stream(self.stream_x)   # a previous frame's dense write
+        dev.current_stream(self._dev_index).wait_stream(self.stream_x)   # a previous frame's dense write
         self._enqueue_stage1(bits)
         return self._finish(bits)
 
@@ -390,9 +391,10 @@ class FramePipeline:
             lut_dev = self.lut_dev[:nl]
         else:
             lut_dev = torch.from_numpy(lut).to(self.device)
-        wr = self.stream_x if torch.cuda.current_stream() == self.stream else torch.cuda.current_stream()
-        wr.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(wr):
+        cur = dev.current_stream(self._dev_index)
+        wr = self.stream_x if cur == self.stream else cur
+        wr.wait_stream(cur)
+        with dev.on_stream(wr):
             self.plan.set_lut(lut_dev)
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()

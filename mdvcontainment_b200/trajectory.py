@@ -166,11 +166,9 @@ class PipelinePool:
         return sum(p.memo_lookups for p in pipes), sum(p.memo_hits for p in pipes)
 
     def get(self, slot: int, dims: np.ndarray):
-        from .atomgroup_to_voxels import voxel_transform
         from .pipeline import FramePipeline
         resolution, closing, morph = self.args
-        _, nbox, _, _ = voxel_transform(dims, resolution)
-        shape = tuple(int(v) for v in np.diagonal(nbox))
+        shape = _shape_of(dims, resolution)
         pipes = self.by_shape.get(shape)
         if pipes is None:
             while len(self.by_shape) >= self.max_shapes:        # oldest shape goes (its frames are finished by now)
@@ -277,7 +275,17 @@ def run_trajectory(frames, dimensions, resolution, closing=True, morph="", n_fra
     return gather_results(local, n_frames, rank, world)
 
 
+_SHAPES = {}
+
+
 def _shape_of(dims, resolution):
-    from .atomgroup_to_voxels import voxel_transform
-    _, nbox, _, _ = voxel_transform(dims, resolution)
-    return tuple(int(v) for v in np.diagonal(nbox))
+    """Grid shape of a box (memoised: an NVT trajectory asks for the same box every frame)."""
+    key = (np.asarray(dims, dtype=np.float32).tobytes(), float(resolution))
+    shape = _SHAPES.get(key)
+    if shape is None:
+        from .atomgroup_to_voxels import voxel_transform
+        _, nbox, _, _ = voxel_transform(dims, resolution)
+        if len(_SHAPES) > 4096:
+            _SHAPES.clear()
+        shape = _SHAPES[key] = tuple(int(v) for v in np.diagonal(nbox))
+    return shape
