@@ -296,6 +296,9 @@ int mdvc_host_component_neighbours(long long n_nodes, const int32_t *comp_of_nod
                                    int32_t *out_cs_host, int32_t *out_cd_host, long long *n_out_host);
 int mdvc_host_adjacency(int32_t n_comps, const int32_t *eu_host, const int32_t *ev_host, long long n,
                         long long *offsets_out_host, int32_t *nbrs_out_host);
+/* the same for an edge sequence without repeats (no pair twice, in either direction): no de-duplication pass */
+int mdvc_host_adjacency_unique(int32_t n_comps, const int32_t *eu_host, const int32_t *ev_host, long long n,
+                               long long *offsets_out_host, int32_t *nbrs_out_host);
 
 /* Slab decomposition (no reference counterpart: the reference is one process on one grid): the global labels,
  * contacts, bridges and volumes from the per-slab results of n_slabs x-slabs, HOST function.  Slab g has local labels

@@ -91,6 +91,7 @@ SIGNATURES = {
     "mdvc_host_shift_graph_ranks": (_I, [_LL, _P, _P, _P, _LL, _P, _P, _P, _P]),
     "mdvc_host_component_neighbours": (_I, [_LL, _P, _I, _P, _P, _LL, _P, _P, _P]),
     "mdvc_host_adjacency": (_I, [_I, _P, _P, _LL, _P, _P]),
+    "mdvc_host_adjacency_unique": (_I, [_I, _P, _P, _LL, _P, _P]),
     "mdvc_host_merge_slabs": (_I, [_I] + [_P] * 18),
 }
 

@@ -255,6 +255,30 @@ extern "C" int mdvc_host_adjacency(int32_t n_comps, const int32_t *eu_host, cons
     return MDVC_OK;
 }
 
+// The same adjacency lists for an edge sequence the caller knows to be free of repeats (no pair twice, in either
+// direction): two counting passes, no hash table.  PeriodicSolution.contact_adjacency has such a sequence: its
+// (component, neighbour) list is grouped by component in ascending order and symmetric, so the first occurrence of
+// every undirected edge is the one with component < neighbour.
+extern "C" int mdvc_host_adjacency_unique(int32_t n_comps, const int32_t *eu_host, const int32_t *ev_host, long long n,
+                                          long long *offsets_out_host, int32_t *nbrs_out_host) {
+    if (n_comps < 0 || n < 0 || !offsets_out_host || (n > 0 && (!eu_host || !ev_host || !nbrs_out_host))) return MDVC_ERR_BADARG;
+    for (int32_t c = 0; c <= n_comps; ++c) offsets_out_host[c] = 0;
+    for (long long k = 0; k < n; ++k) {
+        const int32_t u = eu_host[k], v = ev_host[k];
+        if (u < 0 || v < 0 || u >= n_comps || v >= n_comps) return MDVC_ERR_BADARG;
+        ++offsets_out_host[(size_t)u + 1];
+        if (u != v) ++offsets_out_host[(size_t)v + 1];
+    }
+    for (int32_t c = 0; c < n_comps; ++c) offsets_out_host[(size_t)c + 1] += offsets_out_host[(size_t)c];
+    std::vector<long long> fill(offsets_out_host, offsets_out_host + n_comps);
+    for (long long k = 0; k < n; ++k) {
+        const int32_t u = eu_host[k], v = ev_host[k];
+        nbrs_out_host[fill[(size_t)u]++] = v;
+        if (u != v) nbrs_out_host[fill[(size_t)v]++] = u;
+    }
+    return MDVC_OK;
+}
+
 // ------------------------------------------------------------------------------------------
 // slab decomposition: the global problem from the slabs' results (mdvcontainment_b200/slab.py: merge_slabs)
 // ------------------------------------------------------------------------------------------

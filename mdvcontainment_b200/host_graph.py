@@ -75,15 +75,17 @@ def component_neighbours(comp_of_node, n_comps, src, dst):
     return cs[:n_out.value], cd[:n_out.value]
 
 
-def adjacency(n_comps, eu, ev):
-    """(offsets int64[n_comps + 1], neighbours int64) in networkx's adjacency order (``mdvc_host_adjacency``)."""
+def adjacency(n_comps, eu, ev, unique=False):
+    """(offsets int64[n_comps + 1], neighbours int64) in networkx's adjacency order (``mdvc_host_adjacency``;
+    ``unique``: the sequence holds no pair twice in either direction, ``mdvc_host_adjacency_unique``)."""
     lib = _lib.load()
     u = np.ascontiguousarray(eu, dtype=np.int32)
     v = np.ascontiguousarray(ev, dtype=np.int32)
     offsets = np.zeros(int(n_comps) + 1, dtype=np.int64)
     nbrs = np.empty(2 * len(u), dtype=np.int32)
-    rc = lib.mdvc_host_adjacency(int(n_comps), u.ctypes.data if u.size else None, v.ctypes.data if v.size else None, len(u),
-                                 offsets.ctypes.data, nbrs.ctypes.data if nbrs.size else None)
+    fn = lib.mdvc_host_adjacency_unique if unique else lib.mdvc_host_adjacency
+    rc = fn(int(n_comps), u.ctypes.data if u.size else None, v.ctypes.data if v.size else None, len(u),
+            offsets.ctypes.data, nbrs.ctypes.data if nbrs.size else None)
     _lib.check(rc, "mdvc_host_adjacency")
     return offsets, nbrs[: int(offsets[-1])].astype(np.int64)
 
@@ -211,10 +213,19 @@ def _view_order(n_all: int, subset_vals: np.ndarray) -> np.ndarray:
     return np.arange(n_sub)
 
 
-def _first_occurrence(keys: np.ndarray) -> np.ndarray:
-    """Indices of the first occurrence of every distinct key, ascending."""
-    if len(keys) == 0:
+def _first_occurrence(keys: np.ndarray, bound: int | None = None) -> np.ndarray:
+    """Indices of the first occurrence of every distinct key, ascending.  ``bound``: the keys are integers in
+    [0, bound) -- then two scatter passes replace the sort behind ``np.unique`` (a fancy assignment with repeated
+    indices keeps the value written last, so writing the positions in reverse leaves the first one)."""
+    n = len(keys)
+    if n == 0:
         return np.empty(0, dtype=np.int64)
+    if bound is not None and bound <= 8 * n + 4096:
+        first_pos = np.empty(int(bound), dtype=np.int64)
+        first_pos[keys[::-1]] = np.arange(n - 1, -1, -1, dtype=np.int64)
+        is_first = np.zeros(n, dtype=bool)
+        is_first[first_pos[keys]] = True
+        return np.flatnonzero(is_first)
     _, first = np.unique(keys, return_index=True)
     first.sort()
     return first
@@ -332,7 +343,7 @@ class PeriodicSolution:
             sub = np.flatnonzero(vals > 0) if positive else np.flatnonzero(vals < 0)
             order = sub[_view_order(L, vals[sub])]
             r = root[order]
-            comp_roots.append(r[_first_occurrence(r)])
+            comp_roots.append(r[_first_occurrence(r, L)])
         self.n_pos, self.n_neg = len(comp_roots[0]), len(comp_roots[1])
         K = self.n_pos + self.n_neg
         self.comp_root = np.concatenate(comp_roots).astype(np.int64)
@@ -411,7 +422,15 @@ class PeriodicSolution:
         appears where the first edge joining the two components was added, from either side."""
         if "adj" not in self._cache:
             cs, cd = self.contact_edges()
-            self._cache["adj"] = adjacency(len(self.comp_ids), cs, cd)
+            # the list is grouped by component in ascending order, holds no (component, neighbour) pair twice and no
+            # component as its own neighbour, and is symmetric (every label contact / bridge is a pair of directed
+            # edges): the first occurrence of an undirected edge is the one with component < neighbour
+            grouped = len(cs) < 2 or bool(np.all(cs[1:] >= cs[:-1]))
+            if grouped:
+                first = cs < cd
+                self._cache["adj"] = adjacency(len(self.comp_ids), cs[first], cd[first], unique=True)
+            else:
+                self._cache["adj"] = adjacency(len(self.comp_ids), cs, cd)
         return self._cache["adj"]
 
     def component_contact_graph(self):
@@ -490,7 +509,7 @@ class PeriodicSolution:
             dst = nbrs[pos]
             open_ = ~claimed[dst]
             src, dst = src[open_], dst[open_]
-            first = _first_occurrence(dst)                 # the first frontier component (in order) claims the child
+            first = _first_occurrence(dst, K)              # the first frontier component (in order) claims the child
             src, dst = src[first], dst[first]
             claimed[dst] = True
             eu.append(self.comp_ids[src]); ev.append(self.comp_ids[dst])
