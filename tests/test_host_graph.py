@@ -207,3 +207,34 @@ def test_many_label_case_matches_the_reference_recorded_graph_stage():
     assert sha(dag.nodes.astype(np.int64)) == rec["dag"]["sha_nodes"]
     assert sha(np.array(dag.edges(), dtype=np.int64).reshape(-1, 2)) == rec["dag"]["sha_edges"]
     assert dt < 0.1 * rec["reference_graph_stage_seconds"]
+
+
+def test_first_occurrence_scatter_path_equals_sort_path():
+    """_first_occurrence with a key bound (two scatter passes) against the np.unique form, incl. the sizes where it
+    falls back to the sort (bound far larger than the key count)."""
+    rng = np.random.default_rng(3)
+    for n, bound in ((1, 1), (7, 3), (1000, 40), (50000, 50000), (300, 10 ** 6), (0, 5)):
+        keys = rng.integers(0, bound, n)
+        assert np.array_equal(hg._first_occurrence(keys, bound), hg._first_occurrence(keys))
+
+
+def test_adjacency_unique_equals_hash_version_on_symmetric_grouped_lists():
+    """The component contact list is grouped by component, symmetric and free of self-pairs: keeping the rows with
+    component < neighbour and skipping the de-duplication (mdvc_host_adjacency_unique) must give the adjacency lists
+    the hash-table version builds from the whole list -- same neighbours in the same (networkx) order."""
+    rng = np.random.default_rng(11)
+    for n_comps, n_edges in ((2, 1), (5, 7), (60, 200), (3000, 9000)):
+        a = rng.integers(0, n_comps, n_edges)
+        b = rng.integers(0, n_comps, n_edges)
+        keep = a != b
+        pairs = np.unique(np.stack([np.minimum(a, b)[keep], np.maximum(a, b)[keep]], 1), axis=0)
+        und = pairs[rng.permutation(len(pairs))]                       # undirected edges in a random "insertion" order
+        src = np.concatenate([und[:, 0], und[:, 1]])
+        dst = np.concatenate([und[:, 1], und[:, 0]])
+        # grouped by component (ascending), each group's neighbours in some order of their own
+        order = np.lexsort((rng.random(len(src)), src))
+        cs, cd = src[order], dst[order]
+        off_h, nb_h = hg.adjacency(n_comps, cs, cd)
+        first = cs < cd
+        off_u, nb_u = hg.adjacency(n_comps, cs[first], cd[first], unique=True)
+        assert np.array_equal(off_h, off_u) and np.array_equal(nb_h, nb_u)
